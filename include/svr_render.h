@@ -1,0 +1,174 @@
+/*
+ * svr_render.h -- C ABI of libsvr_b200.so, the B200-native drop-in for the render hot path of
+ * SunVolumeRender (pathtracer.cu + raycasting.cu).
+ *
+ * Part 1 is the reference's own boundary: the seven unmangled symbols a host (gui/canvas.cpp or
+ * tools/svr_headless.cpp) links against.  The reference declares them `extern "C"` with C++
+ * reference parameters; a reference and a pointer are the same thing at the ABI level, so the
+ * prototypes below are binary-identical to pathtracer.h:17-24 and raycasting.h:8 and a host
+ * compiled against the reference headers links to this library unchanged.
+ *
+ * Part 2 is the headless extension the reference lacks: batched samples-per-pixel, float
+ * outputs for parity checks, sum-buffers for the multi-GPU split, resource builders that mirror
+ * the reference's loaders, synthetic volume generators and tap counters.
+ *
+ * All pointers named `img`, `hdrBuffer`, `sum`, `out`, `dev*` are DEVICE pointers unless the name
+ * says host.  No torch types, no C++ types.
+ */
+#ifndef SVR_RENDER_H
+#define SVR_RENDER_H
+
+#include "svr_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1 -- the reference boundary (error convention = utils/helper_cuda.h:967-981: print
+ * "CUDA error at file:line ...", cudaDeviceReset(), exit(EXIT_FAILURE); no return codes).
+ * ------------------------------------------------------------------------------------------ */
+
+/* pathtracer.h:17 / pathtracer.cu:292-304.  One call = one sample per pixel with seed stream
+ * `frameNo`; frameNo == 0 clears hdrBuffer; hdrBuffer holds the running mean afterwards and img
+ * the tone-mapped image.  Asynchronous on the library stream (svr_set_stream). */
+void render_pathtracer(svr_u8vec4* img, const svr_render_params* renderParams);
+
+/* pathtracer.h:20-24 / pathtracer.cu:34-68.  Copy the POD into library-owned device state.
+ * setup_volume / setup_transferfunction also (re)build the macrocell majorant grid. */
+void setup_volume(const svr_volume* vol);
+void setup_transferfunction(const svr_transfer_function* tf);
+void setup_camera(const svr_camera* cam);
+void setup_env_lights(const svr_env_light* light);
+void setup_area_lights(svr_area_light* lights, uint32_t n); /* n is clamped to 8 */
+
+/* raycasting.h:8 / raycasting.cu:69-75.  Deterministic front-to-back compositing; takes its
+ * scene by argument, not from setup_*.  stepSize = 0.5*|spacing| in the reference caller
+ * (core/VolumeReader.cpp:198-201, gui/canvas.cpp:92); the march step is stepSize*0.5. */
+void render_raycasting(svr_u8vec4* img, svr_volume* volume, svr_transfer_function* transferFunction,
+                       svr_camera* camera, float stepSize);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 2 -- headless extension.  Functions returning int: 0 = ok, non-zero = error
+ * (svr_last_error() gives the text).  They never call exit().
+ * ------------------------------------------------------------------------------------------ */
+
+#define SVR_VERSION 100
+
+int svr_version(void);
+const char* svr_last_error(void);
+
+/* Stream all launches and copies are issued on (a cudaStream_t; NULL = legacy default stream). */
+int svr_set_stream(void* cuda_stream);
+/* Bind the calling thread to a device and (re)initialise library state there. */
+int svr_set_device(int device);
+
+enum svr_option {
+    /* path tracer estimator:
+     *   0 = reference-compatible: global majorant, XORWOW stream seeded wangHash(frameNo)+pixel
+     *       in the reference's draw order (path-exact twin of kernel_pathtracer);
+     *   1 = global majorant, Philox4x32-10 counter RNG keyed (seed, pixel, sample);
+     *   2 = local majorants (macrocell DDA) + Philox (default, fastest; same expectation). */
+    SVR_OPT_PT_MODE = 0,
+    /* shadow-ray estimator: 0 = binary delta tracking (transmittance.h:10-17), 1 = ratio tracking */
+    SVR_OPT_SHADOW_ESTIMATOR = 1,
+    /* 0 = escaped paths add nothing (pathtracer.cu:233 is commented out); 1 = add envLight */
+    SVR_OPT_ENV_ENABLED = 2,
+    /* macrocell edge in voxels (power of two, 4..32) */
+    SVR_OPT_MACROCELL_SIZE = 3,
+    /* ray caster empty-space skipping through the macrocell grid: 0 off, 1 on (default) */
+    SVR_OPT_RC_SKIP = 4,
+    /* Philox key */
+    SVR_OPT_SEED = 5,
+    /* 1 = kernels also count taps / lookups / steps (slower; used for bytes_algo) */
+    SVR_OPT_COUNTERS = 6,
+    /* threads per block of the path tracer / ray caster (tuning) */
+    SVR_OPT_PT_BLOCK = 7,
+    SVR_OPT_RC_BLOCK = 8,
+    SVR_OPT_COUNT_
+};
+int svr_set_option(int key, int value);
+int svr_get_option(int key);
+
+/* Equivalent to `spp` consecutive render_pathtracer calls with frameNo, frameNo+1, ... but in one
+ * launch: samples accumulate in registers, hdrBuffer is read and written once, the tone map
+ * runs once.  frameNo == 0 clears first.  img may be NULL (no tone map). */
+int svr_render_pathtracer_spp(svr_u8vec4* img, const svr_render_params* renderParams, uint32_t spp);
+
+/* Multi-GPU building blocks.  `sum` is imageW*imageH float4: rgb = sum of
+ * radiance samples, w = number of samples.  Samples [firstSample, firstSample+nSamples) are
+ * rendered; clear != 0 zeroes `sum` first.  After an NCCL sum-reduce of the per-GPU buffers the
+ * root calls svr_pathtracer_resolve: hdr = rgb / w (optional packed-vec3 output) and the
+ * tone-mapped image (tonemapping.h:13-27), fused in one pass. */
+int svr_pathtracer_accumulate(svr_vec4* sum, uint32_t traceDepth, uint32_t firstSample, uint32_t nSamples, int clear);
+int svr_pathtracer_resolve(svr_u8vec4* img, svr_vec3* hdrOut, const svr_vec4* sum);
+
+/* Ray caster variants: float RGBA before quantisation (parity is checked on these), and a row
+ * range [y0, y1) for the image-tile split across GPUs.  out/img are full-frame buffers. */
+int svr_render_raycasting_f32(svr_vec4* out, const svr_volume* volume, const svr_transfer_function* tf,
+                              const svr_camera* camera, float stepSize);
+int svr_render_raycasting_rows(svr_u8vec4* img, svr_vec4* outOrNull, const svr_volume* volume,
+                               const svr_transfer_function* tf, const svr_camera* camera, float stepSize,
+                               uint32_t y0, uint32_t y1);
+
+/* ---- resource builders (the input contract of the path) ---- */
+enum svr_voxel_format { SVR_VOXEL_U8 = 0, SVR_VOXEL_U16 = 1, SVR_VOXEL_F16 = 2, SVR_VOXEL_F32 = 3 };
+
+/* Mirrors VolumeReader::CreateTextures + CreateDeviceVolume (core/VolumeReader.cpp:138-185):
+ * 3-D cudaArray, border addressing, linear filter, normalised-float reads (element reads for
+ * f16/f32), normalised coordinates; bbox = +-0.5*dim*spacing; invMaxMagnitude = 1/maxGradMag
+ * (maxGradMag <= 0: computed on the device by central differences on the raw values, f16/f32
+ * scaled by 65535).  Clip planes (-1,1), densityScale 1, gradientFactor 0.5 (gui/canvas.cpp:19,31-32).
+ * `data` is x-fastest; data_on_device selects the memcpy kind. */
+int svr_volume_create(svr_volume* out, const void* data, int data_on_device, int format,
+                      uint32_t nx, uint32_t ny, uint32_t nz, float sx, float sy, float sz, float maxGradMag);
+int svr_volume_destroy(svr_volume* vol);
+/* Drop cached macrocell data (keyed on the cudaArray handle); call after re-uploading voxels
+ * into an existing array. */
+int svr_volume_invalidate_cache(void);
+
+/* Mirrors TransferFunction::TransferFunction (gui/transferfunction.cpp:17-44): 1024 float4
+ * (r,g,b,opacity) -> 1-D cudaArray texture, linear, clamp, normalised; maxOpacity = max opacity. */
+int svr_tf_create(svr_transfer_function* out, const float* host_rgba, uint32_t n);
+int svr_tf_destroy(svr_transfer_function* tf);
+
+/* Mirrors Lights::SetEnvironmentLight (core/lights/lights.cpp:31-75): w x h float4 lat-long map. */
+int svr_env_create(svr_env_light* out, const float* host_rgba, uint32_t w, uint32_t h);
+int svr_env_destroy(svr_env_light* env);
+
+/* ---- synthetic volumes, written x-fastest into device memory ---- */
+enum svr_volume_kind { SVR_GEN_SPHERE = 0, SVR_GEN_CT = 1, SVR_GEN_CLOUD = 2 };
+int svr_generate_volume(void* dev_out, int kind, int format, uint32_t n, uint32_t seed);
+/* max over voxels of the central-difference gradient magnitude (VolumeReader.cpp:70-76 semantics) */
+int svr_max_gradient_magnitude(const void* dev_data, int format, uint32_t nx, uint32_t ny, uint32_t nz,
+                               float sx, float sy, float sz, float* host_out);
+
+/* ---- counters (valid while SVR_OPT_COUNTERS = 1) ---- */
+enum svr_counter {
+    SVR_CNT_TRACK_TAPS = 0,   /* volume taps in primary/secondary tracking loops */
+    SVR_CNT_SHADOW_TAPS = 1,  /* volume taps in shadow-ray tracking */
+    SVR_CNT_SHADE_TAPS = 2,   /* volume taps at scatter events / ray-cast steps (1 + 6 gradient) */
+    SVR_CNT_TF_LOOKUPS = 3,   /* transfer-function lookups */
+    SVR_CNT_SCATTERS = 4,     /* scatter events */
+    SVR_CNT_PATHS = 5,        /* paths (pixel samples) or rays */
+    SVR_CNT_CELLS = 6,        /* macrocells visited */
+    SVR_CNT_STEPS = 7,        /* ray-cast steps executed (incl. skipped: see SKIPPED) */
+    SVR_CNT_SKIPPED = 8,      /* ray-cast steps skipped as provably empty */
+    SVR_CNT_COUNT_ = 16
+};
+int svr_counters_reset(void);
+int svr_counters_read(uint64_t* host_out, uint32_t n);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t svr_launch_count(void);
+
+/* Gather-roofline microbenchmarks: `taps_per_thread` dependent-free tex3D taps per thread over
+ * the bound volume, coherent (ray-like) or random.  Returns taps issued via *host_taps. */
+int svr_microbench_taps(const svr_volume* vol, int random, uint32_t threads, uint32_t taps_per_thread,
+                        float* dev_sink, uint64_t* host_taps);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SVR_RENDER_H */

@@ -1,0 +1,822 @@
+/*
+ * TEST INFRASTRUCTURE -- not product code.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library; the product path
+ * (sunvolumerender_b200/) never does and has no CPU fallback.
+ *
+ * CPU oracle for the render hot path of SunVolumeRender.  The reference has NO host render path
+ * (texture fetches compile to `return 0.f` on the host, cuda_volume.h:94-99; the RNG is device
+ * cuRAND), so this file restates the device algorithm on the host:
+ *   - a software sampler for CUDA linear texture filtering (normalised coordinates, x*N-0.5
+ *     addressing, 1.8 fixed-point weights, border = 0 for the volume, clamp for the TF);
+ *   - XORWOW with cuRAND's seeding for (seed, subsequence 0, offset 0);
+ *   - every function of SURVEY.md section 8a, each citing the reference file:line it follows.
+ *
+ * PINNING: the reference has no tests, golden vectors or fixtures of any kind.
+ * This oracle is pinned against outputs of the reference's own unmodified CUDA kernels
+ * (oracle/_ref, built by oracle/build_ref.sh) captured on a B200 by tests/golden/make_golden.py and
+ * committed under tests/golden/; tests/test_oracle_golden.py checks it against them on the CPU.
+ *
+ * Arithmetic class: the reference is built -use_fast_math (CMakeLists.txt:9); this restatement
+ * uses IEEE libm, so it agrees with the GPU to fast-math rounding, not bit for bit.  Stray FP64 in
+ * the reference (2.f*M_PI*u etc.) is kept as FP64 here.
+ */
+#include "svr_oracle.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct V3 {
+    float x, y, z;
+};
+inline V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 mk(const svr_vec3& v) { return V3{v.x, v.y, v.z}; }
+inline V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+inline V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+inline V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+inline V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+inline V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+inline V3 operator/(float s, V3 a) { return mk(s / a.x, s / a.y, s / a.z); }
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return mk(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+inline V3 normalize(V3 a) { return a * (1.f / sqrtf(dot(a, a))); }
+inline V3 reflect(V3 i, V3 n) { return i - n * (dot(n, i) * 2.f); }
+inline float max3(V3 a) { return fmaxf(a.x, fmaxf(a.y, a.z)); }
+
+struct V4 {
+    float x, y, z, w;
+};
+
+/* ---------------------------------------------------------------- RNG: XORWOW as cuRAND seeds it */
+/* curand_init(seed, 0, 0): seed halves salted and multiplied into the Marsaglia xorwow state, no
+ * skip-ahead for subsequence 0 / offset 0.  curand(): xorwow step + Weyl counter 362437.
+ * curand_uniform(): x * 2^-32 + 2^-33, i.e. (0, 1].  Used at pathtracer.cu:205-206. */
+struct Xorwow {
+    uint32_t v[5];
+    uint32_t d;
+    explicit Xorwow(uint64_t seed)
+    {
+        uint32_t s0 = (uint32_t)seed ^ 0xaad26b49u;
+        uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+        uint32_t t0 = 1099087573u * s0;
+        uint32_t t1 = 2591861531u * s1;
+        d = 6615241u + t1 + t0;
+        v[0] = 123456789u + t0;
+        v[1] = 362436069u ^ t0;
+        v[2] = 521288629u + t1;
+        v[3] = 88675123u ^ t1;
+        v[4] = 5783321u + t0;
+    }
+    uint32_t next()
+    {
+        uint32_t t = v[0] ^ (v[0] >> 2);
+        v[0] = v[1];
+        v[1] = v[2];
+        v[2] = v[3];
+        v[3] = v[4];
+        v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+        d += 362437u;
+        return v[4] + d;
+    }
+    float uniform() { return (float)next() * 2.3283064e-10f + (2.3283064e-10f / 2.0f); }
+};
+
+/* pathtracer.cu:70-79 */
+inline uint32_t wang_hash(uint32_t a)
+{
+    a = (a ^ 61u) ^ (a >> 16);
+    a = a + (a << 3);
+    a = a ^ (a >> 4);
+    a = a * 0x27d4eb2du;
+    a = a ^ (a >> 15);
+    return a;
+}
+
+/* ---------------------------------------------------------------- software texture units */
+inline float half_to_float(uint16_t h)
+{
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1fu;
+    uint32_t man = h & 0x3ffu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else {
+            int e = -1;
+            do {
+                man <<= 1;
+                ++e;
+            } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + 112u) << 23) | (man << 13);
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+struct Ctx {
+    const svr_oracle_scene* s;
+    uint64_t cnt[SVR_ORACLE_CNT_COUNT];
+};
+
+/* One texel, border addressing (VolumeReader.cpp:164-166) and cudaReadModeNormalizedFloat (:168). */
+inline float texel3d(const svr_oracle_scene* s, int i, int j, int k)
+{
+    if (i < 0 || j < 0 || k < 0 || i >= (int)s->nx || j >= (int)s->ny || k >= (int)s->nz) return 0.f;
+    size_t idx = ((size_t)k * s->ny + (size_t)j) * s->nx + (size_t)i;
+    switch (s->format) {
+        case 0: return (float)((const uint8_t*)s->voxels)[idx] * (1.f / 255.f);
+        case 1: return (float)((const uint16_t*)s->voxels)[idx] * (1.f / 65535.f);
+        case 2: return half_to_float(((const uint16_t*)s->voxels)[idx]);
+        default: return ((const float*)s->voxels)[idx];
+    }
+}
+
+/* CUDA linear filtering weight: frac stored in 9-bit fixed point with 8 fractional bits. */
+inline float quant_weight(float frac, int mode)
+{
+    if (mode == 0) return floorf(frac * 256.f + 0.5f) * (1.f / 256.f);
+    if (mode == 1) return floorf(frac * 256.f) * (1.f / 256.f);
+    return frac;
+}
+
+/* tex3D<float>(tex, u, v, w): linear, normalised coordinates (VolumeReader.cpp:167-169). */
+inline float tex3d(const svr_oracle_scene* s, float u, float v, float w)
+{
+    float xb = u * (float)s->nx - 0.5f, yb = v * (float)s->ny - 0.5f, zb = w * (float)s->nz - 0.5f;
+    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    /* reject coordinates far outside before converting to int */
+    if (!(fx > -4.f && fy > -4.f && fz > -4.f && fx < (float)s->nx + 4.f && fy < (float)s->ny + 4.f &&
+          fz < (float)s->nz + 4.f))
+        return 0.f;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float a = quant_weight(xb - fx, s->filterMode), b = quant_weight(yb - fy, s->filterMode),
+          c = quant_weight(zb - fz, s->filterMode);
+    float t000 = texel3d(s, i, j, k), t100 = texel3d(s, i + 1, j, k);
+    float t010 = texel3d(s, i, j + 1, k), t110 = texel3d(s, i + 1, j + 1, k);
+    float t001 = texel3d(s, i, j, k + 1), t101 = texel3d(s, i + 1, j, k + 1);
+    float t011 = texel3d(s, i, j + 1, k + 1), t111 = texel3d(s, i + 1, j + 1, k + 1);
+    return (1.f - a) * (1.f - b) * (1.f - c) * t000 + a * (1.f - b) * (1.f - c) * t100 +
+           (1.f - a) * b * (1.f - c) * t010 + a * b * (1.f - c) * t110 + (1.f - a) * (1.f - b) * c * t001 +
+           a * (1.f - b) * c * t101 + (1.f - a) * b * c * t011 + a * b * c * t111;
+}
+
+/* tex1D<float4>(tex, x): linear, clamp, normalised (transferfunction.cpp:38-42);
+ * cudaTransferFunction::operator() (cuda_transfer_function.h:22-30). */
+inline V4 tf_lookup(const svr_oracle_scene* s, float x)
+{
+    int n = (int)s->tfSize;
+    float xb = x * (float)n - 0.5f;
+    if (!(xb == xb)) xb = 0.f;
+    xb = fminf(fmaxf(xb, -2.f), (float)n + 2.f);
+    float fx = floorf(xb);
+    float a = quant_weight(xb - fx, s->filterMode);
+    int i0 = (int)fx, i1 = i0 + 1;
+    i0 = i0 < 0 ? 0 : (i0 > n - 1 ? n - 1 : i0);
+    i1 = i1 < 0 ? 0 : (i1 > n - 1 ? n - 1 : i1);
+    const float* p0 = s->tfTable + 4 * (size_t)i0;
+    const float* p1 = s->tfTable + 4 * (size_t)i1;
+    V4 r;
+    r.x = (1.f - a) * p0[0] + a * p1[0];
+    r.y = (1.f - a) * p0[1] + a * p1[1];
+    r.z = (1.f - a) * p0[2] + a * p1[2];
+    r.w = (1.f - a) * p0[3] + a * p1[3];
+    return r;
+}
+
+/* ---------------------------------------------------------------- volume (cuda_volume.h) */
+/* cuda_volume.h:87-100: world -> normalised tex coord, fetch, times densityScale */
+inline float vol_intensity(const svr_oracle_scene* s, V3 p)
+{
+    const svr_volume& v = s->volume;
+    V3 tc = (p - mk(v.bbox.vmin)) * mk(v.bbox.invSize);
+    return tex3d(s, tc.x, tc.y, tc.z) * v.densityScale;
+}
+
+/* cuda_volume.h:54-61 */
+inline V3 vol_gradient(const svr_oracle_scene* s, V3 p)
+{
+    const svr_volume& v = s->volume;
+    float xd = vol_intensity(s, p + mk(v.spacing.x, 0.f, 0.f)) - vol_intensity(s, p - mk(v.spacing.x, 0.f, 0.f));
+    float yd = vol_intensity(s, p + mk(0.f, v.spacing.y, 0.f)) - vol_intensity(s, p - mk(0.f, v.spacing.y, 0.f));
+    float zd = vol_intensity(s, p + mk(0.f, 0.f, v.spacing.z)) - vol_intensity(s, p - mk(0.f, 0.f, v.spacing.z));
+    return mk(xd, yd, zd) * 0.5f * mk(v.invSpacing);
+}
+
+struct Ray {
+    V3 orig, dir;
+    float tMin, tMax; /* mutable in the reference (cuda_ray.h:40-41) */
+};
+
+/* cuda_bbox.h:33-54 via cuda_volume.h:49-52.  GLM min/max are `x < y ? x : y` / `x > y ? x : y`. */
+inline bool vol_intersect(const svr_oracle_scene* s, const Ray& ray, float* tNear, float* tFar)
+{
+    const svr_volume& v = s->volume;
+    V3 invDir = 1.f / ray.dir;
+    V3 cmin = mk(v.bbox.vmin) * mk(-v.x_clip.x, -v.y_clip.x, -v.z_clip.x);
+    V3 cmax = mk(v.bbox.vmax) * mk(v.x_clip.y, v.y_clip.y, v.z_clip.y);
+    V3 tbot = invDir * (cmin - ray.orig);
+    V3 ttop = invDir * (cmax - ray.orig);
+    V3 tmin = mk(tbot.x < ttop.x ? tbot.x : ttop.x, tbot.y < ttop.y ? tbot.y : ttop.y, tbot.z < ttop.z ? tbot.z : ttop.z);
+    V3 tmax = mk(tbot.x > ttop.x ? tbot.x : ttop.x, tbot.y > ttop.y ? tbot.y : ttop.y, tbot.z > ttop.z ? tbot.z : ttop.z);
+    float largest_tmin = fmaxf(tmin.x, fmaxf(tmin.y, tmin.z));
+    float smallest_tmax = fminf(tmax.x, fminf(tmax.y, tmax.z));
+    *tNear = largest_tmin;
+    *tFar = smallest_tmax;
+    return smallest_tmax > largest_tmin;
+}
+
+/* ---------------------------------------------------------------- cuda_onb.h:26-40 */
+struct Onb {
+    V3 u, v, w;
+    explicit Onb(V3 w_)
+    {
+        w = w_;
+        if (fabsf(w.x) > fabsf(w.y)) {
+            float inv = 1.f / sqrtf(w.x * w.x + w.z * w.z);
+            v = mk(-w.z * inv, 0.f, w.x * inv);
+        } else {
+            float inv = 1.f / sqrtf(w.y * w.y + w.z * w.z);
+            v = mk(0.f, w.z * inv, -w.y * inv);
+        }
+        u = cross(v, w);
+    }
+};
+
+/* ---------------------------------------------------------------- sampling.h */
+/* sampling.h:26-32 (2*M_PI*u is evaluated in double in the reference) */
+inline void uniform_sample_disk(Xorwow& rng, float r, float* ox, float* oy)
+{
+    r *= sqrtf(rng.uniform());
+    float theta = (float)(2.0 * M_PI * (double)rng.uniform());
+    *ox = cosf(theta) * r;
+    *oy = sinf(theta) * r;
+}
+
+/* sampling.h:47-56 */
+inline V3 cosine_weighted_sample_hemisphere(Xorwow& rng, V3 n)
+{
+    Onb onb(n);
+    float phi = (float)(2.0 * M_PI * (double)rng.uniform());
+    float sinTheta = sqrtf(rng.uniform());
+    float cosTheta = sqrtf(fmaxf(0.f, 1.f - sinTheta * sinTheta));
+    return normalize(sinTheta * cosf(phi) * onb.u + sinTheta * sinf(phi) * onb.v + cosTheta * onb.w);
+}
+
+/* ---------------------------------------------------------------- bsdf/ */
+/* fresnel.h:10-15 */
+inline float schlick_fresnel(float ni, float no, float cosin)
+{
+    float R0 = (ni - no) * (ni - no) / ((ni + no) * (ni + no));
+    float c = 1.f - cosin;
+    return R0 + (1.f - R0) * c * c * c * c * c;
+}
+
+/* henyey_greenstein.h:15-22 with g == 0 (PHASE_FUNC_G, pathtracer.cu:29): M_1_PI * 0.25f in double */
+inline float hg_phase_f() { return (float)(M_1_PI * (double)0.25f); }
+
+/* henyey_greenstein.h:29-51 with g == 0 */
+inline void hg_phase_sample_f(V3 wo, V3* wi, float* pdf, Xorwow& rng)
+{
+    float phi = (float)(2.0 * M_PI * (double)rng.uniform());
+    float cosTheta = 1.f - 2.f * rng.uniform();
+    float sinTheta = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));
+    Onb onb(wo);
+    *wi = normalize(sinTheta * cosf(phi) * onb.u + sinTheta * sinf(phi) * onb.v + cosTheta * onb.w);
+    *pdf = hg_phase_f();
+}
+
+/* lambert.h:15-24 */
+inline float lambert_brdf_f() { return 1.f / (float)M_PI; }
+inline void lambert_brdf_sample_f(V3 normal, V3* wi, float* pdf, Xorwow& rng)
+{
+    *wi = cosine_weighted_sample_hemisphere(rng, normal);
+    *pdf = fabsf(dot(*wi, normal)) / (float)M_PI;
+}
+
+/* microfacet.h:18-25 */
+inline float beckmann_distribution(V3 normal, V3 wh, float alpha)
+{
+    float c2 = dot(normal, wh);
+    c2 *= c2;
+    return expf((c2 - 1.f) / (alpha * alpha * c2)) / ((float)M_PI * alpha * alpha * c2 * c2);
+}
+
+/* microfacet.h:42-50 */
+inline float geometry_cook_torrance(V3 wi, V3 wo, V3 normal, V3 wh)
+{
+    float cosO = dot(wo, wh);
+    float cosTerm = dot(normal, wh);
+    float g1 = 2.f * cosTerm * dot(normal, wo) / cosO;
+    float g2 = 2.f * cosTerm * dot(normal, wi) / cosO;
+    return fminf(1.f, fminf(g1, g2));
+}
+
+/* microfacet.h:52-68 (DISTRIBUTION_BECKMANN, :16) */
+inline float microfacet_brdf_f(V3 wi, V3 wo, V3 normal, float ior, float alpha)
+{
+    if (dot(wi, normal) * dot(wo, normal) < 0.f) return 0.f;
+    V3 wh = normalize(wi + wo);
+    float F = schlick_fresnel(1.f, ior, fabsf(dot(wh, wo)));
+    float G = geometry_cook_torrance(wi, wo, normal, wh);
+    float D = beckmann_distribution(normal, wh, alpha);
+    return F * G * D / (4.f * fabsf(dot(normal, wi)) * fabsf(dot(normal, wo)));
+}
+
+/* microfacet.h:70-79 */
+inline V3 sample_beckmann(V3 normal, float alpha, Xorwow& rng)
+{
+    Onb onb(normal);
+    float phi = 2.f * (float)M_PI * rng.uniform();
+    float cosTheta = 1.f / (1.f - alpha * alpha * logf(1.f - rng.uniform()));
+    float sinTheta = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));
+    return normalize(sinTheta * cosf(phi) * onb.u + sinTheta * sinf(phi) * onb.v + cosTheta * onb.w);
+}
+
+/* microfacet.h:95-111 */
+inline void microfacet_brdf_sample_f(V3 wo, V3 normal, float alpha, V3* wi, float* pdf, Xorwow& rng)
+{
+    V3 wh = sample_beckmann(normal, alpha, rng);
+    wh = dot(wo, wh) >= 0.f ? wh : -wh;
+    *wi = reflect(-wo, wh);
+    *pdf = beckmann_distribution(normal, wh, alpha) / (4.f * fabsf(dot(wo, wh)));
+}
+
+/* ---------------------------------------------------------------- lights */
+/* cuda_disk.h:53-56 (double product) */
+inline float disk_area(const svr_disk& d) { return (float)(M_PI * (double)d.radius * (double)d.radius); }
+
+/* cuda_arealight.h:57 */
+inline V3 light_radiance(const svr_area_light& l)
+{
+    return 500.f * mk(l.color) * l.intensity * (float)M_1_PI / disk_area(l.disk);
+}
+
+/* cuda_disk.h:32-51 */
+inline bool disk_intersect(const svr_disk& d, const Ray& ray, float* t)
+{
+    float denom = dot(mk(d.normal), ray.dir);
+    if ((double)fabsf(denom) > 1e-6) {
+        V3 co = mk(d.center) - ray.orig;
+        *t = dot(co, mk(d.normal)) / denom;
+        if (*t >= 0) {
+            V3 p = ray.orig + *t * ray.dir;
+            V3 c2 = p - mk(d.center);
+            return sqrtf(dot(c2, c2)) <= d.radius;
+        }
+        return false;
+    }
+    return false;
+}
+
+struct LightSample {
+    float t;
+    V3 normal, radiance;
+};
+
+/* light_sample.h:23-49 */
+inline bool get_nearest_light_sample(const Ray& ray, const svr_area_light* lights, uint32_t n, LightSample* ls)
+{
+    float tNear = FLT_MAX, t = FLT_MAX;
+    int id = -1;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (disk_intersect(lights[i].disk, ray, &t) && (t < tNear)) {
+            tNear = t;
+            id = (int)i;
+        }
+    }
+    if (id != -1) {
+        ls->t = tNear;
+        ls->normal = mk(lights[id].disk.normal);
+        ls->radiance = light_radiance(lights[id]);
+        return true;
+    }
+    ls->t = -FLT_MAX;
+    return false;
+}
+
+/* light_sample.h:51-68 */
+inline V3 sample_light(const svr_area_light& light, V3 pos, Xorwow& rng, V3* lightPos, V3* wi, float* pdf)
+{
+    float lx, ly;
+    uniform_sample_disk(rng, light.disk.radius, &lx, &ly);
+    V3 ln = mk(light.disk.normal);
+    Onb onb(ln);
+    *lightPos = mk(light.disk.center) + onb.u * lx + onb.v * ly;
+    V3 sv = *lightPos - pos;
+    *wi = normalize(sv);
+    float cosTerm = dot(ln, -(*wi));
+    *pdf = dot(sv, sv) / (fabsf(cosTerm) * disk_area(light.disk));
+    return cosTerm > 0.f ? light_radiance(light) : mk(0.f, 0.f, 0.f);
+}
+
+/* cuda_environment_light.h:58-72, constant-radiance branch (tex == 0) */
+inline V3 env_radiance(const svr_oracle_scene* s) { return mk(s->env.defaultRadiance) * s->env.intensity; }
+
+/* ---------------------------------------------------------------- tracking */
+/* woodcock_tracking.h:20-51 (BASE_SAMPLE_STEP_SIZE 1) */
+inline float sample_distance(Ctx& c, Ray& ray, Xorwow& rng, int cntSlot)
+{
+    const svr_oracle_scene* s = c.s;
+    float tNear, tFar;
+    if (vol_intersect(s, ray, &tNear, &tFar)) {
+        ray.tMin = tNear < 0.f ? (float)1e-6 : tNear;
+        ray.tMax = tFar;
+        float t = ray.tMin;
+        float sigmaMax = s->tf.maxOpacity;
+        float invSigmaMax = 1.f / sigmaMax;
+        float invSigmaMaxSampleInterval = 1.f / (sigmaMax * 1.f);
+        while (true) {
+            t += -logf(1.f - rng.uniform()) * invSigmaMaxSampleInterval;
+            if (t > ray.tMax) return -FLT_MAX;
+            V3 p = ray.orig + t * ray.dir;
+            float intensity = vol_intensity(s, p);
+            V4 co = tf_lookup(s, intensity);
+            c.cnt[cntSlot]++;
+            c.cnt[SVR_ORACLE_CNT_TF_LOOKUPS]++;
+            float sigma_t = co.w;
+            if (rng.uniform() < sigma_t * invSigmaMax || t > ray.tMax) break;
+        }
+        return t;
+    }
+    return -FLT_MAX;
+}
+
+/* transmittance.h:10-17 */
+inline float transmittance(Ctx& c, V3 start, V3 end, Xorwow& rng)
+{
+    Ray ray{start, normalize(end - start), (float)1e-6, FLT_MAX};
+    float t = sample_distance(c, ray, rng, SVR_ORACLE_CNT_SHADOW_TAPS);
+    bool flag = (t > ray.tMin) && (t < ray.tMax);
+    return flag ? 0.f : 1.f;
+}
+
+/* ---------------------------------------------------------------- pathtracer.cu */
+#define SVR_IOR (2.5f)    /* pathtracer.cu:30 */
+#define SVR_ALPHA (0.15f) /* pathtracer.cu:31 */
+
+struct VolumeSample { /* cuda_volume.h:124-132 */
+    V3 ptInWorld, wo;
+    float intensity;
+    V3 gradient;
+    float gradientMagnitude;
+    V4 color_opacity;
+};
+
+enum ShadingType { ISOTROPIC, BRDF };
+
+/* pathtracer.cu:106-131 */
+inline V3 bsdf(const VolumeSample& vs, V3 wi, ShadingType st)
+{
+    V3 diffuseColor = mk(vs.color_opacity.x, vs.color_opacity.y, vs.color_opacity.z);
+    if (st == ISOTROPIC) return diffuseColor * hg_phase_f();
+    V3 normal = normalize(vs.gradient);
+    normal = dot(vs.wo, normal) < 0.f ? -normal : normal;
+    float cosTerm = fmaxf(0.f, dot(wi, normal));
+    float ks = schlick_fresnel(1.0f, SVR_IOR, cosTerm);
+    float kd = 1.f - ks;
+    V3 diffuse = diffuseColor * lambert_brdf_f();
+    V3 specular = mk(1.f, 1.f, 1.f) * microfacet_brdf_f(wi, vs.wo, normal, SVR_IOR, SVR_ALPHA);
+    return (kd * diffuse + ks * specular) * cosTerm;
+}
+
+/* pathtracer.cu:133-169 */
+inline V3 sample_bsdf(const VolumeSample& vs, V3* wi, float* pdf, Xorwow& rng, ShadingType st)
+{
+    V3 color = mk(vs.color_opacity.x, vs.color_opacity.y, vs.color_opacity.z);
+    if (st == ISOTROPIC) {
+        hg_phase_sample_f(vs.wo, wi, pdf, rng);
+        return color * hg_phase_f();
+    }
+    V3 normal = normalize(vs.gradient);
+    float cosTerm = dot(vs.wo, normal);
+    if (cosTerm < 0.f) {
+        cosTerm = -cosTerm;
+        normal = -normal;
+    }
+    float ks = schlick_fresnel(1.f, SVR_IOR, cosTerm);
+    float kd = 1.f - ks;
+    float p = 0.25f + 0.5f * ks;
+    if (rng.uniform() < p) {
+        microfacet_brdf_sample_f(vs.wo, normal, SVR_ALPHA, wi, pdf, rng);
+        float f = microfacet_brdf_f(*wi, vs.wo, normal, SVR_IOR, SVR_ALPHA);
+        return mk(1.f, 1.f, 1.f) * f * ks / p;
+    }
+    lambert_brdf_sample_f(normal, wi, pdf, rng);
+    float f = lambert_brdf_f();
+    return color * f * kd / (1.f - p);
+}
+
+/* pathtracer.cu:171-198 */
+inline V3 estimate_direct_light(Ctx& c, const VolumeSample& vs, Xorwow& rng, ShadingType st)
+{
+    const svr_oracle_scene* s = c.s;
+    V3 Li = mk(0.f, 0.f, 0.f);
+    if (s->numLights == 0) return Li;
+    int lightId = (int)((float)s->numLights * rng.uniform());
+    lightId = lightId < (int)s->numLights ? lightId : (int)s->numLights - 1;
+    const svr_area_light& light = s->lights[lightId];
+    V3 lightPos, wi;
+    float pdf;
+    Li = sample_light(light, vs.ptInWorld, rng, &lightPos, &wi, &pdf);
+    if (pdf > 0.f && max3(Li) > 0.f) {
+        float Tr = transmittance(c, vs.ptInWorld, lightPos, rng);
+        Li = (Tr * (float)s->numLights) * bsdf(vs, wi, st) * Li / pdf;
+    } else {
+        Li = mk(0.f, 0.f, 0.f);
+    }
+    return Li;
+}
+
+/* pathtracer.cu:96-103 (0.0722 is a double literal) */
+inline bool terminate_with_russian_roulette(V3* T, Xorwow& rng)
+{
+    float illum = (float)((double)(0.2126f * T->x + 0.7152f * T->y) + 0.0722 * (double)T->z);
+    if (rng.uniform() > illum) return true;
+    *T = *T / illum;
+    return false;
+}
+
+/* cuda_camera.h:66-83 */
+inline void camera_generate_ray_pt(const svr_camera& cam, uint32_t x, uint32_t y, Xorwow& rng, Ray* ray)
+{
+    float nx = 2.f * (((float)x + rng.uniform()) / ((float)cam.imageW - 1.f)) - 1.f;
+    float ny = 2.f * (((float)y + rng.uniform()) / ((float)cam.imageH - 1.f)) - 1.f;
+    nx = nx * cam.aspectRatio * cam.tanFovxOverTwo;
+    ny = ny * cam.tanFovxOverTwo;
+    nx = nx * cam.focalLength;
+    ny = ny * cam.focalLength;
+    float ax, ay;
+    uniform_sample_disk(rng, cam.apeture, &ax, &ay);
+    V3 u = mk(cam.u), v = mk(cam.v), w = mk(cam.w);
+    ray->orig = mk(cam.pos) + ax * u + ay * v;
+    ray->dir = normalize((nx - ax) * u + (ny - ay) * v - cam.focalLength * w);
+    ray->tMin = (float)1e-6;
+    ray->tMax = FLT_MAX;
+}
+
+/* cuda_camera.h:85-95 */
+inline void camera_generate_ray_rc(const svr_camera& cam, uint32_t x, uint32_t y, Ray* ray)
+{
+    float nx = 2.f * (((float)x + 0.5f) / ((float)cam.imageW - 1.f)) - 1.f;
+    float ny = 2.f * (((float)y + 0.5f) / ((float)cam.imageH - 1.f)) - 1.f;
+    nx = nx * cam.aspectRatio * cam.tanFovxOverTwo;
+    ny = ny * cam.tanFovxOverTwo;
+    ray->orig = mk(cam.pos);
+    ray->dir = normalize(nx * mk(cam.u) + ny * mk(cam.v) - mk(cam.w));
+    ray->tMin = (float)1e-6;
+    ray->tMax = FLT_MAX;
+}
+
+/* pathtracer.cu:200-280, one pixel, one frame; returns the radiance estimate L */
+inline V3 trace_path(Ctx& c, uint32_t idx, uint32_t idy, uint32_t offset, uint32_t traceDepth, uint32_t hashedFrameNo)
+{
+    const svr_oracle_scene* s = c.s;
+    Xorwow rng((uint64_t)(uint32_t)(hashedFrameNo + offset));
+    V3 L = mk(0.f, 0.f, 0.f), T = mk(1.f, 1.f, 1.f);
+    Ray ray;
+    camera_generate_ray_pt(s->camera, idx, idy, rng, &ray);
+    c.cnt[SVR_ORACLE_CNT_PATHS]++;
+
+    LightSample ls;
+    bool hitLight = get_nearest_light_sample(ray, s->lights, s->numLights, &ls);
+    for (uint32_t k = 0; k < traceDepth; ++k) {
+        float t = sample_distance(c, ray, rng, SVR_ORACLE_CNT_TRACK_TAPS);
+        if ((k == 0) && hitLight) {
+            t = t < 0.f ? FLT_MAX : t;
+            if (ls.t < t) {
+                float cosTerm = dot(ls.normal, -ray.dir);
+                L = L + T * ls.radiance * (cosTerm <= 0.f ? 0.f : 1.f);
+                break;
+            }
+        }
+        if (t < 0.f) {
+            if (s->envEnabled) L = L + T * env_radiance(s); /* the line commented out at pathtracer.cu:233 */
+            break;
+        }
+        VolumeSample vs;
+        vs.wo = -ray.dir;
+        vs.ptInWorld = ray.orig + t * ray.dir;
+        vs.intensity = vol_intensity(s, vs.ptInWorld);
+        vs.color_opacity = tf_lookup(s, vs.intensity);
+        vs.gradient = vol_gradient(s, vs.ptInWorld);
+        vs.gradientMagnitude = sqrtf(dot(vs.gradient, vs.gradient));
+        c.cnt[SVR_ORACLE_CNT_SHADE_TAPS] += 7;
+        c.cnt[SVR_ORACLE_CNT_TF_LOOKUPS]++;
+        c.cnt[SVR_ORACLE_CNT_SCATTERS]++;
+
+        V3 wi = mk(0.f, 0.f, 0.f);
+        float pdf = 0.f;
+        ShadingType st;
+        float gf = s->volume.gradientFactor;
+        float Pbrdf = vs.color_opacity.w *
+                      (1.f - expf(-25.f * gf * gf * gf * vs.gradientMagnitude * 65535.f * s->volume.invMaxMagnitude));
+        st = (rng.uniform() < Pbrdf) ? BRDF : ISOTROPIC;
+
+        L = L + T * estimate_direct_light(c, vs, rng, st);
+
+        V3 f = sample_bsdf(vs, &wi, &pdf, rng, st);
+        float cosTerm = fabsf(dot(normalize(vs.gradient), wi));
+        if (max3(f) > 0.f && pdf > 0.f) {
+            if (st == ISOTROPIC)
+                T = T * (f / (pdf * (1.f - Pbrdf)));
+            else
+                T = T * (f * cosTerm / (pdf * Pbrdf));
+        }
+        ray.orig = vs.ptInWorld;
+        ray.dir = wi;
+        if (k >= 3) {
+            if (terminate_with_russian_roulette(&T, rng)) break;
+        }
+    }
+    return L;
+}
+
+/* tonemapping.h:13-27 (default gamma = 1/2.2f, so the exponent is 2.2) */
+inline V3 reinhard_tone_mapping(V3 L, float exposure)
+{
+    V3 l = L * 16.f;
+    l.x = 1.f - expf(-l.x * exposure);
+    l.y = 1.f - expf(-l.y * exposure);
+    l.z = 1.f - expf(-l.z * exposure);
+    float invGamma = 1.f / (1.f / 2.2f);
+    l.x = powf(l.x, invGamma);
+    l.y = powf(l.y, invGamma);
+    l.z = powf(l.z, invGamma);
+    return l;
+}
+
+int g_threads = 0;
+
+}  // namespace
+
+extern "C" {
+
+int svr_oracle_threads(void)
+{
+#ifdef _OPENMP
+    return g_threads > 0 ? g_threads : omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void svr_oracle_set_threads(int n) { g_threads = n; }
+
+/* raycasting.cu:15-67 */
+void svr_oracle_raycast(const svr_oracle_scene* scene, float stepSize, uint32_t strideW, uint32_t y0, uint32_t y1,
+                        float* outRGBA, uint8_t* outU8, uint64_t* counters)
+{
+    const uint32_t W = scene->camera.imageW;
+    uint64_t totals[SVR_ORACLE_CNT_COUNT] = {0};
+#pragma omp parallel num_threads(svr_oracle_threads())
+    {
+        Ctx c;
+        c.s = scene;
+        memset(c.cnt, 0, sizeof(c.cnt));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t idy = (int64_t)y0; idy < (int64_t)y1; ++idy) {
+            for (uint32_t idx = 0; idx < W; ++idx) {
+                size_t offset = (size_t)idy * strideW + idx;
+                Ray ray;
+                camera_generate_ray_rc(scene->camera, idx, (uint32_t)idy, &ray);
+                V4 L = {0.f, 0.f, 0.f, 0.f};
+                float tNear, tFar, t;
+                c.cnt[SVR_ORACLE_CNT_PATHS]++;
+                if (vol_intersect(scene, ray, &tNear, &tFar)) {
+                    t = tNear;
+                    while (t <= tFar) {
+                        V3 p = ray.orig + t * ray.dir;
+                        float intensity = vol_intensity(scene, p);
+                        V4 co = tf_lookup(scene, intensity);
+                        V3 g = vol_gradient(scene, p);
+                        float gm = sqrtf(dot(g, g));
+                        c.cnt[SVR_ORACLE_CNT_SHADE_TAPS] += 7;
+                        c.cnt[SVR_ORACLE_CNT_TF_LOOKUPS]++;
+                        c.cnt[SVR_ORACLE_CNT_STEPS]++;
+                        float cosTerm = 1.f, specularTerm = 0.f;
+                        if ((double)gm > 1e-3) {
+                            V3 normal = normalize(g);
+                            V3 lightDir = normalize(mk(scene->camera.pos) - p);
+                            cosTerm = fabsf(dot(normal, lightDir));
+                            specularTerm = powf(cosTerm, 30.f);
+                        }
+                        co.x = co.x * co.w * cosTerm * 0.8f + co.w * specularTerm * 0.2f;
+                        co.y = co.y * co.w * cosTerm * 0.8f + co.w * specularTerm * 0.2f;
+                        co.z = co.z * co.w * cosTerm * 0.8f + co.w * specularTerm * 0.2f;
+                        float k = 1.f - L.w;
+                        L.x += k * co.x;
+                        L.y += k * co.y;
+                        L.z += k * co.z;
+                        L.w += k * co.w;
+                        if (L.w > 0.95f) break;
+                        t += stepSize * 0.5f;
+                    }
+                }
+                L.x = fminf(L.x, 1.f);
+                L.y = fminf(L.y, 1.f);
+                L.z = fminf(L.z, 1.f);
+                if (outRGBA) {
+                    outRGBA[4 * offset + 0] = L.x;
+                    outRGBA[4 * offset + 1] = L.y;
+                    outRGBA[4 * offset + 2] = L.z;
+                    outRGBA[4 * offset + 3] = L.w;
+                }
+                if (outU8) {
+                    outU8[4 * offset + 0] = (uint8_t)(L.x * 255);
+                    outU8[4 * offset + 1] = (uint8_t)(L.y * 255);
+                    outU8[4 * offset + 2] = (uint8_t)(L.z * 255);
+                    outU8[4 * offset + 3] = (uint8_t)(255 * L.w);
+                }
+            }
+        }
+#pragma omp critical
+        for (int i = 0; i < SVR_ORACLE_CNT_COUNT; ++i) totals[i] += c.cnt[i];
+    }
+    if (counters)
+        for (int i = 0; i < SVR_ORACLE_CNT_COUNT; ++i) counters[i] += totals[i];
+}
+
+/* render_pathtracer (pathtracer.cu:292-304) repeated nFrames times, minus the tone map */
+void svr_oracle_pathtrace(const svr_oracle_scene* scene, uint32_t traceDepth, uint32_t frameNo0, uint32_t nFrames,
+                          uint32_t strideW, uint32_t y0, uint32_t y1, float* hdr, uint64_t* counters)
+{
+    const uint32_t W = scene->camera.imageW;
+    uint64_t totals[SVR_ORACLE_CNT_COUNT] = {0};
+#pragma omp parallel num_threads(svr_oracle_threads())
+    {
+        Ctx c;
+        c.s = scene;
+        memset(c.cnt, 0, sizeof(c.cnt));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t idy = (int64_t)y0; idy < (int64_t)y1; ++idy) {
+            for (uint32_t idx = 0; idx < W; ++idx) {
+                uint32_t offset = (uint32_t)idy * strideW + idx;
+                float* acc = hdr + 3 * (size_t)offset;
+                for (uint32_t f = 0; f < nFrames; ++f) {
+                    uint32_t frameNo = frameNo0 + f;
+                    if (frameNo == 0) acc[0] = acc[1] = acc[2] = 0.f; /* clear_hdr_buffer, pathtracer.cu:86-94 */
+                    V3 L = trace_path(c, idx, (uint32_t)idy, offset, traceDepth, wang_hash(frameNo));
+                    /* running_estimate, pathtracer.cu:81-84 */
+                    float n1 = (float)frameNo + 1.f;
+                    acc[0] += (L.x - acc[0]) / n1;
+                    acc[1] += (L.y - acc[1]) / n1;
+                    acc[2] += (L.z - acc[2]) / n1;
+                }
+            }
+        }
+#pragma omp critical
+        for (int i = 0; i < SVR_ORACLE_CNT_COUNT; ++i) totals[i] += c.cnt[i];
+    }
+    if (counters)
+        for (int i = 0; i < SVR_ORACLE_CNT_COUNT; ++i) counters[i] += totals[i];
+}
+
+/* hdr_to_ldr, pathtracer.cu:282-290 */
+void svr_oracle_tonemap(const float* hdr, float exposure, uint64_t npix, uint8_t* outU8)
+{
+#pragma omp parallel for num_threads(svr_oracle_threads())
+    for (int64_t i = 0; i < (int64_t)npix; ++i) {
+        V3 l = reinhard_tone_mapping(mk(hdr[3 * i], hdr[3 * i + 1], hdr[3 * i + 2]), exposure);
+        outU8[4 * i + 0] = (uint8_t)(l.x * 255);
+        outU8[4 * i + 1] = (uint8_t)(l.y * 255);
+        outU8[4 * i + 2] = (uint8_t)(l.z * 255);
+        outU8[4 * i + 3] = 255;
+    }
+}
+
+float svr_oracle_tex3d(const svr_oracle_scene* scene, float u, float v, float w) { return tex3d(scene, u, v, w); }
+
+void svr_oracle_tf(const svr_oracle_scene* scene, float intensity, float* rgba)
+{
+    V4 r = tf_lookup(scene, intensity);
+    rgba[0] = r.x;
+    rgba[1] = r.y;
+    rgba[2] = r.z;
+    rgba[3] = r.w;
+}
+
+uint32_t svr_oracle_wang_hash(uint32_t a) { return wang_hash(a); }
+
+void svr_oracle_xorwow_uniforms(uint64_t seed, uint32_t n, float* out)
+{
+    Xorwow rng(seed);
+    for (uint32_t i = 0; i < n; ++i) out[i] = rng.uniform();
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""ctypes binding of libsvr_b200.so (include/svr_render.h, include/svr_types.h).
+
+The structures below are the plain-C mirrors of the reference's scene PODs (core/cuda_volume.h:111-121,
+core/cuda_camera.h:98-106, ...); sizes and offsets are asserted at import so a drift from the C
+headers fails loudly.  There is NO fallback: if the CUDA library is missing, importing this module
+raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvr_b200.so")
+
+
+class Vec2(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float)]
+
+
+class Vec3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+    def __init__(self, x=0.0, y=0.0, z=0.0):
+        super().__init__(float(x), float(y), float(z))
+
+    def tuple(self):
+        return (self.x, self.y, self.z)
+
+
+class Vec4(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("w", C.c_float)]
+
+
+class BBox(C.Structure):
+    _fields_ = [("vmin", Vec3), ("vmax", Vec3), ("invSize", Vec3)]
+
+
+class Volume(C.Structure):  # cudaVolume
+    _fields_ = [
+        ("bbox", BBox),
+        ("_pad0", C.c_uint32),
+        ("tex", C.c_ulonglong),
+        ("densityScale", C.c_float),
+        ("invMaxMagnitude", C.c_float),
+        ("gradientFactor", C.c_float),
+        ("spacing", Vec3),
+        ("invSpacing", Vec3),
+        ("x_clip", Vec2),
+        ("y_clip", Vec2),
+        ("z_clip", Vec2),
+        ("_pad1", C.c_uint32),
+    ]
+
+
+class TransferFunction(C.Structure):  # cudaTransferFunction
+    _fields_ = [("tex", C.c_ulonglong), ("maxOpacity", C.c_float), ("_pad0", C.c_uint32)]
+
+
+class Camera(C.Structure):  # cudaCamera
+    _fields_ = [
+        ("imageW", C.c_uint32),
+        ("imageH", C.c_uint32),
+        ("exposure", C.c_float),
+        ("apeture", C.c_float),
+        ("focalLength", C.c_float),
+        ("aspectRatio", C.c_float),
+        ("tanFovxOverTwo", C.c_float),
+        ("pos", Vec3),
+        ("u", Vec3),
+        ("v", Vec3),
+        ("w", Vec3),
+    ]
+
+
+class Disk(C.Structure):  # cudaDisk
+    _fields_ = [("radius", C.c_float), ("center", Vec3), ("normal", Vec3)]
+
+
+class AreaLight(C.Structure):  # cudaAreaLight
+    _fields_ = [("disk", Disk), ("color", Vec3), ("intensity", C.c_float)]
+
+
+class EnvLight(C.Structure):  # cudaEnvironmentLight
+    _fields_ = [("tex", C.c_ulonglong), ("defaultRadiance", Vec3), ("intensity", C.c_float), ("offset", Vec2)]
+
+
+class RenderParams(C.Structure):  # RenderParams
+    _fields_ = [("traceDepth", C.c_uint32), ("frameNo", C.c_uint32), ("hdrBuffer", C.c_void_p)]
+
+
+assert C.sizeof(Vec3) == 12 and C.sizeof(BBox) == 36
+assert C.sizeof(Volume) == 112 and Volume.tex.offset == 40 and Volume.spacing.offset == 60 and Volume.z_clip.offset == 100
+assert C.sizeof(TransferFunction) == 16 and TransferFunction.maxOpacity.offset == 8
+assert C.sizeof(Camera) == 76 and Camera.pos.offset == 28 and Camera.w.offset == 64
+assert C.sizeof(Disk) == 28 and C.sizeof(AreaLight) == 44
+assert C.sizeof(EnvLight) == 32 and EnvLight.intensity.offset == 20
+assert C.sizeof(RenderParams) == 16 and RenderParams.hdrBuffer.offset == 8
+
+# enum svr_option
+OPT_PT_MODE, OPT_SHADOW_ESTIMATOR, OPT_ENV_ENABLED, OPT_MACROCELL_SIZE, OPT_RC_SKIP, OPT_SEED, OPT_COUNTERS, OPT_PT_BLOCK, OPT_RC_BLOCK = range(9)
+# enum svr_voxel_format
+VOXEL_U8, VOXEL_U16, VOXEL_F16, VOXEL_F32 = range(4)
+VOXEL_BYTES = {VOXEL_U8: 1, VOXEL_U16: 2, VOXEL_F16: 2, VOXEL_F32: 4}
+# enum svr_volume_kind
+GEN_SPHERE, GEN_CT, GEN_CLOUD = range(3)
+# enum svr_counter
+CNT_TRACK_TAPS, CNT_SHADOW_TAPS, CNT_SHADE_TAPS, CNT_TF_LOOKUPS, CNT_SCATTERS, CNT_PATHS, CNT_CELLS, CNT_STEPS, CNT_SKIPPED = range(9)
+CNT_NAMES = ["track_taps", "shadow_taps", "shade_taps", "tf_lookups", "scatters", "paths", "cells", "steps", "skipped"]
+
+# every symbol include/svr_render.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = [
+    # Part 1 -- the reference boundary (pathtracer.h:17-24, raycasting.h:8)
+    ("render_pathtracer", None, [_P, C.POINTER(RenderParams)]),
+    ("setup_volume", None, [C.POINTER(Volume)]),
+    ("setup_transferfunction", None, [C.POINTER(TransferFunction)]),
+    ("setup_camera", None, [C.POINTER(Camera)]),
+    ("setup_env_lights", None, [C.POINTER(EnvLight)]),
+    ("setup_area_lights", None, [C.POINTER(AreaLight), C.c_uint32]),
+    ("render_raycasting", None, [_P, C.POINTER(Volume), C.POINTER(TransferFunction), C.POINTER(Camera), C.c_float]),
+    # Part 2 -- headless extension
+    ("svr_version", C.c_int, []),
+    ("svr_last_error", C.c_char_p, []),
+    ("svr_set_stream", C.c_int, [_P]),
+    ("svr_set_device", C.c_int, [C.c_int]),
+    ("svr_set_option", C.c_int, [C.c_int, C.c_int]),
+    ("svr_get_option", C.c_int, [C.c_int]),
+    ("svr_render_pathtracer_spp", C.c_int, [_P, C.POINTER(RenderParams), C.c_uint32]),
+    ("svr_pathtracer_accumulate", C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+    ("svr_pathtracer_resolve", C.c_int, [_P, _P, _P]),
+    ("svr_render_raycasting_f32", C.c_int, [_P, C.POINTER(Volume), C.POINTER(TransferFunction), C.POINTER(Camera), C.c_float]),
+    ("svr_render_raycasting_rows", C.c_int, [_P, _P, C.POINTER(Volume), C.POINTER(TransferFunction), C.POINTER(Camera), C.c_float, C.c_uint32, C.c_uint32]),
+    ("svr_volume_create", C.c_int, [C.POINTER(Volume), _P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float]),
+    ("svr_volume_destroy", C.c_int, [C.POINTER(Volume)]),
+    ("svr_volume_invalidate_cache", C.c_int, []),
+    ("svr_tf_create", C.c_int, [C.POINTER(TransferFunction), _P, C.c_uint32]),
+    ("svr_tf_destroy", C.c_int, [C.POINTER(TransferFunction)]),
+    ("svr_env_create", C.c_int, [C.POINTER(EnvLight), _P, C.c_uint32, C.c_uint32]),
+    ("svr_env_destroy", C.c_int, [C.POINTER(EnvLight)]),
+    ("svr_generate_volume", C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32]),
+    ("svr_max_gradient_magnitude", C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]),
+    ("svr_counters_reset", C.c_int, []),
+    ("svr_counters_read", C.c_int, [C.POINTER(C.c_uint64), C.c_uint32]),
+    ("svr_launch_count", C.c_uint64, []),
+    ("svr_microbench_taps", C.c_int, [C.POINTER(Volume), C.c_int, C.c_uint32, C.c_uint32, _P, C.POINTER(C.c_uint64)]),
+]
+
+
+class SvrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libsvr_b200.so and bind every declared symbol.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make lib` (or __graft_entry__.build()). "
+            "sunvolumerender_b200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
+    for name, res, args in SIGNATURES:
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().svr_last_error()
+        raise SvrError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,668 @@
+// svr_api.cu -- library state, options, the setup_* half of the reference boundary
+// (pathtracer.cu:34-68), resource builders that mirror the reference's loaders, synthetic volume
+// generators, gradient-magnitude reduction, counters, tap microbenchmarks.
+#include <cuda_fp16.h>
+
+#include <cstring>
+#include <vector>
+
+#include "svr_state.h"
+
+namespace svr {
+
+HostState& state()
+{
+    static HostState* s = [] {
+        HostState* p = new HostState();
+        memset(&p->scene, 0, sizeof(p->scene));
+        memset(p->options, 0, sizeof(p->options));
+        p->options[SVR_OPT_PT_MODE] = 2;
+        p->options[SVR_OPT_SHADOW_ESTIMATOR] = 0;
+        p->options[SVR_OPT_ENV_ENABLED] = 0;
+        p->options[SVR_OPT_MACROCELL_SIZE] = 8;
+        p->options[SVR_OPT_RC_SKIP] = 1;
+        p->options[SVR_OPT_SEED] = 0x5EED;
+        p->options[SVR_OPT_COUNTERS] = 0;
+        p->options[SVR_OPT_PT_BLOCK] = 128;
+        p->options[SVR_OPT_RC_BLOCK] = 128;
+        return p;
+    }();
+    return *s;
+}
+
+int fail(const char* where, cudaError_t e)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+    state().lastError = buf;
+    cudaGetLastError();  // clear the sticky-free error so later calls can proceed
+    return (int)e == 0 ? -1 : (int)e;
+}
+
+int fail_msg(const char* msg)
+{
+    state().lastError = msg;
+    return -1;
+}
+
+static void release_grid(HostState& st)
+{
+    if (st.volPointTex) cudaDestroyTextureObject(st.volPointTex);
+    st.volPointTex = 0;
+    cudaFree(st.dRange);
+    cudaFree(st.dMajorant);
+    st.dRange = nullptr;
+    st.dMajorant = nullptr;
+    st.gridArray = nullptr;
+    st.majorantValid = false;
+}
+
+}  // namespace svr
+
+using namespace svr;
+
+// ------------------------------------------------------------------------------------------------
+// Part 1: setup_* (pathtracer.cu:34-68).  The PODs are copied into the host snapshot that every
+// later launch passes as its kernel parameter block; like the reference they return only after
+// the device is idle (cudaDeviceSynchronize), except setup_area_lights (pathtracer.cu:57-61).
+// ------------------------------------------------------------------------------------------------
+extern "C" void setup_volume(const svr_volume* vol)
+{
+    HostState& st = state();
+    st.scene.vol = *vol;
+    st.majorantValid = false;  // densityScale / array may have changed
+    SVR_FATAL(cudaDeviceSynchronize());
+}
+
+extern "C" void setup_transferfunction(const svr_transfer_function* tf)
+{
+    HostState& st = state();
+    st.scene.tf = *tf;
+    st.majorantValid = false;  // every TF edit invalidates the local majorants
+    SVR_FATAL(cudaDeviceSynchronize());
+}
+
+extern "C" void setup_camera(const svr_camera* cam)
+{
+    state().scene.cam = *cam;
+    SVR_FATAL(cudaDeviceSynchronize());
+}
+
+extern "C" void setup_env_lights(const svr_env_light* light)
+{
+    state().scene.env = *light;
+    SVR_FATAL(cudaDeviceSynchronize());
+}
+
+extern "C" void setup_area_lights(svr_area_light* lights, uint32_t n)
+{
+    // the reference overruns its 8-entry constant array for n > 8 (lights.cpp:94 lets a 9th through)
+    if (n > SVR_MAX_LIGHT_SOURCES) n = SVR_MAX_LIGHT_SOURCES;
+    HostState& st = state();
+    st.scene.numLights = n;
+    for (uint32_t i = 0; i < n; ++i) st.scene.lights[i] = lights[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Part 2: library management
+// ------------------------------------------------------------------------------------------------
+extern "C" int svr_version(void) { return SVR_VERSION; }
+extern "C" const char* svr_last_error(void) { return state().lastError.c_str(); }
+
+extern "C" int svr_set_stream(void* cuda_stream)
+{
+    state().stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+extern "C" int svr_set_device(int device)
+{
+    HostState& st = state();
+    SVR_TRY(cudaSetDevice(device));
+    // derived data lives on the previous device: drop it
+    release_grid(st);
+    cudaFree(st.dTfSparse);
+    cudaFree(st.dTfTable);
+    cudaFree(st.dCounters);
+    st.dTfSparse = nullptr;
+    st.dTfTable = nullptr;
+    st.tfEntries = 0;
+    st.dCounters = nullptr;
+    cudaGetLastError();
+    return 0;
+}
+
+extern "C" int svr_set_option(int key, int value)
+{
+    if (key < 0 || key >= SVR_OPT_COUNT_) return fail_msg("svr_set_option: unknown key");
+    HostState& st = state();
+    switch (key) {
+        case SVR_OPT_PT_MODE:
+            if (value < 0 || value > 2) return fail_msg("SVR_OPT_PT_MODE must be 0, 1 or 2");
+            break;
+        case SVR_OPT_MACROCELL_SIZE:
+            if (value < 2 || value > 64 || (value & (value - 1))) return fail_msg("SVR_OPT_MACROCELL_SIZE must be a power of two in 2..64");
+            if (value != st.options[key]) release_grid(st);
+            break;
+        case SVR_OPT_PT_BLOCK:
+        case SVR_OPT_RC_BLOCK:
+            if (value != 64 && value != 128 && value != 256) return fail_msg("block size must be 64, 128 or 256");
+            break;
+        default: break;
+    }
+    st.options[key] = value;
+    return 0;
+}
+
+extern "C" int svr_get_option(int key)
+{
+    if (key < 0 || key >= SVR_OPT_COUNT_) return -1;
+    return state().options[key];
+}
+
+extern "C" uint64_t svr_launch_count(void) { return state().launches; }
+
+extern "C" int svr_volume_invalidate_cache(void)
+{
+    release_grid(state());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// counters
+// ------------------------------------------------------------------------------------------------
+namespace svr {
+Counters* device_counters()
+{
+    HostState& st = state();
+    if (!st.dCounters) {
+        if (cudaMalloc(&st.dCounters, sizeof(Counters)) != cudaSuccess) return nullptr;
+        cudaMemset(st.dCounters, 0, sizeof(Counters));
+    }
+    return st.dCounters;
+}
+}  // namespace svr
+
+extern "C" int svr_counters_reset(void)
+{
+    Counters* c = device_counters();
+    if (!c) return fail_msg("svr_counters_reset: allocation failed");
+    SVR_TRY(cudaMemsetAsync(c, 0, sizeof(Counters), state().stream));
+    return 0;
+}
+
+extern "C" int svr_counters_read(uint64_t* host_out, uint32_t n)
+{
+    Counters* c = device_counters();
+    if (!c) return fail_msg("svr_counters_read: allocation failed");
+    Counters h;
+    SVR_TRY(cudaStreamSynchronize(state().stream));
+    SVR_TRY(cudaMemcpy(&h, c, sizeof(h), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n && i < 16; ++i) host_out[i] = h.v[i];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resource builders
+// ------------------------------------------------------------------------------------------------
+static size_t voxel_bytes(int format)
+{
+    switch (format) {
+        case SVR_VOXEL_U8: return 1;
+        case SVR_VOXEL_U16: return 2;
+        case SVR_VOXEL_F16: return 2;
+        case SVR_VOXEL_F32: return 4;
+        default: return 0;
+    }
+}
+
+static cudaChannelFormatDesc voxel_channel(int format)
+{
+    switch (format) {
+        case SVR_VOXEL_U8: return cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        case SVR_VOXEL_U16: return cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        case SVR_VOXEL_F16: return cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindFloat);
+        default: return cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    }
+}
+
+extern "C" int svr_max_gradient_magnitude(const void* dev_data, int format, uint32_t nx, uint32_t ny, uint32_t nz,
+                                          float sx, float sy, float sz, float* host_out);
+
+// core/VolumeReader.cpp:138-185
+extern "C" int svr_volume_create(svr_volume* out, const void* data, int data_on_device, int format, uint32_t nx,
+                                 uint32_t ny, uint32_t nz, float sx, float sy, float sz, float maxGradMag)
+{
+    size_t bpe = voxel_bytes(format);
+    if (!bpe || !out || !data || !nx || !ny || !nz) return fail_msg("svr_volume_create: bad argument");
+    HostState& st = state();
+    cudaChannelFormatDesc ch = voxel_channel(format);
+    cudaExtent extent = make_cudaExtent(nx, ny, nz);
+    cudaArray_t arr = nullptr;
+    SVR_TRY(cudaMalloc3DArray(&arr, &ch, extent, cudaArrayDefault));
+
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.dstArray = arr;
+    cp.extent = extent;
+    cp.kind = data_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cp.srcPtr = make_cudaPitchedPtr(const_cast<void*>(data), nx * bpe, nx, ny);
+    cudaError_t e = cudaMemcpy3DAsync(&cp, st.stream);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return fail("cudaMemcpy3DAsync(volume)", e);
+    }
+
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+    td.filterMode = cudaFilterModeLinear;
+    // integer formats read as normalised float (VolumeReader.cpp:168); float formats as stored
+    td.readMode = (format == SVR_VOXEL_U8 || format == SVR_VOXEL_U16) ? cudaReadModeNormalizedFloat : cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    cudaTextureObject_t tex = 0;
+    e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return fail("cudaCreateTextureObject(volume)", e);
+    }
+
+    if (!(maxGradMag > 0.f)) {
+        if (!data_on_device) {
+            // stage once on the device for the reduction
+            void* tmp = nullptr;
+            size_t bytes = (size_t)nx * ny * nz * bpe;
+            SVR_TRY(cudaMalloc(&tmp, bytes));
+            cudaMemcpyAsync(tmp, data, bytes, cudaMemcpyHostToDevice, st.stream);
+            int rc = svr_max_gradient_magnitude(tmp, format, nx, ny, nz, sx, sy, sz, &maxGradMag);
+            cudaFree(tmp);
+            if (rc) return rc;
+        } else {
+            int rc = svr_max_gradient_magnitude(data, format, nx, ny, nz, sx, sy, sz, &maxGradMag);
+            if (rc) return rc;
+        }
+        if (!(maxGradMag > 0.f)) maxGradMag = 1.f;
+    }
+
+    memset(out, 0, sizeof(*out));
+    float3 size = f3(nx * sx, ny * sy, nz * sz);
+    float3 vmax = size - size * 0.5f;  // VolumeReader.cpp:178-180
+    out->bbox.vmin = {-vmax.x, -vmax.y, -vmax.z};
+    out->bbox.vmax = {vmax.x, vmax.y, vmax.z};
+    out->bbox.invSize = {1.f / (vmax.x + vmax.x), 1.f / (vmax.y + vmax.y), 1.f / (vmax.z + vmax.z)};
+    out->tex = tex;
+    out->densityScale = 1.f;          // gui/canvas.cpp:32
+    out->invMaxMagnitude = 1.f / maxGradMag;
+    out->gradientFactor = 0.5f;       // gui/canvas.cpp:19
+    out->spacing = {sx, sy, sz};
+    out->invSpacing = {1.f / sx, 1.f / sy, 1.f / sz};
+    out->x_clip = out->y_clip = out->z_clip = {-1.f, 1.f};  // gui/canvas.cpp:31
+    SVR_TRY(cudaStreamSynchronize(st.stream));
+    return 0;
+}
+
+extern "C" int svr_volume_destroy(svr_volume* vol)
+{
+    if (!vol || !vol->tex) return 0;
+    HostState& st = state();
+    cudaResourceDesc rd;
+    SVR_TRY(cudaGetTextureObjectResourceDesc(&rd, vol->tex));
+    SVR_TRY(cudaDeviceSynchronize());
+    if (rd.resType == cudaResourceTypeArray && rd.res.array.array == st.gridArray) release_grid(st);
+    SVR_TRY(cudaDestroyTextureObject(vol->tex));
+    if (rd.resType == cudaResourceTypeArray) SVR_TRY(cudaFreeArray(rd.res.array.array));
+    vol->tex = 0;
+    return 0;
+}
+
+// gui/transferfunction.cpp:17-44
+extern "C" int svr_tf_create(svr_transfer_function* out, const float* host_rgba, uint32_t n)
+{
+    if (!out || !host_rgba || n < 2) return fail_msg("svr_tf_create: bad argument");
+    HostState& st = state();
+    cudaChannelFormatDesc ch = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
+    cudaArray_t arr = nullptr;
+    SVR_TRY(cudaMallocArray(&arr, &ch, n));
+    cudaError_t e = cudaMemcpy2DToArrayAsync(arr, 0, 0, host_rgba, sizeof(float) * 4 * n, sizeof(float) * 4 * n, 1,
+                                             cudaMemcpyHostToDevice, st.stream);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return fail("cudaMemcpy2DToArrayAsync(tf)", e);
+    }
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.normalizedCoords = 1;
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return fail("cudaCreateTextureObject(tf)", e);
+    }
+    float maxOpacity = 0.f;  // transferfunction.cpp:26 (member starts at 0 in the constructor path)
+    for (uint32_t i = 0; i < n; ++i) maxOpacity = fmaxf(maxOpacity, host_rgba[4 * i + 3]);
+    memset(out, 0, sizeof(*out));
+    out->tex = tex;
+    out->maxOpacity = maxOpacity;
+    SVR_TRY(cudaStreamSynchronize(st.stream));
+    return 0;
+}
+
+extern "C" int svr_tf_destroy(svr_transfer_function* tf)
+{
+    if (!tf || !tf->tex) return 0;
+    cudaResourceDesc rd;
+    SVR_TRY(cudaGetTextureObjectResourceDesc(&rd, tf->tex));
+    SVR_TRY(cudaDeviceSynchronize());
+    if (rd.resType == cudaResourceTypeArray && rd.res.array.array == state().majorantTfArray) {
+        state().majorantTfArray = nullptr;
+        state().majorantValid = false;
+    }
+    SVR_TRY(cudaDestroyTextureObject(tf->tex));
+    if (rd.resType == cudaResourceTypeArray) SVR_TRY(cudaFreeArray(rd.res.array.array));
+    tf->tex = 0;
+    return 0;
+}
+
+// core/lights/lights.cpp:31-75
+extern "C" int svr_env_create(svr_env_light* out, const float* host_rgba, uint32_t w, uint32_t h)
+{
+    if (!out || !host_rgba || !w || !h) return fail_msg("svr_env_create: bad argument");
+    HostState& st = state();
+    cudaChannelFormatDesc ch = cudaCreateChannelDesc<float4>();
+    cudaArray_t arr = nullptr;
+    SVR_TRY(cudaMallocArray(&arr, &ch, w, h));
+    cudaError_t e = cudaMemcpy2DToArrayAsync(arr, 0, 0, host_rgba, sizeof(float4) * w, sizeof(float4) * w, h,
+                                             cudaMemcpyHostToDevice, st.stream);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return fail("cudaMemcpy2DToArrayAsync(env)", e);
+    }
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    cudaTextureObject_t tex = 0;
+    e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return fail("cudaCreateTextureObject(env)", e);
+    }
+    memset(out, 0, sizeof(*out));
+    out->tex = tex;          // cudaEnvironmentLight::Set(tex), cuda_environment_light.h:20-25
+    out->intensity = 1.f;
+    out->offset = {0.f, 0.f};
+    SVR_TRY(cudaStreamSynchronize(st.stream));
+    return 0;
+}
+
+extern "C" int svr_env_destroy(svr_env_light* env)
+{
+    if (!env || !env->tex) return 0;
+    cudaResourceDesc rd;
+    SVR_TRY(cudaGetTextureObjectResourceDesc(&rd, env->tex));
+    SVR_TRY(cudaDeviceSynchronize());
+    SVR_TRY(cudaDestroyTextureObject(env->tex));
+    if (rd.resType == cudaResourceTypeArray) SVR_TRY(cudaFreeArray(rd.res.array.array));
+    env->tex = 0;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic volumes.  All generators are pure functions of (voxel, n, seed).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint32_t hash3(int x, int y, int z, uint32_t seed)
+{
+    uint32_t h = seed * 0x9E3779B1u;
+    h ^= (uint32_t)x * 0x85EBCA77u;
+    h = (h << 13) | (h >> 19);
+    h ^= (uint32_t)y * 0xC2B2AE3Du;
+    h = (h << 13) | (h >> 19);
+    h ^= (uint32_t)z * 0x27D4EB2Fu;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return h;
+}
+
+__device__ __forceinline__ float lattice(int x, int y, int z, uint32_t seed)
+{
+    return (float)(hash3(x, y, z, seed) >> 8) * (1.f / 16777216.f);
+}
+
+// trilinear value noise with smoothstep weights, in [0,1)
+__device__ float value_noise(float x, float y, float z, uint32_t seed)
+{
+    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    float a = x - fx, b = y - fy, c = z - fz;
+    a = a * a * (3.f - 2.f * a);
+    b = b * b * (3.f - 2.f * b);
+    c = c * c * (3.f - 2.f * c);
+    float v000 = lattice(ix, iy, iz, seed), v100 = lattice(ix + 1, iy, iz, seed);
+    float v010 = lattice(ix, iy + 1, iz, seed), v110 = lattice(ix + 1, iy + 1, iz, seed);
+    float v001 = lattice(ix, iy, iz + 1, seed), v101 = lattice(ix + 1, iy, iz + 1, seed);
+    float v011 = lattice(ix, iy + 1, iz + 1, seed), v111 = lattice(ix + 1, iy + 1, iz + 1, seed);
+    float x00 = v000 + a * (v100 - v000), x10 = v010 + a * (v110 - v010);
+    float x01 = v001 + a * (v101 - v001), x11 = v011 + a * (v111 - v011);
+    float y0 = x00 + b * (x10 - x00), y1 = x01 + b * (x11 - x01);
+    return y0 + c * (y1 - y0);
+}
+
+__device__ float fbm(float x, float y, float z, int octaves, uint32_t seed)
+{
+    float sum = 0.f, amp = 0.5f, norm = 0.f;
+    for (int o = 0; o < octaves; ++o) {
+        sum += amp * value_noise(x, y, z, seed + (uint32_t)o * 101u);
+        norm += amp;
+        x *= 2.f;
+        y *= 2.f;
+        z *= 2.f;
+        amp *= 0.5f;
+    }
+    return sum / norm;
+}
+
+__device__ float density_at(int kind, int n, int x, int y, int z, uint32_t seed)
+{
+    float c = 0.5f * (float)n;
+    float px = (float)x + 0.5f - c, py = (float)y + 0.5f - c, pz = (float)z + 0.5f - c;
+    if (kind == SVR_GEN_SPHERE) {
+        // C1: rho = clamp(1 - r / (0.45 N), 0, 1)
+        float r = sqrtf(px * px + py * py + pz * pz);
+        return fminf(fmaxf(1.f - r / (0.45f * (float)n), 0.f), 1.f);
+    }
+    float qx = px / c, qy = py / c, qz = pz / c;  // [-1, 1]
+    if (kind == SVR_GEN_CT) {
+        // C2/C3/C5: nested ellipsoid shells -- skin 0.25, soft tissue 0.45, bone 0.85 -- plus three
+        // octaves of value noise (amplitude 0.05) inside the body; air is exactly 0
+        float e = sqrtf(qx * qx / (0.80f * 0.80f) + qy * qy / (0.62f * 0.62f) + qz * qz / (0.88f * 0.88f));
+        if (e >= 1.f) return 0.f;
+        float v = e > 0.93f ? 0.25f : 0.45f;
+        float b = sqrtf(qx * qx / (0.46f * 0.46f) + qy * qy / (0.36f * 0.36f) + qz * qz / (0.60f * 0.60f));
+        if (b < 1.f && b > 0.78f) v = 0.85f;
+        // two small dense inclusions ("vertebrae")
+        float dx = qx - 0.18f, dy = qy + 0.1f, dz = qz - 0.2f;
+        if (dx * dx + dy * dy + dz * dz < 0.01f) v = 0.85f;
+        dx = qx + 0.2f, dy = qy - 0.05f, dz = qz + 0.3f;
+        if (dx * dx + dy * dy + dz * dz < 0.008f) v = 0.85f;
+        float s = 8.f;
+        float nz3 = fbm(qx * s + 17.f, qy * s + 5.f, qz * s + 11.f, 3, seed);
+        v += 0.05f * (2.f * nz3 - 1.f);
+        return fminf(fmaxf(v, 0.f), 1.f);
+    }
+    // C4 cloud: 5-octave fBm shaped by a sphere mask
+    float r = sqrtf(qx * qx + qy * qy + qz * qz);
+    float mask = fminf(fmaxf((0.85f - r) / 0.35f, 0.f), 1.f);
+    float f = fbm(qx * 4.f + 3.f, qy * 4.f + 7.f, qz * 4.f + 13.f, 5, seed);
+    float d = (f - 0.42f) * 3.2f * mask;
+    return fminf(fmaxf(d, 0.f), 1.f);
+}
+
+template <typename T>
+__device__ __forceinline__ T encode(float d);
+template <>
+__device__ __forceinline__ uint8_t encode<uint8_t>(float d) { return (uint8_t)(d * 255.f + 0.5f); }
+template <>
+__device__ __forceinline__ uint16_t encode<uint16_t>(float d) { return (uint16_t)(d * 65535.f + 0.5f); }
+template <>
+__device__ __forceinline__ __half encode<__half>(float d) { return __float2half_rn(d); }
+template <>
+__device__ __forceinline__ float encode<float>(float d) { return d; }
+
+template <typename T>
+__global__ void gen_kernel(T* out, int kind, int n, uint32_t seed)
+{
+    size_t total = (size_t)n * n * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % n), y = (int)((i / n) % n), z = (int)(i / ((size_t)n * n));
+        out[i] = encode<T>(density_at(kind, n, x, y, z, seed));
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ float raw_value(const T* d, size_t i);
+template <>
+__device__ __forceinline__ float raw_value<uint8_t>(const uint8_t* d, size_t i) { return (float)d[i] * 257.f; }  // as u16
+template <>
+__device__ __forceinline__ float raw_value<uint16_t>(const uint16_t* d, size_t i) { return (float)d[i]; }
+template <>
+__device__ __forceinline__ float raw_value<__half>(const __half* d, size_t i) { return __half2float(d[i]) * 65535.f; }
+template <>
+__device__ __forceinline__ float raw_value<float>(const float* d, size_t i) { return d[i] * 65535.f; }
+
+// max |central-difference gradient| of the raw values, interior voxels, spacing-scaled
+// (VolumeReader.cpp:70-76: vtkImageGradientMagnitude on the short data, then the maximum)
+template <typename T>
+__global__ void gradmax_kernel(const T* d, int nx, int ny, int nz, float hx, float hy, float hz, unsigned int* outBits)
+{
+    size_t total = (size_t)nx * ny * nz;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((size_t)nx * ny));
+        int x0 = max(x - 1, 0), x1 = min(x + 1, nx - 1);
+        int y0 = max(y - 1, 0), y1 = min(y + 1, ny - 1);
+        int z0 = max(z - 1, 0), z1 = min(z + 1, nz - 1);
+        size_t row = ((size_t)z * ny + y) * nx, col = (size_t)z * ny * nx + x;
+        float gx = (raw_value<T>(d, row + x1) - raw_value<T>(d, row + x0)) * hx;
+        float gy = (raw_value<T>(d, col + (size_t)y1 * nx) - raw_value<T>(d, col + (size_t)y0 * nx)) * hy;
+        float gz = (raw_value<T>(d, ((size_t)z1 * ny + y) * nx + x) - raw_value<T>(d, ((size_t)z0 * ny + y) * nx + x)) * hz;
+        m = fmaxf(m, sqrtf(gx * gx + gy * gy + gz * gz));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(outBits, __float_as_uint(m));  // m >= 0: bit order == value order
+}
+
+}  // namespace
+
+extern "C" int svr_generate_volume(void* dev_out, int kind, int format, uint32_t n, uint32_t seed)
+{
+    if (!dev_out || !n || kind < 0 || kind > 2) return fail_msg("svr_generate_volume: bad argument");
+    HostState& st = state();
+    int blocks = 148 * 8, threads = 256;
+    switch (format) {
+        case SVR_VOXEL_U8: gen_kernel<uint8_t><<<blocks, threads, 0, st.stream>>>((uint8_t*)dev_out, kind, (int)n, seed); break;
+        case SVR_VOXEL_U16: gen_kernel<uint16_t><<<blocks, threads, 0, st.stream>>>((uint16_t*)dev_out, kind, (int)n, seed); break;
+        case SVR_VOXEL_F16: gen_kernel<__half><<<blocks, threads, 0, st.stream>>>((__half*)dev_out, kind, (int)n, seed); break;
+        case SVR_VOXEL_F32: gen_kernel<float><<<blocks, threads, 0, st.stream>>>((float*)dev_out, kind, (int)n, seed); break;
+        default: return fail_msg("svr_generate_volume: bad format");
+    }
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svr_max_gradient_magnitude(const void* dev_data, int format, uint32_t nx, uint32_t ny, uint32_t nz,
+                                          float sx, float sy, float sz, float* host_out)
+{
+    if (!dev_data || !host_out) return fail_msg("svr_max_gradient_magnitude: bad argument");
+    HostState& st = state();
+    unsigned int* dBits = nullptr;
+    SVR_TRY(cudaMalloc(&dBits, sizeof(unsigned int)));
+    cudaMemsetAsync(dBits, 0, sizeof(unsigned int), st.stream);
+    int blocks = 148 * 8, threads = 256;
+    float hx = 0.5f / sx, hy = 0.5f / sy, hz = 0.5f / sz;
+    switch (format) {
+        case SVR_VOXEL_U8: gradmax_kernel<uint8_t><<<blocks, threads, 0, st.stream>>>((const uint8_t*)dev_data, nx, ny, nz, hx, hy, hz, dBits); break;
+        case SVR_VOXEL_U16: gradmax_kernel<uint16_t><<<blocks, threads, 0, st.stream>>>((const uint16_t*)dev_data, nx, ny, nz, hx, hy, hz, dBits); break;
+        case SVR_VOXEL_F16: gradmax_kernel<__half><<<blocks, threads, 0, st.stream>>>((const __half*)dev_data, nx, ny, nz, hx, hy, hz, dBits); break;
+        case SVR_VOXEL_F32: gradmax_kernel<float><<<blocks, threads, 0, st.stream>>>((const float*)dev_data, nx, ny, nz, hx, hy, hz, dBits); break;
+        default: cudaFree(dBits); return fail_msg("svr_max_gradient_magnitude: bad format");
+    }
+    count_launch();
+    unsigned int bits = 0;
+    cudaError_t e = cudaMemcpyAsync(&bits, dBits, sizeof(bits), cudaMemcpyDeviceToHost, st.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st.stream);
+    cudaFree(dBits);
+    if (e != cudaSuccess) return fail("svr_max_gradient_magnitude", e);
+    memcpy(host_out, &bits, sizeof(float));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather-roofline microbenchmarks: independent tex3D taps, coherent (neighbouring threads walk
+// neighbouring rays) or random (hashed coordinates), no dependent arithmetic between taps.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void taps_kernel(svr_volume vol, int random, uint32_t tapsPerThread, float* sink)
+{
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    if (random) {
+        uint32_t h = tid * 0x9E3779B1u + 12345u;
+#pragma unroll 8
+        for (uint32_t i = 0; i < tapsPerThread; ++i) {
+            h = h * 1664525u + 1013904223u;
+            uint32_t a = h ^ (h >> 15);
+            a *= 0x2C1B3C6Du;
+            a ^= a >> 13;
+            float u = (float)(a & 0x3ffu) * (1.f / 1024.f);
+            float v = (float)((a >> 10) & 0x3ffu) * (1.f / 1024.f);
+            float w = (float)((a >> 20) & 0x3ffu) * (1.f / 1024.f);
+            acc += tex3D<float>(vol.tex, u, v, w);
+        }
+    } else {
+        // warp = 8x4 pixel tile of a 1024-wide virtual image, marching along +z
+        uint32_t warp = tid >> 5, lane = tid & 31;
+        uint32_t px = (warp % 128u) * 8u + (lane & 7u), py = ((warp / 128u) % 256u) * 4u + (lane >> 3);
+        float u = ((float)px + 0.5f) * (1.f / 1024.f), v = ((float)py + 0.5f) * (1.f / 1024.f);
+        float dw = 1.f / (float)tapsPerThread;
+#pragma unroll 8
+        for (uint32_t i = 0; i < tapsPerThread; ++i) acc += tex3D<float>(vol.tex, u, v, ((float)i + 0.5f) * dw);
+    }
+    if (acc == 123456.789f) sink[0] = acc;  // keep the taps alive
+}
+}  // namespace
+
+extern "C" int svr_microbench_taps(const svr_volume* vol, int random, uint32_t threads, uint32_t taps_per_thread,
+                                   float* dev_sink, uint64_t* host_taps)
+{
+    if (!vol || !vol->tex || !dev_sink) return fail_msg("svr_microbench_taps: bad argument");
+    uint32_t block = 256, grid = (threads + block - 1) / block;
+    taps_kernel<<<grid, block, 0, state().stream>>>(*vol, random, taps_per_thread, dev_sink);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    if (host_taps) *host_taps = (uint64_t)grid * block * taps_per_thread;
+    return 0;
+}

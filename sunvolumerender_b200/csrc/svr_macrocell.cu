@@ -1,0 +1,202 @@
+// svr_macrocell.cu -- macrocell majorant grid (callee-owned derived data; the reference has none:
+// woodcock_tracking.h:28-30 uses the single global majorant tf.GetMaxOpacity()).
+//
+// Two stages, so that the expensive one runs once per volume and the cheap one on every
+// transfer-function / density-scale edit:
+//   1. range grid : per cell, min/max of every texel a trilinear fetch positioned inside the cell can
+//      touch.  A fetch at texel-space coordinate xb = u*N - 0.5 reads texels floor(xb) and
+//      floor(xb)+1, so positions inside cell c (u*N in [cC, (c+1)C)) read texels cC-1 .. (c+1)C;
+//      one more texel on each side absorbs the float rounding of world -> texture coordinates.
+//      Texels outside the array read 0 (border addressing, VolumeReader.cpp:164-166), and the
+//      fixed-point filter weights are a convex combination, so every filtered value lies in
+//      [min, max] of that footprint.
+//   2. majorant grid: per cell, max TF opacity over the intensity interval [min,max]*densityScale,
+//      widened by one table entry on each side of the linear-filter footprint
+//      (cuda_volume.h:96, cuda_transfer_function.h:22-30; clamp addressing), answered in O(1) from a
+//      sparse range-max table over the TF's opacity column.
+// The boundary passes only a texture handle (cuda_volume.h:111-121); dims, format and voxels are
+// recovered with cudaGetTextureObjectResourceDesc -> cudaArrayGetInfo.
+#include <cstring>
+
+#include "svr_state.h"
+
+namespace svr {
+namespace {
+
+__global__ void range_kernel(cudaTextureObject_t pointTex, int3 vol, int3 grid, int cell, float2* out)
+{
+    int cx = blockIdx.x, cy = blockIdx.y, cz = blockIdx.z;
+    int R = cell + 4;  // [cC-2, (c+1)C+1]
+    int x0 = cx * cell - 2, y0 = cy * cell - 2, z0 = cz * cell - 2;
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    int total = R * R * R;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int x = i % R, y = (i / R) % R, z = i / (R * R);
+        // unnormalised point fetch at the texel centre; out-of-range reads the border value 0
+        float v = tex3D<float>(pointTex, (float)(x0 + x) + 0.5f, (float)(y0 + y) + 0.5f, (float)(z0 + z) + 0.5f);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ float smn[8], smx[8];
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        smn[w] = mn;
+        smx[w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nw = blockDim.x >> 5;
+        for (int i = 1; i < nw; ++i) {
+            mn = fminf(mn, smn[i]);
+            mx = fmaxf(mx, smx[i]);
+        }
+        out[((size_t)cz * grid.y + cy) * grid.x + cx] = make_float2(mn, mx);
+    }
+}
+
+// level l, entry i: max(opacity[i .. min(i + 2^l, n) - 1])
+__global__ void tf_sparse_kernel(const float4* table, int n, int levels, float* sparse)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sparse[i] = table[i].w;
+    __syncthreads();
+    for (int l = 1; l < levels; ++l) {
+        int half = 1 << (l - 1);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            float a = sparse[(l - 1) * n + i];
+            int j = i + half;
+            float b = j < n ? sparse[(l - 1) * n + j] : a;
+            sparse[l * n + i] = fmaxf(a, b);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void majorant_kernel(const float2* range, size_t cells, const float* sparse, int n, float densityScale,
+                                float* majorant)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    float2 r = range[i];
+    float a = r.x * densityScale, b = r.y * densityScale;
+    if (a > b) {
+        float t = a;
+        a = b;
+        b = t;
+    }
+    // linear-filter footprint of tex1D at x: entries floor(x*n - 0.5), +1 (clamped); widen by one
+    float fa = floorf(a * (float)n - 0.5f) - 1.f, fb = floorf(b * (float)n - 0.5f) + 2.f;
+    if (!(fa == fa)) fa = 0.f;                 // NaN voxels: cover the whole table
+    if (!(fb == fb)) fb = (float)(n - 1);
+    int lo = (int)fminf(fmaxf(fa, 0.f), (float)(n - 1));
+    int hi = (int)fminf(fmaxf(fb, 0.f), (float)(n - 1));
+    int len = hi - lo + 1;
+    int k = 31 - __clz(len);
+    float m = fmaxf(sparse[k * n + lo], sparse[k * n + hi - (1 << k) + 1]);
+    majorant[i] = fmaxf(m, 0.f);
+}
+
+}  // namespace
+
+int ensure_grid(DevScene* scene, bool force)
+{
+    HostState& st = state();
+    const svr_volume& vol = scene->vol;
+    const svr_transfer_function& tf = scene->tf;
+    if (!vol.tex || !tf.tex) return fail_msg("ensure_grid: volume or transfer function texture is not set");
+
+    cudaResourceDesc vrd, trd;
+    SVR_TRY(cudaGetTextureObjectResourceDesc(&vrd, vol.tex));
+    SVR_TRY(cudaGetTextureObjectResourceDesc(&trd, tf.tex));
+    if (vrd.resType != cudaResourceTypeArray || trd.resType != cudaResourceTypeArray)
+        return fail_msg("ensure_grid: textures must be bound to cudaArrays");
+    cudaArray_t varr = vrd.res.array.array, tarr = trd.res.array.array;
+
+    const int cell = st.options[SVR_OPT_MACROCELL_SIZE];
+    if (varr != st.gridArray || cell != st.gridCell || !st.dRange) {
+        // ---- stage 1: range grid
+        cudaChannelFormatDesc ch;
+        cudaExtent ext;
+        unsigned int flags = 0;
+        SVR_TRY(cudaArrayGetInfo(&ch, &ext, &flags, varr));
+        if (ext.depth == 0) return fail_msg("ensure_grid: volume array is not 3-D");
+        if (st.volPointTex) cudaDestroyTextureObject(st.volPointTex);
+        st.volPointTex = 0;
+        cudaFree(st.dRange);
+        cudaFree(st.dMajorant);
+        st.dRange = nullptr;
+        st.dMajorant = nullptr;
+        st.gridArray = nullptr;
+
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = (ch.f == cudaChannelFormatKindFloat) ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 0;
+        SVR_TRY(cudaCreateTextureObject(&st.volPointTex, &vrd, &td, nullptr));
+
+        st.volDims = make_int3((int)ext.width, (int)ext.height, (int)ext.depth);
+        st.gridDims = make_int3((st.volDims.x + cell - 1) / cell, (st.volDims.y + cell - 1) / cell,
+                                (st.volDims.z + cell - 1) / cell);
+        size_t cells = (size_t)st.gridDims.x * st.gridDims.y * st.gridDims.z;
+        SVR_TRY(cudaMalloc(&st.dRange, cells * sizeof(float2)));
+        SVR_TRY(cudaMalloc(&st.dMajorant, cells * sizeof(float)));
+        dim3 g(st.gridDims.x, st.gridDims.y, st.gridDims.z);
+        int threads = cell >= 8 ? 128 : 64;
+        range_kernel<<<g, threads, 0, st.stream>>>(st.volPointTex, st.volDims, st.gridDims, cell, st.dRange);
+        count_launch();
+        SVR_TRY(cudaGetLastError());
+        st.gridArray = varr;
+        st.gridCell = cell;
+        st.majorantValid = false;
+    }
+
+    if (force || !st.majorantValid || st.majorantDensityScale != vol.densityScale || st.majorantTfArray != tarr) {
+        // ---- stage 2: majorants from (range, TF, densityScale)
+        cudaChannelFormatDesc ch;
+        cudaExtent ext;
+        unsigned int flags = 0;
+        SVR_TRY(cudaArrayGetInfo(&ch, &ext, &flags, tarr));
+        int n = (int)ext.width;
+        if (n < 2 || ch.x != 32 || ch.w != 32) return fail_msg("ensure_grid: transfer function must be a 1-D float4 array");
+        int levels = 32 - __builtin_clz((unsigned)n);
+        if (n != st.tfEntries) {
+            cudaFree(st.dTfSparse);
+            cudaFree(st.dTfTable);
+            st.dTfSparse = nullptr;
+            st.dTfTable = nullptr;
+            SVR_TRY(cudaMalloc(&st.dTfTable, (size_t)n * sizeof(float4)));
+            SVR_TRY(cudaMalloc(&st.dTfSparse, (size_t)levels * n * sizeof(float)));
+            st.tfEntries = n;
+        }
+        SVR_TRY(cudaMemcpy2DFromArrayAsync(st.dTfTable, (size_t)n * sizeof(float4), tarr, 0, 0, (size_t)n * sizeof(float4), 1,
+                                           cudaMemcpyDeviceToDevice, st.stream));
+        tf_sparse_kernel<<<1, 1024, 0, st.stream>>>(st.dTfTable, n, levels, st.dTfSparse);
+        size_t cells = (size_t)st.gridDims.x * st.gridDims.y * st.gridDims.z;
+        majorant_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st.stream>>>(st.dRange, cells, st.dTfSparse, n,
+                                                                                vol.densityScale, st.dMajorant);
+        count_launch(2);
+        SVR_TRY(cudaGetLastError());
+        st.majorantValid = true;
+        st.majorantDensityScale = vol.densityScale;
+        st.majorantTfArray = tarr;
+    }
+
+    scene->volDim = st.volDims;
+    scene->grid.majorant = st.dMajorant;
+    scene->grid.range = st.dRange;
+    scene->grid.gx = st.gridDims.x;
+    scene->grid.gy = st.gridDims.y;
+    scene->grid.gz = st.gridDims.z;
+    scene->grid.cell = st.gridCell;
+    scene->grid.scale = f3((float)st.volDims.x / (float)st.gridCell, (float)st.volDims.y / (float)st.gridCell,
+                           (float)st.volDims.z / (float)st.gridCell);
+    return 0;
+}
+
+}  // namespace svr

@@ -1,0 +1,117 @@
+// svr_rng.cuh -- the two random streams of the path tracer.
+//
+//  * XorwowCompat reproduces what the reference draws: curand_init(wangHash(frameNo) + pixelOffset,
+//    0, 0) followed by curand_uniform (pathtracer.cu:70-79, 205-206, 302).  With subsequence 0 and
+//    offset 0 cuRAND performs no skip-ahead, so the state is a closed form of the seed; only the
+//    six state words are kept (cuRAND's 48-byte state also carries Box-Muller fields).
+//  * Philox is the product stream: Philox2x32-10 (Salmon et al., SC'11), counter = (draw block,
+//    sample index), key = f(pixel, seed).  A path is a pure function of (seed, pixel, sample), so an
+//    image does not depend on launch shape, on how samples are batched, or on how they are split
+//    across GPUs.
+#pragma once
+
+#include "svr_math.cuh"
+
+namespace svr {
+
+SVR_HD uint32_t wang_hash(uint32_t a)  // pathtracer.cu:70-79
+{
+    a = (a ^ 61u) ^ (a >> 16);
+    a = a + (a << 3);
+    a = a ^ (a >> 4);
+    a = a * 0x27d4eb2du;
+    a = a ^ (a >> 15);
+    return a;
+}
+
+struct XorwowCompat {
+    uint32_t v0, v1, v2, v3, v4, d;
+
+    // stream for (frame, pixel): seed = wangHash(frameNo) + offset, as kernel_pathtracer seeds it
+    SVR_DEV void init(uint32_t /*seedKey*/, uint32_t pixel, uint32_t sample)
+    {
+        uint32_t seed = wang_hash(sample) + pixel;
+        uint32_t s0 = seed ^ 0xaad26b49u;
+        uint32_t s1 = 0xf7dcefddu;  // high seed word is zero
+        uint32_t t0 = 1099087573u * s0;
+        uint32_t t1 = 2591861531u * s1;
+        d = 6615241u + t1 + t0;
+        v0 = 123456789u + t0;
+        v1 = 362436069u ^ t0;
+        v2 = 521288629u + t1;
+        v3 = 88675123u ^ t1;
+        v4 = 5783321u + t0;
+    }
+    SVR_DEV uint32_t next_u32()
+    {
+        uint32_t t = v0 ^ (v0 >> 2);
+        v0 = v1;
+        v1 = v2;
+        v2 = v3;
+        v3 = v4;
+        v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
+        d += 362437u;
+        return v4 + d;
+    }
+    // curand_uniform: (0, 1]
+    SVR_DEV float next() { return (float)next_u32() * 2.3283064e-10f + (2.3283064e-10f / 2.0f); }
+    // 1 - u as the reference computes it before logf
+    SVR_DEV float next_one_minus() { return 1.f - next(); }
+};
+
+struct Philox {
+    uint32_t key, sample, block;
+    uint32_t r1;   // second word of the current block
+    uint32_t have; // 1 = r1 not yet consumed
+
+    static constexpr uint32_t M = 0xD256D193u;  // Philox2x32 multiplier
+    static constexpr uint32_t W = 0x9E3779B9u;  // Weyl key increment
+
+    SVR_DEV void init(uint32_t seedKey, uint32_t pixel, uint32_t sample_)
+    {
+        key = pixel * 0x9E3779B1u + seedKey;  // bijective in pixel for a fixed seed
+        sample = sample_;
+        block = 0;
+        have = 0;
+        r1 = 0;
+    }
+    SVR_DEV void generate(uint32_t& o0, uint32_t& o1)
+    {
+        uint32_t c0 = block++, c1 = sample, k = key;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            uint32_t hi = __umulhi(M, c0);
+            uint32_t lo = M * c0;
+            c0 = hi ^ k ^ c1;
+            c1 = lo;
+            k += W;
+        }
+        o0 = c0;
+        o1 = c1;
+    }
+    SVR_DEV uint32_t next_u32()
+    {
+        if (have) {
+            have = 0;
+            return r1;
+        }
+        uint32_t a;
+        generate(a, r1);
+        have = 1;
+        return a;
+    }
+    // [0, 1): 24 random mantissa bits
+    SVR_DEV float next() { return (float)(next_u32() >> 8) * 5.9604645e-8f; }
+    // (0, 1]
+    SVR_DEV float next_one_minus() { return 1.f - next(); }
+    // two fresh uniforms from one block (drops a buffered word so call sites stay convergent)
+    SVR_DEV void next2(float& a, float& b)
+    {
+        uint32_t x, y;
+        generate(x, y);
+        a = (float)(x >> 8) * 5.9604645e-8f;
+        b = (float)(y >> 8) * 5.9604645e-8f;
+    }
+};
+
+}  // namespace svr

@@ -1,0 +1,73 @@
+// svr_state.h -- host-side state shared by the translation units of libsvr_b200.so.
+//
+// Like the reference (one set of __constant__ scene PODs per process, pathtracer.cu:34-68) the
+// library holds ONE scene per process and is not re-entrant; all work is issued on one stream.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "../../include/svr_render.h"
+#include "svr_scene.cuh"
+
+namespace svr {
+
+struct HostState {
+    cudaStream_t stream = nullptr;
+    DevScene scene;  // what setup_* stored (zero-initialised in state())
+    int options[SVR_OPT_COUNT_];
+
+    // macrocell cache -- callee-owned derived data, keyed on the caller's cudaArray handle
+    cudaArray_t gridArray = nullptr;      // volume array the range grid was built from
+    int gridCell = 0;
+    int3 gridDims = {0, 0, 0};
+    int3 volDims = {0, 0, 0};
+    float2* dRange = nullptr;
+    float* dMajorant = nullptr;
+    float* dTfSparse = nullptr;           // range-max sparse table over the TF opacity
+    float4* dTfTable = nullptr;           // linear copy of the TF array
+    int tfEntries = 0;
+    cudaTextureObject_t volPointTex = 0;  // point-sampled view of gridArray
+    bool majorantValid = false;           // false after setup_volume/setup_transferfunction
+    float majorantDensityScale = 0.f;
+    cudaArray_t majorantTfArray = nullptr;
+
+    Counters* dCounters = nullptr;
+    unsigned long long launches = 0;
+    std::string lastError;
+};
+
+HostState& state();
+
+// Part-1 error convention, utils/helper_cuda.h:967-981: print, cudaDeviceReset, exit(EXIT_FAILURE)
+inline void check_fatal(cudaError_t e, const char* what, const char* file, int line)
+{
+    if (e != cudaSuccess) {
+        fprintf(stderr, "CUDA error at %s:%d code=%d(%s) \"%s\" \n", file, line, (int)e, cudaGetErrorName(e), what);
+        cudaDeviceReset();
+        exit(EXIT_FAILURE);
+    }
+}
+#define SVR_FATAL(x) ::svr::check_fatal((x), #x, __FILE__, __LINE__)
+
+// Part-2 error convention: record the text, return non-zero
+int fail(const char* where, cudaError_t e);
+int fail_msg(const char* msg);
+#define SVR_TRY(x)                                             \
+    do {                                                       \
+        cudaError_t e_ = (x);                                  \
+        if (e_ != cudaSuccess) return ::svr::fail(#x, e_);     \
+    } while (0)
+
+// Builds / refreshes the macrocell grid for (vol, tf) and fills scene->grid, scene->volDim.
+// `force` rebuilds the majorants even when the cache key matches (ray caster: the TF content can
+// change behind an unchanged handle, gui/transferfunction.cpp:128-151).
+int ensure_grid(DevScene* scene, bool force);
+
+inline void count_launch(int n = 1) { state().launches += (unsigned long long)n; }
+
+}  // namespace svr

@@ -1,0 +1,200 @@
+"""Python host side of the render path: a thin mirror of what gui/canvas.cpp does with the seven
+entry points (SetUp* -> setup_*, paintGL -> render_*), on top of the C ABI.  torch is used only for
+device buffers, streams and torch.distributed; every pixel is produced by libsvr_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import scene as S
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Renderer:
+    """One scene on one GPU (the library, like the reference, holds one scene per process)."""
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sunvolumerender_b200 needs a CUDA device; there is no CPU path")
+        self.lib = L.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        L.check(self.lib.svr_set_device(device), "svr_set_device")
+        self.sync_stream()
+        self.volume = None
+        self.tf = None
+        self.camera = None
+        self.env = None
+        self.lights = []
+        self.hdr = None
+        self.img = None
+        self.frame_no = 0
+
+    # ---- plumbing
+    def sync_stream(self):
+        L.check(self.lib.svr_set_stream(C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "svr_set_stream")
+
+    def set_option(self, key, value):
+        L.check(self.lib.svr_set_option(key, int(value)), "svr_set_option")
+
+    def get_option(self, key):
+        return self.lib.svr_get_option(key)
+
+    def counters(self, reset=False):
+        buf = (C.c_uint64 * 16)()
+        L.check(self.lib.svr_counters_read(buf, 16), "svr_counters_read")
+        out = {name: int(buf[i]) for i, name in enumerate(L.CNT_NAMES)}
+        if reset:
+            L.check(self.lib.svr_counters_reset(), "svr_counters_reset")
+        return out
+
+    def reset_counters(self):
+        L.check(self.lib.svr_counters_reset(), "svr_counters_reset")
+
+    def launch_count(self):
+        return int(self.lib.svr_launch_count())
+
+    # ---- resources (VolumeReader / TransferFunction / Lights stand-ins)
+    def generate_volume(self, kind, fmt, n, seed=1234):
+        """Synthetic volume in device memory (x fastest), as a torch uint8 byte tensor."""
+        nbytes = n * n * n * L.VOXEL_BYTES[fmt]
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        L.check(self.lib.svr_generate_volume(_ptr(buf), kind, fmt, n, seed), "svr_generate_volume")
+        return buf
+
+    def load_volume(self, data, fmt, dims, spacing=(1.0, 1.0, 1.0), max_grad_mag=0.0):
+        """Canvas::LoadVolume: upload voxels (host numpy array or device byte tensor), bind the
+        texture, publish with setup_volume (gui/canvas.cpp:27-41)."""
+        self.free_volume()
+        vol = L.Volume()
+        nx, ny, nz = dims
+        if isinstance(data, torch.Tensor):
+            on_device = 1 if data.is_cuda else 0
+            ptr = _ptr(data)
+        else:
+            data = np.ascontiguousarray(data)
+            on_device = 0
+            ptr = C.c_void_p(data.ctypes.data)
+        L.check(
+            self.lib.svr_volume_create(C.byref(vol), ptr, on_device, fmt, nx, ny, nz, spacing[0], spacing[1], spacing[2], max_grad_mag),
+            "svr_volume_create",
+        )
+        self.volume = vol
+        self.lib.setup_volume(C.byref(vol))
+        return vol
+
+    def free_volume(self):
+        if self.volume is not None:
+            L.check(self.lib.svr_volume_destroy(C.byref(self.volume)), "svr_volume_destroy")
+            self.volume = None
+
+    def set_volume_params(self, density_scale=None, gradient_factor=None, x_clip=None, y_clip=None, z_clip=None):
+        """Canvas::SetDensityScale / SetGradientFactor / Set?ClipPlane (gui/canvas.h:49-175)."""
+        v = self.volume
+        if density_scale is not None:
+            v.densityScale = density_scale
+        if gradient_factor is not None:
+            v.gradientFactor = gradient_factor
+        if x_clip is not None:
+            v.x_clip = L.Vec2(*x_clip)
+        if y_clip is not None:
+            v.y_clip = L.Vec2(*y_clip)
+        if z_clip is not None:
+            v.z_clip = L.Vec2(*z_clip)
+        self.lib.setup_volume(C.byref(v))
+        self.frame_no = 0
+
+    def set_transfer_function(self, table):
+        table = np.ascontiguousarray(table, dtype=np.float32)
+        if self.tf is not None:
+            L.check(self.lib.svr_tf_destroy(C.byref(self.tf)), "svr_tf_destroy")
+        tf = L.TransferFunction()
+        L.check(self.lib.svr_tf_create(C.byref(tf), C.c_void_p(table.ctypes.data), table.shape[0]), "svr_tf_create")
+        self.tf = tf
+        self.lib.setup_transferfunction(C.byref(tf))
+        self.frame_no = 0
+        return tf
+
+    def set_camera(self, cam):
+        if self.camera is None or (cam.imageW, cam.imageH) != (self.camera.imageW, self.camera.imageH):
+            # RenderParams::SetupHDRBuffer (core/render_parameters.h:17-23) + the PBO of gui/canvas.cpp:50-55
+            self.hdr = torch.zeros(cam.imageH * cam.imageW * 3, dtype=torch.float32, device=self.device)
+            self.img = torch.zeros(cam.imageH * cam.imageW * 4, dtype=torch.uint8, device=self.device)
+        self.camera = cam
+        self.lib.setup_camera(C.byref(cam))
+        self.frame_no = 0
+
+    def set_area_lights(self, lights):
+        self.lights = list(lights)
+        arr = (L.AreaLight * max(1, len(self.lights)))(*self.lights)
+        self.lib.setup_area_lights(arr, len(self.lights))
+        self.frame_no = 0
+
+    def set_env_light(self, env, enabled=True):
+        self.env = env
+        self.lib.setup_env_lights(C.byref(env))
+        self.set_option(L.OPT_ENV_ENABLED, 1 if enabled else 0)
+        self.frame_no = 0
+
+    # ---- rendering
+    def render_pathtracer(self, trace_depth=1):
+        """One reference-style frame: one sample per pixel, frame counter advanced by the caller
+        (gui/canvas.cpp:96,116)."""
+        rp = L.RenderParams(trace_depth, self.frame_no, self.hdr.data_ptr())
+        self.lib.render_pathtracer(_ptr(self.img), C.byref(rp))
+        self.frame_no += 1
+
+    def render_pathtracer_spp(self, spp, trace_depth=1, tonemap=True):
+        rp = L.RenderParams(trace_depth, self.frame_no, self.hdr.data_ptr())
+        L.check(self.lib.svr_render_pathtracer_spp(_ptr(self.img if tonemap else None), C.byref(rp), spp), "svr_render_pathtracer_spp")
+        self.frame_no += spp
+
+    def accumulate(self, sum_buf, trace_depth, first_sample, n_samples, clear=True):
+        L.check(self.lib.svr_pathtracer_accumulate(_ptr(sum_buf), trace_depth, first_sample, n_samples, 1 if clear else 0), "svr_pathtracer_accumulate")
+
+    def resolve(self, sum_buf, want_hdr=True):
+        L.check(self.lib.svr_pathtracer_resolve(_ptr(self.img), _ptr(self.hdr if want_hdr else None), _ptr(sum_buf)), "svr_pathtracer_resolve")
+
+    def render_raycasting(self, step_size=None):
+        if step_size is None:
+            step_size = S.raycast_step_size(self.volume.spacing.tuple())
+        self.lib.render_raycasting(_ptr(self.img), C.byref(self.volume), C.byref(self.tf), C.byref(self.camera), step_size)
+
+    def render_raycasting_f32(self, out, step_size=None, rows=None, img=None):
+        if step_size is None:
+            step_size = S.raycast_step_size(self.volume.spacing.tuple())
+        y0, y1 = rows if rows is not None else (0, self.camera.imageH)
+        L.check(
+            self.lib.svr_render_raycasting_rows(_ptr(img), _ptr(out), C.byref(self.volume), C.byref(self.tf), C.byref(self.camera), step_size, y0, y1),
+            "svr_render_raycasting_rows",
+        )
+
+    # ---- results
+    def hdr_image(self):
+        return self.hdr.view(self.camera.imageH, self.camera.imageW, 3)
+
+    def ldr_image(self):
+        return self.img.view(self.camera.imageH, self.camera.imageW, 4)
+
+    def close(self):
+        self.free_volume()
+        if self.tf is not None:
+            self.lib.svr_tf_destroy(C.byref(self.tf))
+            self.tf = None
+
+
+def setup_config(r, cfg, volume_bytes=None):
+    """Populate a Renderer with one of the BASELINE.json configurations (scene.CONFIGS)."""
+    if volume_bytes is None:
+        volume_bytes = r.generate_volume(cfg.gen, cfg.fmt, cfg.n, cfg.gen_seed)
+    r.load_volume(volume_bytes, cfg.fmt, (cfg.n,) * 3)
+    r.set_transfer_function(S.tf_table(cfg.tf))
+    r.set_camera(S.default_camera(cfg.extent, cfg.width, cfg.height))
+    r.set_area_lights([S.default_area_light(cfg.extent)])
+    r.set_env_light(S.constant_env_light(), enabled=cfg.env)
+    return volume_bytes
