@@ -167,6 +167,18 @@ uint64_t svr_launch_count(void);
 int svr_microbench_taps(const svr_volume* vol, int random, uint32_t threads, uint32_t taps_per_thread,
                         float* dev_sink, uint64_t* host_taps);
 
+/* ---- inspection hooks (used by the parity tests; cheap, never on the render path) ---- */
+/* Raw fetches through the caller's texture objects, exactly as the kernels issue them:
+ * out[i] = tex3D<float>(vol->tex, uvw[3i], uvw[3i+1], uvw[3i+2]) (normalised coordinates, before
+ * densityScale); rgba[4i..] = tex1D<float4>(tf->tex, x[i]).  All pointers are device pointers. */
+int svr_debug_sample_volume(const svr_volume* vol, const float* dev_uvw, uint32_t n, float* dev_out);
+int svr_debug_sample_tf(const svr_transfer_function* tf, const float* dev_x, uint32_t n, float* dev_rgba);
+/* Macrocell grid built for the scene of the last render call: dims[3] = cells per axis, *cell = edge
+ * in voxels.  svr_grid_copy copies majorants (dims[0]*dims[1]*dims[2] floats, x fastest) and/or
+ * the (min,max) intensity ranges (2 floats per cell) to HOST memory; either may be NULL. */
+int svr_grid_info(int32_t* dims, int32_t* cell);
+int svr_grid_copy(float* host_majorant, float* host_range);
+
 #ifdef __cplusplus
 }
 #endif

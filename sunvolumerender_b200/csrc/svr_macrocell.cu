@@ -200,3 +200,63 @@ int ensure_grid(DevScene* scene, bool force)
 }
 
 }  // namespace svr
+
+// ------------------------------------------------------------------------------------------------
+// inspection hooks
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void sample_volume_kernel(cudaTextureObject_t tex, const float* uvw, uint32_t n, float* out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tex3D<float>(tex, uvw[3 * i], uvw[3 * i + 1], uvw[3 * i + 2]);
+}
+__global__ void sample_tf_kernel(cudaTextureObject_t tex, const float* x, uint32_t n, float4* out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tex1D<float4>(tex, x[i]);
+}
+}  // namespace
+
+extern "C" int svr_debug_sample_volume(const svr_volume* vol, const float* dev_uvw, uint32_t n, float* dev_out)
+{
+    if (!vol || !vol->tex || !dev_uvw || !dev_out) return svr::fail_msg("svr_debug_sample_volume: bad argument");
+    if (!n) return 0;
+    sample_volume_kernel<<<(n + 255u) / 256u, 256, 0, svr::state().stream>>>(vol->tex, dev_uvw, n, dev_out);
+    svr::count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svr_debug_sample_tf(const svr_transfer_function* tf, const float* dev_x, uint32_t n, float* dev_rgba)
+{
+    if (!tf || !tf->tex || !dev_x || !dev_rgba) return svr::fail_msg("svr_debug_sample_tf: bad argument");
+    if (!n) return 0;
+    sample_tf_kernel<<<(n + 255u) / 256u, 256, 0, svr::state().stream>>>(tf->tex, dev_x, n, (float4*)dev_rgba);
+    svr::count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svr_grid_info(int32_t* dims, int32_t* cell)
+{
+    svr::HostState& st = svr::state();
+    if (!st.dRange) return svr::fail_msg("svr_grid_info: no grid has been built yet");
+    if (dims) {
+        dims[0] = st.gridDims.x;
+        dims[1] = st.gridDims.y;
+        dims[2] = st.gridDims.z;
+    }
+    if (cell) *cell = st.gridCell;
+    return 0;
+}
+
+extern "C" int svr_grid_copy(float* host_majorant, float* host_range)
+{
+    svr::HostState& st = svr::state();
+    if (!st.dRange || !st.dMajorant) return svr::fail_msg("svr_grid_copy: no grid has been built yet");
+    size_t cells = (size_t)st.gridDims.x * st.gridDims.y * st.gridDims.z;
+    SVR_TRY(cudaStreamSynchronize(st.stream));
+    if (host_majorant) SVR_TRY(cudaMemcpy(host_majorant, st.dMajorant, cells * sizeof(float), cudaMemcpyDeviceToHost));
+    if (host_range) SVR_TRY(cudaMemcpy(host_range, st.dRange, cells * sizeof(float2), cudaMemcpyDeviceToHost));
+    return 0;
+}
