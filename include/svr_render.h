@@ -85,6 +85,12 @@ enum svr_option {
     /* threads per block of the path tracer / ray caster (tuning) */
     SVR_OPT_PT_BLOCK = 7,
     SVR_OPT_RC_BLOCK = 8,
+    /* path-tracer kernel shape: 0 = per-lane state machine (generate / track / event phases run
+     * convergently across the warp; default), 1 = megakernel (the reference's loop nest) */
+    SVR_OPT_PT_KERNEL = 9,
+    /* state machine: tracking rounds between two event phases; 0 = track until every lane of the
+     * warp has an event */
+    SVR_OPT_PT_ROUNDS = 10,
     SVR_OPT_COUNT_
 };
 int svr_set_option(int key, int value);

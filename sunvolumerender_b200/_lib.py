@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvr_b200.so")
+# SVR_B200_LIB selects an alternative build of the same library (A/B experiments with compiler flags)
+LIB_PATH = os.environ.get("SVR_B200_LIB") or os.path.join(_HERE, "libsvr_b200.so")
 
 
 class Vec2(C.Structure):
@@ -96,7 +97,8 @@ assert C.sizeof(EnvLight) == 32 and EnvLight.intensity.offset == 20
 assert C.sizeof(RenderParams) == 16 and RenderParams.hdrBuffer.offset == 8
 
 # enum svr_option
-OPT_PT_MODE, OPT_SHADOW_ESTIMATOR, OPT_ENV_ENABLED, OPT_MACROCELL_SIZE, OPT_RC_SKIP, OPT_SEED, OPT_COUNTERS, OPT_PT_BLOCK, OPT_RC_BLOCK = range(9)
+(OPT_PT_MODE, OPT_SHADOW_ESTIMATOR, OPT_ENV_ENABLED, OPT_MACROCELL_SIZE, OPT_RC_SKIP, OPT_SEED, OPT_COUNTERS,
+ OPT_PT_BLOCK, OPT_RC_BLOCK, OPT_PT_KERNEL, OPT_PT_ROUNDS) = range(11)
 # enum svr_voxel_format
 VOXEL_U8, VOXEL_U16, VOXEL_F16, VOXEL_F32 = range(4)
 VOXEL_BYTES = {VOXEL_U8: 1, VOXEL_U16: 2, VOXEL_F16: 2, VOXEL_F32: 4}

@@ -51,8 +51,11 @@ static void release_grid(HostState& st)
     st.volPointTex = 0;
     cudaFree(st.dRange);
     cudaFree(st.dMajorant);
+    cudaFree(st.dDist[0]);
+    cudaFree(st.dDist[1]);
     st.dRange = nullptr;
     st.dMajorant = nullptr;
+    st.dDist[0] = st.dDist[1] = nullptr;
     st.gridArray = nullptr;
     st.majorantValid = false;
 }
@@ -147,6 +150,12 @@ extern "C" int svr_set_option(int key, int value)
         case SVR_OPT_PT_BLOCK:
         case SVR_OPT_RC_BLOCK:
             if (value != 64 && value != 128 && value != 256) return fail_msg("block size must be 64, 128 or 256");
+            break;
+        case SVR_OPT_PT_KERNEL:
+            if (value != 0 && value != 1) return fail_msg("SVR_OPT_PT_KERNEL must be 0 or 1");
+            break;
+        case SVR_OPT_PT_ROUNDS:
+            if (value < 0) return fail_msg("SVR_OPT_PT_ROUNDS must be >= 0");
             break;
         default: break;
     }

@@ -14,6 +14,11 @@
 //      widened by one table entry on each side of the linear-filter footprint
 //      (cuda_volume.h:96, cuda_transfer_function.h:22-30; clamp addressing), answered in O(1) from a
 //      sparse range-max table over the TF's opacity column.
+//   3. empty-space distances: every cell whose majorant is 0 stores -(Chebyshev distance, in cells,
+//      to the nearest cell with a non-zero majorant), capped at SVR_LEAP_CAP+1.  A ray inside such a
+//      cell can leap to the boundary of the cube of radius distance-1 around it without a single
+//      fetch (Cohen & Sheffer's proximity clouds on the macrocell grid).  One float per cell carries
+//      both: > 0 majorant, < 0 minus the leap distance.
 // The boundary passes only a texture handle (cuda_volume.h:111-121); dims, format and voxels are
 // recovered with cudaGetTextureObjectResourceDesc -> cudaArrayGetInfo.
 #include <cstring>
@@ -88,8 +93,12 @@ __global__ void majorant_kernel(const float2* range, size_t cells, const float* 
         a = b;
         b = t;
     }
-    // linear-filter footprint of tex1D at x: entries floor(x*n - 0.5), +1 (clamped); widen by one
-    float fa = floorf(a * (float)n - 0.5f) - 1.f, fb = floorf(b * (float)n - 0.5f) + 2.f;
+    // linear-filter footprint of tex1D at x: entries floor(x*n - 0.5) and +1 (clamped).  The unit
+    // converts x*n - 0.5 to fixed point with 8 fractional bits, so widen the interval by 2/256 of an
+    // entry; a coordinate rounded onto an entry boundary gives the entry beyond it weight 0.
+    // (Widening by whole entries would make air, intensity exactly 0, inherit the opacity of
+    // entry 1 and never be empty.)
+    float fa = floorf(a * (float)n - 0.5f - 0.0078125f), fb = floorf(b * (float)n - 0.5f + 0.0078125f) + 1.f;
     if (!(fa == fa)) fa = 0.f;                 // NaN voxels: cover the whole table
     if (!(fb == fb)) fb = (float)(n - 1);
     int lo = (int)fminf(fmaxf(fa, 0.f), (float)(n - 1));
@@ -98,6 +107,51 @@ __global__ void majorant_kernel(const float2* range, size_t cells, const float* 
     int k = 31 - __clz(len);
     float m = fmaxf(sparse[k * n + lo], sparse[k * n + hi - (1 << k) + 1]);
     majorant[i] = fmaxf(m, 0.f);
+}
+
+#define SVR_LEAP_CAP 15
+
+__global__ void dist_init_kernel(const float* majorant, size_t cells, uint8_t* dist)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cells) dist[i] = majorant[i] > 0.f ? 0 : 255;
+}
+
+// one Chebyshev dilation step: d'(c) = min(d(c), min over the 26 neighbours d + 1)
+__global__ void dist_pass_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int gx, int gy, int gz)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+    if (x >= gx || y >= gy) return;
+    size_t i = ((size_t)z * gy + y) * gx + x;
+    int best = src[i];
+    if (best != 0) {
+        int nb = 255;
+        for (int dz = -1; dz <= 1; ++dz) {
+            int zz = z + dz;
+            if (zz < 0 || zz >= gz) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                int yy = y + dy;
+                if (yy < 0 || yy >= gy) continue;
+                const uint8_t* row = src + ((size_t)zz * gy + yy) * gx;
+                for (int dx = -1; dx <= 1; ++dx) {
+                    int xx = x + dx;
+                    if (xx < 0 || xx >= gx) continue;
+                    nb = min(nb, (int)row[xx]);
+                }
+            }
+        }
+        if (nb < 255) best = min(best, nb + 1);
+    }
+    dst[i] = (uint8_t)best;
+}
+
+// empty cells: majorant <- -(leap distance)
+__global__ void dist_store_kernel(const uint8_t* dist, size_t cells, float* majorant)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    int d = dist[i];
+    if (d > 0) majorant[i] = -(float)min(d, SVR_LEAP_CAP + 1);
 }
 
 }  // namespace
@@ -128,8 +182,11 @@ int ensure_grid(DevScene* scene, bool force)
         st.volPointTex = 0;
         cudaFree(st.dRange);
         cudaFree(st.dMajorant);
+        cudaFree(st.dDist[0]);
+        cudaFree(st.dDist[1]);
         st.dRange = nullptr;
         st.dMajorant = nullptr;
+        st.dDist[0] = st.dDist[1] = nullptr;
         st.gridArray = nullptr;
 
         cudaTextureDesc td;
@@ -146,6 +203,8 @@ int ensure_grid(DevScene* scene, bool force)
         size_t cells = (size_t)st.gridDims.x * st.gridDims.y * st.gridDims.z;
         SVR_TRY(cudaMalloc(&st.dRange, cells * sizeof(float2)));
         SVR_TRY(cudaMalloc(&st.dMajorant, cells * sizeof(float)));
+        SVR_TRY(cudaMalloc(&st.dDist[0], cells));
+        SVR_TRY(cudaMalloc(&st.dDist[1], cells));
         dim3 g(st.gridDims.x, st.gridDims.y, st.gridDims.z);
         int threads = cell >= 8 ? 128 : 64;
         range_kernel<<<g, threads, 0, st.stream>>>(st.volPointTex, st.volDims, st.gridDims, cell, st.dRange);
@@ -180,7 +239,17 @@ int ensure_grid(DevScene* scene, bool force)
         size_t cells = (size_t)st.gridDims.x * st.gridDims.y * st.gridDims.z;
         majorant_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st.stream>>>(st.dRange, cells, st.dTfSparse, n,
                                                                                 vol.densityScale, st.dMajorant);
-        count_launch(2);
+        // ---- stage 3: leap distances for empty cells
+        const unsigned cb = (unsigned)((cells + 255) / 256);
+        dist_init_kernel<<<cb, 256, 0, st.stream>>>(st.dMajorant, cells, st.dDist[0]);
+        dim3 pb(32, 4, 1), pg((st.gridDims.x + 31) / 32, (st.gridDims.y + 3) / 4, st.gridDims.z);
+        int cur = 0;
+        for (int pass = 0; pass < SVR_LEAP_CAP; ++pass) {
+            dist_pass_kernel<<<pg, pb, 0, st.stream>>>(st.dDist[cur], st.dDist[cur ^ 1], st.gridDims.x, st.gridDims.y, st.gridDims.z);
+            cur ^= 1;
+        }
+        dist_store_kernel<<<cb, 256, 0, st.stream>>>(st.dDist[cur], cells, st.dMajorant);
+        count_launch(4 + SVR_LEAP_CAP);
         SVR_TRY(cudaGetLastError());
         st.majorantValid = true;
         st.majorantDensityScale = vol.densityScale;

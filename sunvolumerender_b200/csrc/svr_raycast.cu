@@ -52,11 +52,13 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ De
                     int cz = min(max((int)floorf(g.z), 0), s.grid.gz - 1);
                     float sig = __ldg(&s.grid.majorant[((size_t)cz * s.grid.gy + cy) * s.grid.gx + cx]);
                     lc.add(SVR_CNT_CELLS, 1);
-                    if (sig == 0.f) {
-                        // distance to the far faces of this cell along the ray
-                        float ex = ((dg.x > 0.f ? (float)(cx + 1) : (float)cx) - g.x) * invDg.x;
-                        float ey = ((dg.y > 0.f ? (float)(cy + 1) : (float)cy) - g.y) * invDg.y;
-                        float ez = ((dg.z > 0.f ? (float)(cz + 1) : (float)cz) - g.z) * invDg.z;
+                    if (sig <= 0.f) {
+                        // empty cell, and so is the cube of radius d-1 around it (svr_macrocell.cu stage 3):
+                        // distance to the far faces of that cube along the ray
+                        const int d = (int)(-sig) > 1 ? (int)(-sig) : 1;
+                        float ex = ((dg.x > 0.f ? (float)(cx + d) : (float)(cx - d + 1)) - g.x) * invDg.x;
+                        float ey = ((dg.y > 0.f ? (float)(cy + d) : (float)(cy - d + 1)) - g.y) * invDg.y;
+                        float ez = ((dg.z > 0.f ? (float)(cz + d) : (float)(cz - d + 1)) - g.z) * invDg.z;
                         float tExit = t + fminf(fminf(dg.x != 0.f ? ex : FLT_MAX, dg.y != 0.f ? ey : FLT_MAX),
                                                 dg.z != 0.f ? ez : FLT_MAX);
                         uint32_t skipped = 0;

@@ -28,6 +28,7 @@ struct HostState {
     int3 volDims = {0, 0, 0};
     float2* dRange = nullptr;
     float* dMajorant = nullptr;
+    uint8_t* dDist[2] = {nullptr, nullptr};  // ping-pong Chebyshev distance to the nearest non-empty cell
     float* dTfSparse = nullptr;           // range-max sparse table over the TF opacity
     float4* dTfTable = nullptr;           // linear copy of the TF array
     int tfEntries = 0;

@@ -1,5 +1,8 @@
-"""Short, fixed workload for ncu: `python tools/prof_run.py <pt|rc> <config> [mode] [spp] [reps]`.
-Sets up one BASELINE.json configuration and launches the chosen kernel a few times."""
+"""Short, fixed workload for ncu:
+    python tools/prof_run.py <pt|rc|ref> <config> [mode] [spp] [reps] [shape] [view]
+Sets up one BASELINE.json configuration and launches the chosen kernel a few times.  `ref` runs the
+reference's own kernels (oracle/_ref) on the same scene, for side-by-side profiles.  view = close
+moves the camera in so that the volume fills the frame."""
 import sys
 
 import torch
@@ -13,15 +16,30 @@ cfg = S.CONFIGS[sys.argv[2] if len(sys.argv) > 2 else "C3"]
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 spp = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+shape = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+view = sys.argv[7] if len(sys.argv) > 7 else "default"
 
 r = Renderer(0)
 setup_config(r, cfg)
+if view == "close":
+    cam = r.camera
+    r.set_camera(S.make_camera((0, 0, cam.pos.z * 0.45), (1, 0, 0), (0, 1, 0), (0, 0, 1), 45.0, 0.0, 1.0, 1.0, cfg.width, cfg.height))
 r.set_option(L.OPT_PT_MODE, mode)
-for _ in range(reps):
-    if what == "pt":
-        r.frame_no = 0
-        r.render_pathtracer_spp(spp, cfg.trace_depth)
-    else:
-        r.render_raycasting()
+r.set_option(L.OPT_PT_KERNEL, shape)
+if what == "ref":
+    from oracle import binding as B  # noqa: E402  (profiling aid, not a product path)
+
+    ref = B.RefCuda(cfg.width, cfg.height)
+    ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
+    for _ in range(reps):
+        ref.frame_no = 0
+        ref.render_pathtracer(spp, cfg.trace_depth)
+else:
+    for _ in range(reps):
+        if what == "pt":
+            r.frame_no = 0
+            r.render_pathtracer_spp(spp, cfg.trace_depth)
+        else:
+            r.render_raycasting()
 torch.cuda.synchronize()
 print("done", what, cfg.name, mode, spp, r.launch_count())
