@@ -85,12 +85,19 @@ enum svr_option {
     /* threads per block of the path tracer / ray caster (tuning) */
     SVR_OPT_PT_BLOCK = 7,
     SVR_OPT_RC_BLOCK = 8,
-    /* path-tracer kernel shape: 0 = per-lane state machine (generate / track / event phases run
-     * convergently across the warp; default), 1 = megakernel (the reference's loop nest) */
+    /* path-tracer kernel shape: 1 = megakernel (one path at a time per lane; default, measured
+     * fastest), 0 = phase-scheduled warp (generate / march / collide / event / bounce phases, the warp
+     * votes each round and runs the phase most lanes wait in) */
     SVR_OPT_PT_KERNEL = 9,
-    /* state machine: tracking rounds between two event phases; 0 = track until every lane of the
-     * warp has an event */
+    /* phase-scheduled kernel: macrocell visits per MARCH round (0 = default 4) */
     SVR_OPT_PT_ROUNDS = 10,
+    /* 1 (default) = empty macrocells record how far the empty space around them extends and rays
+     * leap over it; 0 = one cell at a time.  Images are bit-identical either way. */
+    SVR_OPT_LEAP = 11,
+    /* 1 (default) = each pixel finds once, along its centre ray, how far the camera rays of all its
+     * samples can be advanced through empty macrocells; 0 = every sample walks from the volume face.
+     * Images are bit-identical either way (only empty cells are skipped). */
+    SVR_OPT_PT_ENTRY_CACHE = 12,
     SVR_OPT_COUNT_
 };
 int svr_set_option(int key, int value);

@@ -25,6 +25,9 @@ HostState& state()
         p->options[SVR_OPT_COUNTERS] = 0;
         p->options[SVR_OPT_PT_BLOCK] = 128;
         p->options[SVR_OPT_RC_BLOCK] = 128;
+        p->options[SVR_OPT_PT_KERNEL] = 1;  // megakernel: measured 2.5x faster than the phase-scheduled shape (profiles/r01)
+        p->options[SVR_OPT_LEAP] = 1;
+        p->options[SVR_OPT_PT_ENTRY_CACHE] = 1;
         return p;
     }();
     return *s;
@@ -43,21 +46,6 @@ int fail_msg(const char* msg)
 {
     state().lastError = msg;
     return -1;
-}
-
-static void release_grid(HostState& st)
-{
-    if (st.volPointTex) cudaDestroyTextureObject(st.volPointTex);
-    st.volPointTex = 0;
-    cudaFree(st.dRange);
-    cudaFree(st.dMajorant);
-    cudaFree(st.dDist[0]);
-    cudaFree(st.dDist[1]);
-    st.dRange = nullptr;
-    st.dMajorant = nullptr;
-    st.dDist[0] = st.dDist[1] = nullptr;
-    st.gridArray = nullptr;
-    st.majorantValid = false;
 }
 
 }  // namespace svr

@@ -1,7 +1,7 @@
 // svr_macrocell.cu -- macrocell majorant grid (callee-owned derived data; the reference has none:
 // woodcock_tracking.h:28-30 uses the single global majorant tf.GetMaxOpacity()).
 //
-// Two stages, so that the expensive one runs once per volume and the cheap one on every
+// Stages, so that the expensive one runs once per volume and the cheap ones on every
 // transfer-function / density-scale edit:
 //   1. range grid : per cell, min/max of every texel a trilinear fetch positioned inside the cell can
 //      touch.  A fetch at texel-space coordinate xb = u*N - 0.5 reads texels floor(xb) and
@@ -10,18 +10,23 @@
 //      Texels outside the array read 0 (border addressing, VolumeReader.cpp:164-166), and the
 //      fixed-point filter weights are a convex combination, so every filtered value lies in
 //      [min, max] of that footprint.
-//   2. majorant grid: per cell, max TF opacity over the intensity interval [min,max]*densityScale,
-//      widened by one table entry on each side of the linear-filter footprint
+//   2. majorant grid: per cell, max TF opacity over the intensity interval [min,max]*densityScale
 //      (cuda_volume.h:96, cuda_transfer_function.h:22-30; clamp addressing), answered in O(1) from a
 //      sparse range-max table over the TF's opacity column.
 //   3. empty-space distances: every cell whose majorant is 0 stores -(Chebyshev distance, in cells,
 //      to the nearest cell with a non-zero majorant), capped at SVR_LEAP_CAP+1.  A ray inside such a
 //      cell can leap to the boundary of the cube of radius distance-1 around it without a single
-//      fetch (Cohen & Sheffer's proximity clouds on the macrocell grid).  One float per cell carries
-//      both: > 0 majorant, < 0 minus the leap distance.
+//      fetch (proximity clouds on the macrocell grid).  One float per cell carries both:
+//      > 0 majorant, < 0 minus the leap distance.
+//   4. occupied box: the bounding box, in cells, of the cells with a non-zero majorant; rays are
+//      clipped to it.
+// The majorant grid is stored with a one-cell empty border on every side so that a position-based
+// walk needs no clamping at the volume faces.
 // The boundary passes only a texture handle (cuda_volume.h:111-121); dims, format and voxels are
 // recovered with cudaGetTextureObjectResourceDesc -> cudaArrayGetInfo.
+#include <climits>
 #include <cstring>
+#include <vector>
 
 #include "svr_state.h"
 
@@ -81,12 +86,13 @@ __global__ void tf_sparse_kernel(const float4* table, int n, int levels, float* 
     }
 }
 
-__global__ void majorant_kernel(const float2* range, size_t cells, const float* sparse, int n, float densityScale,
-                                float* majorant)
+// padded majorant grid <- max TF opacity over each cell's intensity range; also grows the occupied box
+__global__ void majorant_kernel(const float2* range, int3 grid, const float* sparse, int n, float densityScale,
+                                float* padded, int* occ)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cells) return;
-    float2 r = range[i];
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+    if (x >= grid.x || y >= grid.y) return;
+    float2 r = range[((size_t)z * grid.y + y) * grid.x + x];
     float a = r.x * densityScale, b = r.y * densityScale;
     if (a > b) {
         float t = a;
@@ -99,17 +105,30 @@ __global__ void majorant_kernel(const float2* range, size_t cells, const float* 
     // (Widening by whole entries would make air, intensity exactly 0, inherit the opacity of
     // entry 1 and never be empty.)
     float fa = floorf(a * (float)n - 0.5f - 0.0078125f), fb = floorf(b * (float)n - 0.5f + 0.0078125f) + 1.f;
-    if (!(fa == fa)) fa = 0.f;                 // NaN voxels: cover the whole table
+    if (!(fa == fa)) fa = 0.f;  // NaN voxels: cover the whole table
     if (!(fb == fb)) fb = (float)(n - 1);
     int lo = (int)fminf(fmaxf(fa, 0.f), (float)(n - 1));
     int hi = (int)fminf(fmaxf(fb, 0.f), (float)(n - 1));
     int len = hi - lo + 1;
     int k = 31 - __clz(len);
-    float m = fmaxf(sparse[k * n + lo], sparse[k * n + hi - (1 << k) + 1]);
-    majorant[i] = fmaxf(m, 0.f);
+    float m = fmaxf(fmaxf(sparse[k * n + lo], sparse[k * n + hi - (1 << k) + 1]), 0.f);
+    int px = grid.x + 2, py = grid.y + 2;
+    padded[((size_t)(z + 1) * py + (y + 1)) * px + (x + 1)] = m;
+    if (m > 0.f) {
+        atomicMin(&occ[0], x);
+        atomicMin(&occ[1], y);
+        atomicMin(&occ[2], z);
+        atomicMax(&occ[3], x);
+        atomicMax(&occ[4], y);
+        atomicMax(&occ[5], z);
+    }
 }
 
-#define SVR_LEAP_CAP 15
+__global__ void occ_init_kernel(int* occ)
+{
+    if (threadIdx.x < 3) occ[threadIdx.x] = INT_MAX;
+    else if (threadIdx.x < 6) occ[threadIdx.x] = -1;
+}
 
 __global__ void dist_init_kernel(const float* majorant, size_t cells, uint8_t* dist)
 {
@@ -146,15 +165,32 @@ __global__ void dist_pass_kernel(const uint8_t* __restrict__ src, uint8_t* __res
 }
 
 // empty cells: majorant <- -(leap distance)
-__global__ void dist_store_kernel(const uint8_t* dist, size_t cells, float* majorant)
+__global__ void dist_store_kernel(const uint8_t* dist, size_t cells, float* majorant, int leap)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cells) return;
     int d = dist[i];
-    if (d > 0) majorant[i] = -(float)min(d, SVR_LEAP_CAP + 1);
+    if (d > 0) majorant[i] = leap ? -(float)min(d, SVR_LEAP_CAP + 1) : -1.f;
 }
 
 }  // namespace
+
+void release_grid(HostState& st)
+{
+    if (st.volPointTex) cudaDestroyTextureObject(st.volPointTex);
+    st.volPointTex = 0;
+    cudaFree(st.dRange);
+    cudaFree(st.dMajorant);
+    cudaFree(st.dDist[0]);
+    cudaFree(st.dDist[1]);
+    cudaFree(st.dOcc);
+    st.dRange = nullptr;
+    st.dMajorant = nullptr;
+    st.dDist[0] = st.dDist[1] = nullptr;
+    st.dOcc = nullptr;
+    st.gridArray = nullptr;
+    st.majorantValid = false;
+}
 
 int ensure_grid(DevScene* scene, bool force)
 {
@@ -178,16 +214,7 @@ int ensure_grid(DevScene* scene, bool force)
         unsigned int flags = 0;
         SVR_TRY(cudaArrayGetInfo(&ch, &ext, &flags, varr));
         if (ext.depth == 0) return fail_msg("ensure_grid: volume array is not 3-D");
-        if (st.volPointTex) cudaDestroyTextureObject(st.volPointTex);
-        st.volPointTex = 0;
-        cudaFree(st.dRange);
-        cudaFree(st.dMajorant);
-        cudaFree(st.dDist[0]);
-        cudaFree(st.dDist[1]);
-        st.dRange = nullptr;
-        st.dMajorant = nullptr;
-        st.dDist[0] = st.dDist[1] = nullptr;
-        st.gridArray = nullptr;
+        release_grid(st);
 
         cudaTextureDesc td;
         memset(&td, 0, sizeof(td));
@@ -201,10 +228,12 @@ int ensure_grid(DevScene* scene, bool force)
         st.gridDims = make_int3((st.volDims.x + cell - 1) / cell, (st.volDims.y + cell - 1) / cell,
                                 (st.volDims.z + cell - 1) / cell);
         size_t cells = (size_t)st.gridDims.x * st.gridDims.y * st.gridDims.z;
+        size_t padded = (size_t)(st.gridDims.x + 2) * (st.gridDims.y + 2) * (st.gridDims.z + 2);
         SVR_TRY(cudaMalloc(&st.dRange, cells * sizeof(float2)));
-        SVR_TRY(cudaMalloc(&st.dMajorant, cells * sizeof(float)));
-        SVR_TRY(cudaMalloc(&st.dDist[0], cells));
-        SVR_TRY(cudaMalloc(&st.dDist[1], cells));
+        SVR_TRY(cudaMalloc(&st.dMajorant, padded * sizeof(float)));
+        SVR_TRY(cudaMalloc(&st.dDist[0], padded));
+        SVR_TRY(cudaMalloc(&st.dDist[1], padded));
+        SVR_TRY(cudaMalloc(&st.dOcc, 6 * sizeof(int)));
         dim3 g(st.gridDims.x, st.gridDims.y, st.gridDims.z);
         int threads = cell >= 8 ? 128 : 64;
         range_kernel<<<g, threads, 0, st.stream>>>(st.volPointTex, st.volDims, st.gridDims, cell, st.dRange);
@@ -215,8 +244,10 @@ int ensure_grid(DevScene* scene, bool force)
         st.majorantValid = false;
     }
 
-    if (force || !st.majorantValid || st.majorantDensityScale != vol.densityScale || st.majorantTfArray != tarr) {
-        // ---- stage 2: majorants from (range, TF, densityScale)
+    const int leap = st.options[SVR_OPT_LEAP] != 0;
+    if (force || !st.majorantValid || st.majorantDensityScale != vol.densityScale || st.majorantTfArray != tarr ||
+        st.majorantLeap != leap) {
+        // ---- stage 2: majorants from (range, TF, densityScale), into the padded grid
         cudaChannelFormatDesc ch;
         cudaExtent ext;
         unsigned int flags = 0;
@@ -236,35 +267,44 @@ int ensure_grid(DevScene* scene, bool force)
         SVR_TRY(cudaMemcpy2DFromArrayAsync(st.dTfTable, (size_t)n * sizeof(float4), tarr, 0, 0, (size_t)n * sizeof(float4), 1,
                                            cudaMemcpyDeviceToDevice, st.stream));
         tf_sparse_kernel<<<1, 1024, 0, st.stream>>>(st.dTfTable, n, levels, st.dTfSparse);
-        size_t cells = (size_t)st.gridDims.x * st.gridDims.y * st.gridDims.z;
-        majorant_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st.stream>>>(st.dRange, cells, st.dTfSparse, n,
-                                                                                vol.densityScale, st.dMajorant);
-        // ---- stage 3: leap distances for empty cells
-        const unsigned cb = (unsigned)((cells + 255) / 256);
-        dist_init_kernel<<<cb, 256, 0, st.stream>>>(st.dMajorant, cells, st.dDist[0]);
-        dim3 pb(32, 4, 1), pg((st.gridDims.x + 31) / 32, (st.gridDims.y + 3) / 4, st.gridDims.z);
+        const int px = st.gridDims.x + 2, py = st.gridDims.y + 2, pz = st.gridDims.z + 2;
+        const size_t padded = (size_t)px * py * pz;
+        SVR_TRY(cudaMemsetAsync(st.dMajorant, 0, padded * sizeof(float), st.stream));
+        occ_init_kernel<<<1, 32, 0, st.stream>>>(st.dOcc);
+        dim3 mb(32, 4, 1), mg((st.gridDims.x + 31) / 32, (st.gridDims.y + 3) / 4, st.gridDims.z);
+        majorant_kernel<<<mg, mb, 0, st.stream>>>(st.dRange, st.gridDims, st.dTfSparse, n, vol.densityScale, st.dMajorant, st.dOcc);
+        // ---- stage 3: leap distances for empty cells (border cells included)
+        const unsigned cb = (unsigned)((padded + 255) / 256);
+        dist_init_kernel<<<cb, 256, 0, st.stream>>>(st.dMajorant, padded, st.dDist[0]);
+        dim3 pg((px + 31) / 32, (py + 3) / 4, pz);
         int cur = 0;
-        for (int pass = 0; pass < SVR_LEAP_CAP; ++pass) {
-            dist_pass_kernel<<<pg, pb, 0, st.stream>>>(st.dDist[cur], st.dDist[cur ^ 1], st.gridDims.x, st.gridDims.y, st.gridDims.z);
+        const int passes = leap ? SVR_LEAP_CAP : 0;
+        for (int pass = 0; pass < passes; ++pass) {
+            dist_pass_kernel<<<pg, mb, 0, st.stream>>>(st.dDist[cur], st.dDist[cur ^ 1], px, py, pz);
             cur ^= 1;
         }
-        dist_store_kernel<<<cb, 256, 0, st.stream>>>(st.dDist[cur], cells, st.dMajorant);
-        count_launch(4 + SVR_LEAP_CAP);
+        dist_store_kernel<<<cb, 256, 0, st.stream>>>(st.dDist[cur], padded, st.dMajorant, leap);
+        count_launch(5 + passes);
         SVR_TRY(cudaGetLastError());
         st.majorantValid = true;
         st.majorantDensityScale = vol.densityScale;
         st.majorantTfArray = tarr;
+        st.majorantLeap = leap;
     }
 
     scene->volDim = st.volDims;
-    scene->grid.majorant = st.dMajorant;
-    scene->grid.range = st.dRange;
-    scene->grid.gx = st.gridDims.x;
-    scene->grid.gy = st.gridDims.y;
-    scene->grid.gz = st.gridDims.z;
-    scene->grid.cell = st.gridCell;
-    scene->grid.scale = f3((float)st.volDims.x / (float)st.gridCell, (float)st.volDims.y / (float)st.gridCell,
-                           (float)st.volDims.z / (float)st.gridCell);
+    DevGrid& g = scene->grid;
+    g.px = st.gridDims.x + 2;
+    g.pxy = g.px * (st.gridDims.y + 2);
+    g.cells = st.dMajorant + g.pxy + g.px + 1;  // interior cell (0,0,0)
+    g.range = st.dRange;
+    g.occ = st.dOcc;
+    g.gx = st.gridDims.x;
+    g.gy = st.gridDims.y;
+    g.gz = st.gridDims.z;
+    g.cell = st.gridCell;
+    g.scale = f3((float)st.volDims.x / (float)st.gridCell, (float)st.volDims.y / (float)st.gridCell,
+                 (float)st.volDims.z / (float)st.gridCell);
     return 0;
 }
 
@@ -323,9 +363,17 @@ extern "C" int svr_grid_copy(float* host_majorant, float* host_range)
 {
     svr::HostState& st = svr::state();
     if (!st.dRange || !st.dMajorant) return svr::fail_msg("svr_grid_copy: no grid has been built yet");
-    size_t cells = (size_t)st.gridDims.x * st.gridDims.y * st.gridDims.z;
+    const int gx = st.gridDims.x, gy = st.gridDims.y, gz = st.gridDims.z;
+    size_t cells = (size_t)gx * gy * gz;
     SVR_TRY(cudaStreamSynchronize(st.stream));
-    if (host_majorant) SVR_TRY(cudaMemcpy(host_majorant, st.dMajorant, cells * sizeof(float), cudaMemcpyDeviceToHost));
+    if (host_majorant) {
+        const int px = gx + 2, py = gy + 2, pz = gz + 2;
+        std::vector<float> padded((size_t)px * py * pz);
+        SVR_TRY(cudaMemcpy(padded.data(), st.dMajorant, padded.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int z = 0; z < gz; ++z)
+            for (int y = 0; y < gy; ++y)
+                memcpy(host_majorant + ((size_t)z * gy + y) * gx, &padded[((size_t)(z + 1) * py + (y + 1)) * px + 1], gx * sizeof(float));
+    }
     if (host_range) SVR_TRY(cudaMemcpy(host_range, st.dRange, cells * sizeof(float2), cudaMemcpyDeviceToHost));
     return 0;
 }

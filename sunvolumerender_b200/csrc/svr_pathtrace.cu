@@ -20,12 +20,13 @@
 // tracking (SVR_OPT_SHADOW_ESTIMATOR = 1).
 //
 // Kernel shapes (SVR_OPT_PT_KERNEL):
-//   0  per-lane state machine ("wavefront in a warp"): the reference's three nested data-dependent
-//      loops (bounces x tracking x shadow tracking) are flattened into
-//      GENERATE -> TRACK -> EVENT phases; all lanes of a warp run the tracking phase together
-//      whatever their ray is (camera, bounce or shadow ray), tentative collisions are evaluated
-//      together, and the expensive shading code runs once per round for every lane that has an
-//      event.  A lane whose path ends starts its next sample at once.
+//   0  phase-scheduled warp: the reference's three nested data-dependent loops (bounces x tracking
+//      x shadow tracking) are cut into five phases -- GENERATE, MARCH (walk
+//      macrocells / draw a free flight), COLLIDE (fetch + accept/reject), EVENT (shade, sample the
+//      light, start the shadow ray) and BOUNCE (add direct light, sample the BSDF).  Every lane
+//      carries its own phase; each round the warp votes and runs the phase most lanes are waiting
+//      in, so each piece of code executes with as many active lanes as the warp can muster, whatever
+//      ray (camera, bounce, shadow) or sample each lane is on.
 //   1  megakernel: the reference's loop nest as written, one path at a time per lane.
 #include "svr_rng.cuh"
 #include "svr_state.h"
@@ -50,7 +51,8 @@ struct PtLaunch {
     uint32_t* img;         // tone-mapped u8vec4 or null
     float4* sum;           // rgb = sum of samples, w = sample count (multi-GPU partials) or null
     int32_t clearSum;
-    int32_t trackRounds;   // state machine: tracking rounds between event phases (0 = until all lanes have an event)
+    int32_t marchBurst;    // phase-scheduled kernel: macrocell visits per MARCH round
+    int32_t entryCache;    // 1 = per-pixel camera-ray entry cache (mode 2)
 };
 
 template <int MODE>
@@ -63,18 +65,18 @@ struct RngOf<0> {
 };
 
 // ---------------------------------------------------------------------------------------------
-// free-path sampling, split into march() (advance to the next tentative collision or out of the
+// free-path sampling, split into visit() (advance to the next tentative collision or out of the
 // volume; no volume fetch) and collide() (fetch + accept/reject) so that a warp can run each half
 // convergently.
 // ---------------------------------------------------------------------------------------------
-enum MarchResult { MARCH_COLLIDE = 0, MARCH_ESCAPED = 1 };
+enum VisitResult { VISIT_CONTINUE = 0, VISIT_COLLIDE = 1, VISIT_ESCAPED = 2 };
 
 // woodcock_tracking.h:20-51, global majorant tf.GetMaxOpacity()
 struct TrackGlobal {
     float t, tMin, tMax;
 
     template <class Rng>
-    SVR_DEV bool begin(const DevScene& s, const Ray& ray, Rng&)
+    SVR_DEV bool begin(const DevScene& s, const Ray& ray, Rng&, float)
     {
         float tNear, tFar;
         if (!intersect_volume(s.vol, ray, &tNear, &tFar)) return false;
@@ -84,11 +86,11 @@ struct TrackGlobal {
         return true;
     }
     template <bool COUNT, class Rng>
-    SVR_DEV MarchResult march(const DevScene& s, const Ray&, Rng& rng, LocalCounters<COUNT>&)
+    SVR_DEV VisitResult visit(const DevScene& s, const Ray&, Rng& rng, LocalCounters<COUNT>&)
     {
         const float invSigmaMaxSampleInterval = 1.f / (s.tf.maxOpacity * 1.f);  // BASE_SAMPLE_STEP_SIZE 1
         t += -logf(rng.next_one_minus()) * invSigmaMaxSampleInterval;
-        return t > tMax ? MARCH_ESCAPED : MARCH_COLLIDE;
+        return t > tMax ? VISIT_ESCAPED : VISIT_COLLIDE;
     }
     // true = real collision at t
     template <bool COUNT, class Rng>
@@ -107,40 +109,12 @@ struct TrackGlobal {
     }
 };
 
-// Delta tracking against per-macrocell majorants with empty-space leaping.
-// Occupied cells are walked with a classic incremental 3-D DDA; an empty cell stores the radius of
-// the empty cube around it, and the ray jumps to that cube's far face in one step, after which the
-// DDA state is rebuilt from the new cell.
-struct TrackLocal {
-    float t, tMin, tMax;
-    float tau;            // optical depth still to travel before the next tentative collision
-    float sig;            // majorant of the cell the tentative collision lies in
-    float3 invDg, kk;     // face crossing: t = bound * invDg - kk per axis (cell coordinates)
-    float tNx, tNy, tNz;  // ray parameter at the next face of the current cell, per axis
-    int cx, cy, cz;
-
-    SVR_DEV void locate(const DevScene& s, const Ray& ray, float tt, int& ox, int& oy, int& oz) const
+// Cell-space description of a ray: a face at cell coordinate b is crossed at t = b * invDg - kk.
+struct CellRay {
+    float3 invDg, kk;
+    float eps;  // ray-parameter step that moves 1e-3 cell along the fastest axis
+    SVR_DEV void init(const DevScene& s, const Ray& ray)
     {
-        const float3 toCell = f3(s.vol.bbox.invSize) * s.grid.scale;
-        const float3 g = (ray.orig + tt * ray.dir - f3(s.vol.bbox.vmin)) * toCell;
-        ox = (int)floorf(g.x);
-        oy = (int)floorf(g.y);
-        oz = (int)floorf(g.z);
-    }
-    SVR_DEV void faces()
-    {
-        tNx = fmaf((float)(invDg.x > 0.f ? cx + 1 : cx), invDg.x, -kk.x);
-        tNy = fmaf((float)(invDg.y > 0.f ? cy + 1 : cy), invDg.y, -kk.y);
-        tNz = fmaf((float)(invDg.z > 0.f ? cz + 1 : cz), invDg.z, -kk.z);
-    }
-    template <class Rng>
-    SVR_DEV bool begin(const DevScene& s, const Ray& ray, Rng& rng)
-    {
-        float tNear, tFar;
-        if (!intersect_volume(s.vol, ray, &tNear, &tFar)) return false;
-        tMin = tNear < 0.f ? 1e-6f : tNear;
-        tMax = tFar;
-        t = tMin;
         const float3 toCell = f3(s.vol.bbox.invSize) * s.grid.scale;
         const float3 g0 = (ray.orig - f3(s.vol.bbox.vmin)) * toCell;
         const float3 dg = ray.dir * toCell;
@@ -151,72 +125,98 @@ struct TrackLocal {
         kk.x = dg.x != 0.f ? g0.x * invDg.x : -FLT_MAX;
         kk.y = dg.y != 0.f ? g0.y * invDg.y : -FLT_MAX;
         kk.z = dg.z != 0.f ? g0.z * invDg.z : -FLT_MAX;
-        locate(s, ray, t, cx, cy, cz);
-        cx = min(max(cx, 0), s.grid.gx - 1);
-        cy = min(max(cy, 0), s.grid.gy - 1);
-        cz = min(max(cz, 0), s.grid.gz - 1);
-        faces();
+        eps = 1e-3f * fminf(fminf(dg.x != 0.f ? fabsf(invDg.x) : FLT_MAX, dg.y != 0.f ? fabsf(invDg.y) : FLT_MAX),
+                            dg.z != 0.f ? fabsf(invDg.z) : FLT_MAX);
+    }
+    // parameter interval inside the slab [lo, hi] (cell coordinates) on every axis
+    SVR_DEV void clip(float3 lo, float3 hi, float* tA, float* tB) const
+    {
+        const float ax = fmaf(lo.x, invDg.x, -kk.x), bx = fmaf(hi.x, invDg.x, -kk.x);
+        const float ay = fmaf(lo.y, invDg.y, -kk.y), by = fmaf(hi.y, invDg.y, -kk.y);
+        const float az = fmaf(lo.z, invDg.z, -kk.z), bz = fmaf(hi.z, invDg.z, -kk.z);
+        // a static axis yields (FLT_MAX, FLT_MAX): it constrains nothing here (the volume-box test did)
+        const float nx = invDg.x != 0.f ? fminf(ax, bx) : -FLT_MAX, fx = fmaxf(ax, bx);
+        const float ny = invDg.y != 0.f ? fminf(ay, by) : -FLT_MAX, fy = fmaxf(ay, by);
+        const float nz = invDg.z != 0.f ? fminf(az, bz) : -FLT_MAX, fz = fmaxf(az, bz);
+        *tA = fmaxf(fmaxf(nx, ny), nz);
+        *tB = fminf(fminf(fx, fy), fz);
+    }
+    // cell containing the ray at parameter te, as floats and ints
+    SVR_DEV void locate(const DevScene& s, const Ray& ray, float te, float3* cf, int* ix, int* iy, int* iz) const
+    {
+        const float3 toCell = f3(s.vol.bbox.invSize) * s.grid.scale;
+        const float3 off = f3(s.vol.bbox.vmin) * toCell;
+        cf->x = floorf(fmaf(fmaf(te, ray.dir.x, ray.orig.x), toCell.x, -off.x));
+        cf->y = floorf(fmaf(fmaf(te, ray.dir.y, ray.orig.y), toCell.y, -off.y));
+        cf->z = floorf(fmaf(fmaf(te, ray.dir.z, ray.orig.z), toCell.z, -off.z));
+        *ix = (int)cf->x;
+        *iy = (int)cf->y;
+        *iz = (int)cf->z;
+    }
+    // parameter at which the ray leaves the cube of `r` cells beyond cell cf on the far side
+    // (r = 1: the cell itself) and r - 1 cells on the near side
+    SVR_DEV float exit_t(float3 cf, float r) const
+    {
+        const float n = 1.f - r;
+        const float tx = fmaf(cf.x + (invDg.x > 0.f ? r : n), invDg.x, -kk.x);
+        const float ty = fmaf(cf.y + (invDg.y > 0.f ? r : n), invDg.y, -kk.y);
+        const float tz = fmaf(cf.z + (invDg.z > 0.f ? r : n), invDg.z, -kk.z);
+        return fminf(fminf(tx, ty), tz);
+    }
+};
+
+// Delta tracking against per-macrocell majorants with empty-space leaping.  The walk is position
+// based: each visit looks up the cell under the ray just past the current parameter, spends the
+// cell's optical depth (or leaps over the empty cube an empty cell records) and moves to the far
+// face.  Occupied and empty cells run the same instructions, so lanes do not diverge inside the walk,
+// and no per-axis DDA state has to live in registers.
+struct TrackLocal {
+    float t, tMin, tMax;
+    float tau;  // optical depth still to travel before the next tentative collision
+    float sig;  // majorant of the cell the tentative collision lies in
+    CellRay cr;
+
+    SVR_DEV bool begin(const DevScene& s, const Ray& ray, Philox& rng, float tSkip)
+    {
+        float tNear, tFar;
+        if (!intersect_volume(s.vol, ray, &tNear, &tFar)) return false;
+        // a NaN direction component slips through the slab test (fminf/fmaxf drop NaNs); it must not index the grid
+        if (!(fabsf(ray.dir.x) + fabsf(ray.dir.y) + fabsf(ray.dir.z) < 4.f)) return false;
+        tMin = tNear < 0.f ? 1e-6f : tNear;
+        cr.init(s, ray);
+        // nothing can collide outside the box of non-empty cells, nor before the pixel's cached entry
+        const int* occ = s.grid.occ;
+        float tA, tB;
+        cr.clip(f3((float)__ldg(occ + 0), (float)__ldg(occ + 1), (float)__ldg(occ + 2)),
+                f3((float)(__ldg(occ + 3) + 1), (float)(__ldg(occ + 4) + 1), (float)(__ldg(occ + 5) + 1)), &tA, &tB);
+        t = fmaxf(fmaxf(tMin, tA), tSkip);
+        tMax = fminf(tFar, tB);
+        if (!(t < tMax)) return false;
         tau = -logf(rng.next_one_minus());
         return true;
     }
-    template <bool COUNT, class Rng>
-    SVR_DEV MarchResult march(const DevScene& s, const Ray& ray, Rng&, LocalCounters<COUNT>& lc)
+    template <bool COUNT>
+    SVR_DEV VisitResult visit(const DevScene& s, const Ray& ray, Philox&, LocalCounters<COUNT>& lc)
     {
-        const DevGrid& g = s.grid;
-        while (true) {
-            const float m = __ldg(&g.majorant[(cz * g.gy + cy) * g.gx + cx]);
-            lc.add(SVR_CNT_CELLS, 1);
-            if (m > 0.f) {
-                // occupied cell: spend optical depth m * length, or collide inside it
-                const float tN = fminf(fminf(tNx, tNy), tNz);
-                const float dd = fmaxf(fminf(tN, tMax) - t, 0.f) * m;
-                if (tau < dd) {
-                    t += tau / m;
-                    sig = m;
-                    return MARCH_COLLIDE;
-                }
-                tau -= dd;
-                t = tN;
-                if (tN >= tMax) return MARCH_ESCAPED;
-                if (tNx <= tNy && tNx <= tNz) {
-                    cx += invDg.x > 0.f ? 1 : -1;
-                    tNx += fabsf(invDg.x);
-                    if ((unsigned)cx >= (unsigned)g.gx) return MARCH_ESCAPED;
-                } else if (tNy <= tNz) {
-                    cy += invDg.y > 0.f ? 1 : -1;
-                    tNy += fabsf(invDg.y);
-                    if ((unsigned)cy >= (unsigned)g.gy) return MARCH_ESCAPED;
-                } else {
-                    cz += invDg.z > 0.f ? 1 : -1;
-                    tNz += fabsf(invDg.z);
-                    if ((unsigned)cz >= (unsigned)g.gz) return MARCH_ESCAPED;
-                }
-            } else {
-                // empty cell, and so is the cube of radius d-1 around it: leap to that cube's far face
-                const int d = max((int)(-m), 1);
-                const float lx = fmaf((float)(invDg.x > 0.f ? cx + d : cx - d + 1), invDg.x, -kk.x);
-                const float ly = fmaf((float)(invDg.y > 0.f ? cy + d : cy - d + 1), invDg.y, -kk.y);
-                const float lz = fmaf((float)(invDg.z > 0.f ? cz + d : cz - d + 1), invDg.z, -kk.z);
-                const float tL = fminf(fminf(lx, ly), lz);
-                if (tL >= tMax) return MARCH_ESCAPED;
-                t = fmaxf(t, tL);
-                // exact on the exit axis, re-located and clamped to the cube on the others
-                int nx, ny, nz;
-                locate(s, ray, t, nx, ny, nz);
-                nx = min(max(nx, cx - d + 1), cx + d - 1);
-                ny = min(max(ny, cy - d + 1), cy + d - 1);
-                nz = min(max(nz, cz - d + 1), cz + d - 1);
-                if (lx <= ly && lx <= lz) nx = invDg.x > 0.f ? cx + d : cx - d;
-                else if (ly <= lz) ny = invDg.y > 0.f ? cy + d : cy - d;
-                else nz = invDg.z > 0.f ? cz + d : cz - d;
-                if ((unsigned)nx >= (unsigned)g.gx || (unsigned)ny >= (unsigned)g.gy || (unsigned)nz >= (unsigned)g.gz)
-                    return MARCH_ESCAPED;
-                cx = nx;
-                cy = ny;
-                cz = nz;
-                faces();
-            }
+        const float te = t + cr.eps;
+        float3 cf;
+        int ix, iy, iz;
+        cr.locate(s, ray, te, &cf, &ix, &iy, &iz);
+        const float m = s.grid.at(ix, iy, iz);
+        lc.add(SVR_CNT_CELLS, 1);
+        // m > 0: majorant of this cell.  m < 0: empty, and so is the cube of radius -m-1 around it.
+        const float sg = fmaxf(m, 0.f);
+        const float tE = cr.exit_t(cf, fmaxf(-m, 1.f));
+        const float dd = fmaxf(fminf(tE, tMax) - t, 0.f) * sg;
+        if (tau < dd) {
+            t += tau / sg;
+            sig = sg;
+            return VISIT_COLLIDE;
         }
+        tau -= dd;
+        if (tE >= tMax) return VISIT_ESCAPED;
+        t = fmaxf(tE, te);
+        return VISIT_CONTINUE;
     }
     template <bool COUNT>
     SVR_DEV bool collide(const DevScene& s, const Ray& ray, Philox& rng, LocalCounters<COUNT>& lc, int slot, float* ratioT)
@@ -244,6 +244,58 @@ template <>
 struct TrackOf<2> {
     typedef TrackLocal type;
 };
+
+// Per-pixel camera-ray entry cache (mode 2).  All samples of a pixel shoot nearly the same camera
+// ray: with a pinhole (aperture 0) they share the origin and differ by at most half a pixel diagonal
+// in direction, i.e. by less than one macrocell sideways anywhere inside the volume.  The pixel's
+// centre ray is walked ONCE with every empty cube shrunk by one cell; as long as it stays in empty
+// space, every jittered ray of the pixel is in empty space too.  Returns the parameter up to which
+// camera rays of this pixel may be advanced before they start walking cells: 0 when nothing can be
+// said, FLT_MAX when no sample of the pixel can ever reach a non-empty cell.  Only empty cells are
+// skipped and no random number is consumed, so images are bit-identical with the cache off.
+SVR_DEV float camera_entry_cache(const DevScene& s, uint32_t idx, uint32_t idy)
+{
+    const svr_camera& c = s.cam;
+    if (c.apeture != 0.f) return 0.f;
+    Ray ray;
+    {
+        float nx = 2.f * (((float)idx + 0.5f) / ((float)c.imageW - 1.f)) - 1.f;
+        float ny = 2.f * (((float)idy + 0.5f) / ((float)c.imageH - 1.f)) - 1.f;
+        nx = nx * c.aspectRatio * c.tanFovxOverTwo;
+        ny = ny * c.tanFovxOverTwo;
+        ray.orig = f3(c.pos);
+        ray.dir = normalize(nx * f3(c.u) + ny * f3(c.v) - f3(c.w));
+    }
+    // walk the centre ray through the volume box grown by one cell (the grid's empty border), so that
+    // jittered rays that enter or leave the box slightly earlier / later are covered as well
+    CellRay cr;
+    cr.init(s, ray);
+    float tA, tB;
+    cr.clip(f3(-1.f), f3((float)(s.grid.gx + 1), (float)(s.grid.gy + 1), (float)(s.grid.gz + 1)), &tA, &tB);
+    tA = fmaxf(tA, 0.f);
+    if (!(tA < tB)) return 0.f;  // centre ray misses even the grown box: a jittered ray may still clip a corner
+    // sideways spread of the pixel's rays at the far end must stay below one cell (in world units)
+    const float hx = c.aspectRatio * c.tanFovxOverTwo / ((float)c.imageW - 1.f), hy = c.tanFovxOverTwo / ((float)c.imageH - 1.f);
+    const float spread = tB * sqrtf(hx * hx + hy * hy) * 1.05f;
+    const float3 cellWorld = f3((float)s.grid.cell) * f3(s.vol.spacing);
+    if (!(spread < 0.9f * fminf(fminf(cellWorld.x, cellWorld.y), cellWorld.z))) return 0.f;
+    float t = tA;
+    for (int guard = 0; guard < 4096; ++guard) {
+        const float te = t + cr.eps;
+        float3 cf;
+        int ix, iy, iz;
+        cr.locate(s, ray, te, &cf, &ix, &iy, &iz);
+        ix = min(max(ix, -1), s.grid.gx);
+        iy = min(max(iy, -1), s.grid.gy);
+        iz = min(max(iz, -1), s.grid.gz);
+        const float m = s.grid.at(ix, iy, iz);
+        if (!(m <= -2.f)) return t;  // a non-empty cell is at most one cell away from the centre ray
+        const float tE = cr.exit_t(cf, -m - 1.f);  // cube of radius d-2: the sideways cell stays inside the empty cube of radius d-1
+        if (tE >= tB) return FLT_MAX;
+        t = fmaxf(tE, te);
+    }
+    return t;
+}
 
 // ---------------------------------------------------------------------------------------------
 // shading (pathtracer.cu:96-198)
@@ -318,8 +370,6 @@ struct PathState {
     Ray ray;          // the ray being tracked (camera / bounce ray, or the shadow ray)
     float3 L, T;
     uint32_t k;
-    LightHit ls;      // nearest light along the camera ray (pathtracer.cu:214-215)
-    bool hitLight;
     // stash across the shadow ray
     VolumeSample vs;
     float3 pending;   // numLights * bsdf * Li / pdf, to be multiplied by the transmittance
@@ -329,12 +379,14 @@ struct PathState {
     bool shadow;      // the tracked ray is a shadow ray
 };
 
-enum EventResult { EV_TRACK = 0, EV_PATH_DONE = 1 };
+// what a lane does next
+enum Next { NEXT_TRACK = 0, NEXT_PATH_DONE = 1, NEXT_FLIGHT_MISSED = 2, NEXT_BOUNCE = 3 };
 
-// pathtracer.cu:204-215: seed, camera ray, nearest light; then start tracking the camera ray.
-// Returns false when the ray misses the volume (an immediate "escaped" event).
+// pathtracer.cu:204-213: seed, camera ray; then start tracking it.  Returns false when the ray
+// cannot collide (misses the volume): an immediate "escaped" event.
 template <int MODE>
-SVR_DEV bool path_begin(const DevScene& s, PathState<MODE>& ps, uint32_t idx, uint32_t idy, uint32_t offset, uint32_t sample)
+SVR_DEV bool path_begin(const DevScene& s, PathState<MODE>& ps, uint32_t idx, uint32_t idy, uint32_t offset, uint32_t sample,
+                        float tSkip)
 {
     constexpr bool EXACT_PI = MODE == 0;
     ps.rng.init(s.seedKey, offset, sample);
@@ -343,106 +395,97 @@ SVR_DEV bool path_begin(const DevScene& s, PathState<MODE>& ps, uint32_t idx, ui
     ps.k = 0;
     ps.shadow = false;
     ps.ray = camera_ray_jittered<EXACT_PI>(s.cam, idx, idy, ps.rng);
-    ps.hitLight = nearest_light(s, ps.ray, &ps.ls);
-    return ps.trk.begin(s, ps.ray, ps.rng);
+    return ps.trk.begin(s, ps.ray, ps.rng, tSkip);
 }
 
-// Everything between two tracked flights (pathtracer.cu:218-277 plus 171-198).  `t` is the
-// collision distance of the flight that just ended, or -FLT_MAX when it left the volume.
+// A camera / bounce flight ended at distance t (or left the volume: t = -FLT_MAX):
+// pathtracer.cu:214-255 plus estimate_direct_light up to the shadow ray (:171-191).
 template <int MODE, bool COUNT>
-SVR_DEV EventResult path_event(const DevScene& s, PathState<MODE>& ps, float t, uint32_t traceDepth, LocalCounters<COUNT>& lc)
+SVR_DEV Next event_flight_end(const DevScene& s, PathState<MODE>& ps, float t, LocalCounters<COUNT>& lc)
 {
     constexpr bool EXACT_PI = MODE == 0;
-    while (true) {
-        if (!ps.shadow) {
-            if ((ps.k == 0) && ps.hitLight) {
-                float tt = t < 0.f ? FLT_MAX : t;
-                if (ps.ls.t < tt) {
-                    float cosTerm = dot(ps.ls.normal, -ps.ray.dir);
-                    ps.L += ps.T * ps.ls.radiance * (cosTerm <= 0.f ? 0.f : 1.f);
-                    return EV_PATH_DONE;
-                }
+    if (ps.k == 0) {
+        // get_nearest_light_sample on the camera ray (pathtracer.cu:214-215, 220-229); the ray is still
+        // the camera ray here, so the hit is evaluated at the event instead of living in registers
+        LightHit ls;
+        if (nearest_light(s, ps.ray, &ls)) {
+            float tt = t < 0.f ? FLT_MAX : t;
+            if (ls.t < tt) {
+                float cosTerm = dot(ls.normal, -ps.ray.dir);
+                ps.L += ps.T * ls.radiance * (cosTerm <= 0.f ? 0.f : 1.f);
+                return NEXT_PATH_DONE;
             }
-            if (t < 0.f) {
-                if (s.envEnabled) ps.L += ps.T * env_radiance(s.env, ps.ray.dir);  // the line commented out at pathtracer.cu:233
-                return EV_PATH_DONE;
-            }
-            VolumeSample& vs = ps.vs;
-            vs.wo = -ps.ray.dir;
-            vs.ptInWorld = ps.ray.orig + t * ps.ray.dir;
-            float intensity = intensity_at(s.vol, vs.ptInWorld);
-            vs.color_opacity = tf_at(s.tf, intensity);
-            vs.gradient = gradient_at(s.vol, vs.ptInWorld);
-            float gradientMagnitude = sqrtf(dot(vs.gradient, vs.gradient));
-            lc.add(SVR_CNT_SHADE_TAPS, 7);
-            lc.add(SVR_CNT_TF_LOOKUPS, 1);
-            lc.add(SVR_CNT_SCATTERS, 1);
-            const float gf = s.vol.gradientFactor;
-            ps.Pbrdf = vs.color_opacity.w *
-                       (1.f - expf(-25.f * gf * gf * gf * gradientMagnitude * 65535.f * s.vol.invMaxMagnitude));
-            ps.st = (ps.rng.next() < ps.Pbrdf) ? BRDF : ISOTROPIC;
-
-            // estimate_direct_light, pathtracer.cu:171-198
-            bool needShadow = false;
-            if (s.numLights != 0) {
-                int lightId = (int)((float)s.numLights * ps.rng.next());
-                lightId = lightId < (int)s.numLights ? lightId : (int)s.numLights - 1;
-                float3 lightPos, wi;
-                float pdf;
-                float3 Li = sample_light<EXACT_PI>(s.lights[lightId], vs.ptInWorld, ps.rng, &lightPos, &wi, &pdf);
-                if (pdf > 0.f && max3(Li) > 0.f) {
-                    ps.pending = (float)s.numLights * bsdf(vs, wi, ps.st) * Li / pdf;
-                    // transmittance.h:10-17: track from the sample toward the light through the whole box
-                    ps.ray.orig = vs.ptInWorld;
-                    ps.ray.dir = normalize(lightPos - vs.ptInWorld);
-                    ps.shadow = true;
-                    ps.ratioT = 1.f;
-                    needShadow = true;
-                }
-            }
-            if (needShadow) {
-                if (ps.trk.begin(s, ps.ray, ps.rng)) return EV_TRACK;
-                t = -FLT_MAX;  // shadow ray misses the box: unoccluded
-                continue;
-            }
-            ps.shadow = true;  // no light sample: fall through to the bounce with nothing pending
-            ps.pending = f3(0.f);
-            ps.ratioT = 1.f;
-            t = -FLT_MAX;
-            continue;
-        }
-
-        // ---- the shadow flight ended: add the direct light, then bounce (pathtracer.cu:257-276)
-        {
-            float Tr;
-            if (s.shadowEstimator) Tr = ps.ratioT;
-            else Tr = ((t > ps.trk.tMin) && (t < ps.trk.tMax)) ? 0.f : 1.f;
-            ps.L += ps.T * (Tr * ps.pending);
-            ps.shadow = false;
-            const VolumeSample& vs = ps.vs;
-            // the last bounce's BSDF sample is never used: skip it unless reproducing the reference's draws
-            if (MODE != 0 && ps.k + 1 >= traceDepth) return EV_PATH_DONE;
-            float3 wi = f3(0.f);
-            float pdf = 0.f;
-            float3 f = sample_bsdf<EXACT_PI>(vs, &wi, &pdf, ps.rng, ps.st);
-            float cosTerm = fabsf(dot(normalize(vs.gradient), wi));
-            if (max3(f) > 0.f && pdf > 0.f) {
-                if (ps.st == ISOTROPIC)
-                    ps.T *= f / (pdf * (1.f - ps.Pbrdf));
-                else
-                    ps.T *= f * cosTerm / (pdf * ps.Pbrdf);
-            }
-            ps.ray.orig = vs.ptInWorld;
-            ps.ray.dir = wi;
-            if (ps.k >= 3) {
-                if (russian_roulette<EXACT_PI>(&ps.T, ps.rng)) return EV_PATH_DONE;
-            }
-            ps.k += 1;
-            if (ps.k >= traceDepth) return EV_PATH_DONE;
-            if (ps.trk.begin(s, ps.ray, ps.rng)) return EV_TRACK;
-            t = -FLT_MAX;  // bounce ray misses the (clipped) box
         }
     }
+    if (t < 0.f) {
+        if (s.envEnabled) ps.L += ps.T * env_radiance(s.env, ps.ray.dir);  // the line commented out at pathtracer.cu:233
+        return NEXT_PATH_DONE;
+    }
+    VolumeSample& vs = ps.vs;
+    vs.wo = -ps.ray.dir;
+    vs.ptInWorld = ps.ray.orig + t * ps.ray.dir;
+    float intensity = intensity_at(s.vol, vs.ptInWorld);
+    vs.color_opacity = tf_at(s.tf, intensity);
+    vs.gradient = gradient_at(s.vol, vs.ptInWorld);
+    float gradientMagnitude = sqrtf(dot(vs.gradient, vs.gradient));
+    lc.add(SVR_CNT_SHADE_TAPS, 7);
+    lc.add(SVR_CNT_TF_LOOKUPS, 1);
+    lc.add(SVR_CNT_SCATTERS, 1);
+    const float gf = s.vol.gradientFactor;
+    ps.Pbrdf = vs.color_opacity.w * (1.f - expf(-25.f * gf * gf * gf * gradientMagnitude * 65535.f * s.vol.invMaxMagnitude));
+    ps.st = (ps.rng.next() < ps.Pbrdf) ? BRDF : ISOTROPIC;
+
+    // estimate_direct_light, pathtracer.cu:171-198
+    ps.shadow = true;
+    ps.pending = f3(0.f);
+    ps.ratioT = 1.f;
+    if (s.numLights != 0) {
+        int lightId = (int)((float)s.numLights * ps.rng.next());
+        lightId = lightId < (int)s.numLights ? lightId : (int)s.numLights - 1;
+        float3 lightPos, wi;
+        float pdf;
+        float3 Li = sample_light<EXACT_PI>(s.lights[lightId], vs.ptInWorld, ps.rng, &lightPos, &wi, &pdf);
+        if (pdf > 0.f && max3(Li) > 0.f) {
+            ps.pending = (float)s.numLights * bsdf(vs, wi, ps.st) * Li / pdf;
+            // transmittance.h:10-17: track from the sample toward the light through the whole box
+            ps.ray.orig = vs.ptInWorld;
+            ps.ray.dir = normalize(lightPos - vs.ptInWorld);
+            return ps.trk.begin(s, ps.ray, ps.rng, 0.f) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+        }
+    }
+    return NEXT_BOUNCE;  // no shadow ray to fly: bounce with nothing pending
+}
+
+// The shadow flight ended (or there was none): add the direct light, then bounce (pathtracer.cu:257-276).
+// `occluded` is the binary estimator's verdict (transmittance.h:14-16).
+template <int MODE, bool COUNT>
+SVR_DEV Next event_bounce(const DevScene& s, PathState<MODE>& ps, bool occluded, uint32_t traceDepth, LocalCounters<COUNT>&)
+{
+    constexpr bool EXACT_PI = MODE == 0;
+    const float Tr = s.shadowEstimator ? ps.ratioT : (occluded ? 0.f : 1.f);
+    ps.L += ps.T * (Tr * ps.pending);
+    ps.shadow = false;
+    const VolumeSample& vs = ps.vs;
+    // the last bounce's BSDF sample is never used: skip it unless reproducing the reference's draws
+    if (MODE != 0 && ps.k + 1 >= traceDepth) return NEXT_PATH_DONE;
+    float3 wi = f3(0.f);
+    float pdf = 0.f;
+    float3 f = sample_bsdf<EXACT_PI>(vs, &wi, &pdf, ps.rng, ps.st);
+    float cosTerm = fabsf(dot(normalize(vs.gradient), wi));
+    if (max3(f) > 0.f && pdf > 0.f) {
+        if (ps.st == ISOTROPIC)
+            ps.T *= f / (pdf * (1.f - ps.Pbrdf));
+        else
+            ps.T *= f * cosTerm / (pdf * ps.Pbrdf);
+    }
+    ps.ray.orig = vs.ptInWorld;
+    ps.ray.dir = wi;
+    if (ps.k >= 3) {
+        if (russian_roulette<EXACT_PI>(&ps.T, ps.rng)) return NEXT_PATH_DONE;
+    }
+    ps.k += 1;
+    if (ps.k >= traceDepth) return NEXT_PATH_DONE;
+    return ps.trk.begin(s, ps.ray, ps.rng, 0.f) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
 }
 
 // Russian roulette for ratio tracking on a nearly opaque segment; true = terminate with T = 0
@@ -483,6 +526,10 @@ SVR_DEV void write_pixel(const DevScene& s, const PtLaunch& a, uint32_t offset, 
     }
 }
 
+// the flight's verdict for the binary transmittance estimator, transmittance.h:14-15
+template <class Trk>
+SVR_DEV bool occluded_at(const Trk& trk, float t) { return (t > trk.tMin) && (t < trk.tMax); }
+
 // ---------------------------------------------------------------------------------------------
 // kernel shape 1: megakernel (the reference's loop nest)
 // ---------------------------------------------------------------------------------------------
@@ -496,33 +543,32 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(
     LocalCounters<COUNT> lc;
     if (inside) {
         const uint32_t offset = idy * s.cam.imageW + idx;
+        const float tSkip = (MODE == 2 && a.entryCache) ? camera_entry_cache(s, idx, idy) : 0.f;
         float3 sum = f3(0.f);
         PathState<MODE> ps;
         for (uint32_t n = 0; n < a.nSamples; ++n) {
             lc.add(SVR_CNT_PATHS, 1);
-            bool tracking = path_begin<MODE>(s, ps, idx, idy, offset, a.firstSample + n);
-            float t = -FLT_MAX;
-            while (true) {
-                if (tracking) {
+            Next next = path_begin<MODE>(s, ps, idx, idy, offset, a.firstSample + n, tSkip) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+            while (next != NEXT_PATH_DONE) {
+                float t = -FLT_MAX;
+                if (next == NEXT_TRACK) {
                     const int slot = ps.shadow ? SVR_CNT_SHADOW_TAPS : SVR_CNT_TRACK_TAPS;
                     float* ratio = (ps.shadow && s.shadowEstimator) ? &ps.ratioT : nullptr;
                     while (true) {
-                        if (ps.trk.template march<COUNT>(s, ps.ray, ps.rng, lc) == MARCH_ESCAPED) {
-                            t = -FLT_MAX;
-                            break;
-                        }
+                        VisitResult v = ps.trk.template visit<COUNT>(s, ps.ray, ps.rng, lc);
+                        if (v == VISIT_CONTINUE) continue;
+                        if (v == VISIT_ESCAPED) break;
                         if (ps.trk.template collide<COUNT>(s, ps.ray, ps.rng, lc, slot, ratio)) {
                             t = ps.trk.t;
                             break;
                         }
-                        if (ratio && ratio_roulette(ps.ratioT, ps.rng)) {
-                            t = -FLT_MAX;
-                            break;
-                        }
+                        if (ratio && ratio_roulette(ps.ratioT, ps.rng)) break;
                     }
                 }
-                if (path_event<MODE, COUNT>(s, ps, t, a.traceDepth, lc) == EV_PATH_DONE) break;
-                tracking = true;
+                if (next == NEXT_BOUNCE || ps.shadow)
+                    next = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, t), a.traceDepth, lc);
+                else
+                    next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
             }
             sum += ps.L;
         }
@@ -532,12 +578,12 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel shape 0: per-lane state machine
+// kernel shape 0: phase-scheduled warp
 // ---------------------------------------------------------------------------------------------
-enum Phase { PH_GEN = 0, PH_TRACK = 1, PH_EVENT = 2, PH_DONE = 3 };
+enum Phase { PH_GEN = 0, PH_MARCH = 1, PH_COLLIDE = 2, PH_EVENT = 3, PH_BOUNCE = 4, PH_DONE = 5 };
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_sm_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+__global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_sched_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idx = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
@@ -550,54 +596,87 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_sm_kernel(co
     float3 sum = f3(0.f);
     uint32_t n = 0;
     int phase = inside ? PH_GEN : PH_DONE;
-    float tEvent = -FLT_MAX;
+    float tEvent = -FLT_MAX;   // flight result handed to EVENT / BOUNCE
+    const float tSkip = (MODE == 2 && a.entryCache && inside) ? camera_entry_cache(s, idx, idy) : 0.f;
 
     while (true) {
-        // ---- GENERATE: lanes without a path start their next sample
-        if (phase == PH_GEN) {
-            if (n == a.nSamples) {
-                phase = PH_DONE;
-            } else {
-                lc.add(SVR_CNT_PATHS, 1);
-                const bool tracking = path_begin<MODE>(s, ps, idx, idy, offset, a.firstSample + n);
-                ++n;
-                tEvent = -FLT_MAX;
-                phase = tracking ? PH_TRACK : PH_EVENT;
-            }
-        }
-        if (__all_sync(0xffffffffu, phase == PH_DONE)) break;
+        const unsigned mG = __ballot_sync(0xffffffffu, phase == PH_GEN);
+        const unsigned mM = __ballot_sync(0xffffffffu, phase == PH_MARCH);
+        const unsigned mC = __ballot_sync(0xffffffffu, phase == PH_COLLIDE);
+        const unsigned mE = __ballot_sync(0xffffffffu, phase == PH_EVENT);
+        const unsigned mB = __ballot_sync(0xffffffffu, phase == PH_BOUNCE);
+        if (!(mG | mM | mC | mE | mB)) break;
+        // run the phase most lanes are waiting in (ties go to the cheaper phase)
+        int pick = PH_MARCH, best = __popc(mM);
+        if (__popc(mC) > best) { pick = PH_COLLIDE; best = __popc(mC); }
+        if (__popc(mG) > best) { pick = PH_GEN; best = __popc(mG); }
+        if (__popc(mB) > best) { pick = PH_BOUNCE; best = __popc(mB); }
+        if (__popc(mE) > best) { pick = PH_EVENT; best = __popc(mE); }
 
-        // ---- TRACK: every tracking lane marches to its next tentative collision, then all of them
-        //      evaluate it together; repeat until the round budget is spent or nobody is tracking
-        int rounds = a.trackRounds;
-        while (__any_sync(0xffffffffu, phase == PH_TRACK)) {
-            if (phase == PH_TRACK) {
-                if (ps.trk.template march<COUNT>(s, ps.ray, ps.rng, lc) == MARCH_ESCAPED) {
-                    tEvent = -FLT_MAX;
-                    phase = PH_EVENT;
+        if (pick == PH_MARCH) {
+            // a burst of macrocell visits (mode 2) / one free-flight draw (modes 0, 1)
+            const int burst = MODE == 2 ? a.marchBurst : 1;
+            for (int i = 0; i < burst; ++i) {
+                if (phase == PH_MARCH) {
+                    VisitResult v = ps.trk.template visit<COUNT>(s, ps.ray, ps.rng, lc);
+                    if (v == VISIT_COLLIDE) phase = PH_COLLIDE;
+                    else if (v == VISIT_ESCAPED) {
+                        tEvent = -FLT_MAX;
+                        phase = ps.shadow ? PH_BOUNCE : PH_EVENT;
+                    }
                 }
+                if (!__any_sync(0xffffffffu, phase == PH_MARCH)) break;
             }
-            if (phase == PH_TRACK) {
+        } else if (pick == PH_COLLIDE) {
+            if (phase == PH_COLLIDE) {
                 const int slot = ps.shadow ? SVR_CNT_SHADOW_TAPS : SVR_CNT_TRACK_TAPS;
                 float* ratio = (ps.shadow && s.shadowEstimator) ? &ps.ratioT : nullptr;
                 if (ps.trk.template collide<COUNT>(s, ps.ray, ps.rng, lc, slot, ratio)) {
                     tEvent = ps.trk.t;
-                    phase = PH_EVENT;
+                    phase = ps.shadow ? PH_BOUNCE : PH_EVENT;
                 } else if (ratio && ratio_roulette(ps.ratioT, ps.rng)) {
                     tEvent = -FLT_MAX;
-                    phase = PH_EVENT;
+                    phase = PH_BOUNCE;
+                } else {
+                    phase = PH_MARCH;
                 }
             }
-            if (a.trackRounds > 0 && --rounds == 0) break;
-        }
-
-        // ---- EVENT: shade / add direct light / bounce / finish, for every lane whose flight ended
-        if (phase == PH_EVENT) {
-            if (path_event<MODE, COUNT>(s, ps, tEvent, a.traceDepth, lc) == EV_PATH_DONE) {
-                sum += ps.L;
-                phase = PH_GEN;
-            } else {
-                phase = PH_TRACK;
+        } else if (pick == PH_GEN) {
+            if (phase == PH_GEN) {
+                if (n == a.nSamples) {
+                    phase = PH_DONE;
+                } else {
+                    lc.add(SVR_CNT_PATHS, 1);
+                    const bool tracking = path_begin<MODE>(s, ps, idx, idy, offset, a.firstSample + n, tSkip);
+                    ++n;
+                    tEvent = -FLT_MAX;
+                    phase = tracking ? PH_MARCH : PH_EVENT;
+                }
+            }
+        } else if (pick == PH_EVENT) {
+            if (phase == PH_EVENT) {
+                Next nx = event_flight_end<MODE, COUNT>(s, ps, tEvent, lc);
+                if (nx == NEXT_TRACK) phase = PH_MARCH;
+                else if (nx == NEXT_PATH_DONE) {
+                    sum += ps.L;
+                    phase = PH_GEN;
+                } else {
+                    // NEXT_BOUNCE: no shadow ray; NEXT_FLIGHT_MISSED: the shadow ray cannot collide
+                    tEvent = -FLT_MAX;
+                    phase = PH_BOUNCE;
+                }
+            }
+        } else {
+            if (phase == PH_BOUNCE) {
+                Next nx = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, tEvent), a.traceDepth, lc);
+                if (nx == NEXT_TRACK) phase = PH_MARCH;
+                else if (nx == NEXT_PATH_DONE) {
+                    sum += ps.L;
+                    phase = PH_GEN;
+                } else {
+                    tEvent = -FLT_MAX;  // the bounce ray misses the (clipped) box
+                    phase = PH_EVENT;
+                }
             }
         }
     }
@@ -632,8 +711,8 @@ void launch_mode(int shape, dim3 grid, int block, cudaStream_t stream, const Dev
         if (cnt) pathtrace_mega_kernel<MODE, true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_mega_kernel<MODE, false><<<grid, block, 0, stream>>>(sc, a, cnt);
     } else {
-        if (cnt) pathtrace_sm_kernel<MODE, true><<<grid, block, 0, stream>>>(sc, a, cnt);
-        else pathtrace_sm_kernel<MODE, false><<<grid, block, 0, stream>>>(sc, a, cnt);
+        if (cnt) pathtrace_sched_kernel<MODE, true><<<grid, block, 0, stream>>>(sc, a, cnt);
+        else pathtrace_sched_kernel<MODE, false><<<grid, block, 0, stream>>>(sc, a, cnt);
     }
 }
 
@@ -655,7 +734,8 @@ int launch_pathtrace(PtLaunch a)
     }
     if (a.y1 > sc.cam.imageH) a.y1 = sc.cam.imageH;
     if (a.y0 >= a.y1 || a.nSamples == 0) return 0;
-    a.trackRounds = st.options[SVR_OPT_PT_ROUNDS];
+    a.marchBurst = st.options[SVR_OPT_PT_ROUNDS] > 0 ? st.options[SVR_OPT_PT_ROUNDS] : 4;
+    a.entryCache = st.options[SVR_OPT_PT_ENTRY_CACHE] && a.nSamples >= 2;
     Counters* cnt = nullptr;
     if (st.options[SVR_OPT_COUNTERS]) {
         cnt = device_counters();

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ De
                     int cx = min(max((int)floorf(g.x), 0), s.grid.gx - 1);
                     int cy = min(max((int)floorf(g.y), 0), s.grid.gy - 1);
                     int cz = min(max((int)floorf(g.z), 0), s.grid.gz - 1);
-                    float sig = __ldg(&s.grid.majorant[((size_t)cz * s.grid.gy + cy) * s.grid.gx + cx]);
+                    float sig = s.grid.at(cx, cy, cz);
                     lc.add(SVR_CNT_CELLS, 1);
                     if (sig <= 0.f) {
                         // empty cell, and so is the cube of radius d-1 around it (svr_macrocell.cu stage 3):

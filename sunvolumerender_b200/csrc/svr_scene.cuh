@@ -12,12 +12,18 @@
 namespace svr {
 
 // Macrocell majorant grid: cell (i,j,k) covers voxels [i*C, (i+1)*C) per axis in texel-index space.
+// `cells` holds one float per cell: > 0 the majorant (max TF opacity reachable inside the cell);
+// < 0 the cell is empty and so is the cube of radius (-value - 1) cells around it.  The array has a
+// one-cell empty border, so indices -1 .. g are valid on every axis; `cells` points at cell (0,0,0).
 struct DevGrid {
-    const float* majorant;   // gx*gy*gz, x fastest: max TF opacity reachable inside the cell
-    const float2* range;     // per cell (min, max) of the filtered intensity before densityScale
+    const float* cells;
+    const float2* range;     // per cell (min, max) of the filtered intensity before densityScale (no border)
+    const int* occ;          // bounding box of the non-empty cells: lo x,y,z then hi x,y,z (inclusive)
     int gx, gy, gz;
+    int px, pxy;             // row and slice pitch of `cells`
     int cell;                // cell edge in voxels
     float3 scale;            // normalised texture coordinate -> cell coordinate (dims / cell)
+    SVR_DEV float at(int cx, int cy, int cz) const { return __ldg(cells + (cz * pxy + cy * px + cx)); }
 };
 
 struct DevScene {

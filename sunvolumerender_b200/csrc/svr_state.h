@@ -27,8 +27,10 @@ struct HostState {
     int3 gridDims = {0, 0, 0};
     int3 volDims = {0, 0, 0};
     float2* dRange = nullptr;
-    float* dMajorant = nullptr;
+    float* dMajorant = nullptr;              // padded: (gx+2)(gy+2)(gz+2), one empty cell around the grid
     uint8_t* dDist[2] = {nullptr, nullptr};  // ping-pong Chebyshev distance to the nearest non-empty cell
+    int* dOcc = nullptr;                     // bounding box of the non-empty cells: lo xyz, hi xyz
+    int majorantLeap = -1;
     float* dTfSparse = nullptr;           // range-max sparse table over the TF opacity
     float4* dTfTable = nullptr;           // linear copy of the TF array
     int tfEntries = 0;
@@ -43,6 +45,12 @@ struct HostState {
 };
 
 HostState& state();
+
+// largest empty-space leap, in cells, a macrocell can record (svr_macrocell.cu stage 3)
+#define SVR_LEAP_CAP 15
+
+// drops the macrocell cache (range grid, majorants, distances, point-sampled view)
+void release_grid(HostState& st);
 
 // Part-1 error convention, utils/helper_cuda.h:967-981: print, cudaDeviceReset, exit(EXIT_FAILURE)
 inline void check_fatal(cudaError_t e, const char* what, const char* file, int line)

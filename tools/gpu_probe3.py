@@ -1,4 +1,4 @@
-"""Probe 3: kernel-shape / rounds / cell-size sweep on C3 + quick parity re-check.  Scratch tool."""
+"""Probe 3: parity re-check + kernel-shape / burst / cell-size sweep on C3 (normal and close view).  Scratch tool."""
 import sys, time
 import numpy as np
 import torch
@@ -48,16 +48,28 @@ for shape in (0, 1):
     r.set_option(L.OPT_SHADOW_ESTIMATOR, 0)
 del ref
 
-# ---- C3 sweep
+# ---- C3: bit-identity of the acceleration toggles, then sweeps
 cfg = S.CONFIGS['C3']
 setup_config(r, cfg)
 spp = 16
+r.set_option(L.OPT_PT_MODE, 2)
+imgs = {}
+for shape in (0, 1):
+    for leap in (1, 0):
+        for cache in (1, 0):
+            r.set_option(L.OPT_PT_KERNEL, shape); r.set_option(L.OPT_LEAP, leap); r.set_option(L.OPT_PT_ENTRY_CACHE, cache)
+            r.frame_no = 0; r.render_pathtracer_spp(4, 3)
+            imgs[(shape, leap, cache)] = r.hdr_image().clone()
+base = imgs[(1, 0, 0)]
+for k, v in imgs.items():
+    print('identity shape/leap/cache', k, 'max abs diff vs (1,0,0):', (v - base).abs().max().item())
+r.set_option(L.OPT_LEAP, 1); r.set_option(L.OPT_PT_ENTRY_CACHE, 1)
+
 ref = B.RefCuda(cfg.width, cfg.height); ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
 def refN():
     ref.frame_no = 0; ref.render_pathtracer(spp, 1)
 tref = ev_time(refN, 2)
 print(f'C3 ref {spp}spp: {tref*1e3:.2f} ms {cfg.width*cfg.height*spp/tref/1e6:.1f} Msamples/s')
-del ref
 def mineN():
     r.frame_no = 0; r.render_pathtracer_spp(spp, 1)
 for shape in (0, 1):
@@ -67,13 +79,20 @@ for shape in (0, 1):
         t = ev_time(mineN)
         print(f'C3 shape={shape} mode={mode}: {t*1e3:.2f} ms {cfg.width*cfg.height*spp/t/1e6:.1f} Msamples/s  x{tref/t:.2f}')
 r.set_option(L.OPT_PT_MODE, 2)
+for shape in (0, 1):
+    r.set_option(L.OPT_PT_KERNEL, shape)
+    for leap, cache in ((0, 0), (1, 0), (1, 1)):
+        r.set_option(L.OPT_LEAP, leap); r.set_option(L.OPT_PT_ENTRY_CACHE, cache)
+        t = ev_time(mineN)
+        print(f'C3 mode=2 shape={shape} leap={leap} cache={cache}: {t*1e3:.2f} ms  x{tref/t:.2f}')
+        r.set_option(L.OPT_COUNTERS, 1); r.reset_counters(); mineN(); print('   counters', r.counters()); r.set_option(L.OPT_COUNTERS, 0)
 r.set_option(L.OPT_PT_KERNEL, 0)
-for rounds in (1, 2, 4, 8, 16, 0):
-    r.set_option(L.OPT_PT_ROUNDS, rounds)
+for burst in (1, 2, 4, 8, 16):
+    r.set_option(L.OPT_PT_ROUNDS, burst)
     t = ev_time(mineN)
-    print(f'C3 sm mode=2 rounds={rounds}: {t*1e3:.2f} ms  x{tref/t:.2f}')
+    print(f'C3 sched mode=2 burst={burst}: {t*1e3:.2f} ms  x{tref/t:.2f}')
 r.set_option(L.OPT_PT_ROUNDS, 0)
-for cell in (4, 8, 16, 32):
+for cell in (4, 8, 16):
     r.set_option(L.OPT_MACROCELL_SIZE, cell)
     mineN()
     for shape in (0, 1):
@@ -82,5 +101,16 @@ for cell in (4, 8, 16, 32):
             r.set_option(L.OPT_PT_BLOCK, blk)
             t = ev_time(mineN)
             print(f'C3 mode=2 cell={cell} shape={shape} blk={blk}: {t*1e3:.2f} ms  x{tref/t:.2f}')
-    r.set_option(L.OPT_PT_BLOCK, 128); r.set_option(L.OPT_PT_KERNEL, 0)
-    r.set_option(L.OPT_COUNTERS, 1); r.reset_counters(); mineN(); print('   counters', r.counters()); r.set_option(L.OPT_COUNTERS, 0)
+    r.set_option(L.OPT_PT_BLOCK, 128)
+r.set_option(L.OPT_MACROCELL_SIZE, 8)
+# ---- close view
+cam = r.camera
+near = S.make_camera((0, 0, cam.pos.z * 0.45), (1, 0, 0), (0, 1, 0), (0, 0, 1), 45.0, 0.0, 1.0, 1.0, cfg.width, cfg.height)
+r.set_camera(near)
+ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
+tref = ev_time(refN, 2)
+print(f'close ref {spp}spp: {tref*1e3:.2f} ms')
+for shape in (0, 1):
+    r.set_option(L.OPT_PT_KERNEL, shape)
+    t = ev_time(mineN)
+    print(f'close mode=2 shape={shape}: {t*1e3:.2f} ms  x{tref/t:.2f}')
