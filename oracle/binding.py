@@ -114,18 +114,20 @@ class CpuOracle:
         return out
 
 
-def ref_lib_path(width, height, r32=False):
+def ref_lib_path(width, height, r32=False, f32=False):
     h16 = (height + 15) // 16 * 16
-    return os.path.join(REF_DIR, f"libsvr_ref_{width}x{h16}{'_r32' if r32 else ''}.so")
+    suffix = "_r32" if r32 else ("_f32" if f32 else "")
+    return os.path.join(REF_DIR, f"libsvr_ref_{width}x{h16}{suffix}.so")
 
 
 _ref_cache = {}
 
 
-def ref(width, height, r32=False):
+def ref(width, height, r32=False, f32=False):
     """The reference's own kernels for a WIDTH x HEIGHT canvas (HEIGHT rounded up to 16: the launch
-    has no bounds guard, pathtracer.cu:294-295).  Returns None when that size was not prebuilt."""
-    path = ref_lib_path(width, height, r32)
+    has no bounds guard, pathtracer.cu:294-295).  r32 = built with the shipped -maxrregcount=32;
+    f32 = float twin (img holds 4 floats per pixel, see glm_shim).  None when not prebuilt."""
+    path = ref_lib_path(width, height, r32, f32)
     if path in _ref_cache:
         return _ref_cache[path]
     if not os.path.exists(path):
@@ -145,18 +147,19 @@ class RefCuda:
     render_pathtracer per frame with frameNo = 0, 1, ... (canvas.cpp:96,116), or render_raycasting.
     Texture objects come from the caller (same descriptors as the reference's loaders)."""
 
-    def __init__(self, width, height, r32=False, device=None):
+    def __init__(self, width, height, r32=False, f32=False, device=None):
         import torch
 
         self.torch = torch
-        self.lib = ref(width, height, r32)
+        self.f32 = f32
+        self.lib = ref(width, height, r32, f32)
         if self.lib is None:
-            raise FileNotFoundError(ref_lib_path(width, height, r32))
+            raise FileNotFoundError(ref_lib_path(width, height, r32, f32))
         self.W, self.H = width, height
         self.HB = self.lib.buffer_height
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.hdr = torch.zeros(self.HB * self.W * 3, dtype=torch.float32, device=dev)
-        self.img = torch.zeros(self.HB * self.W * 4, dtype=torch.uint8, device=dev)
+        self.img = torch.zeros(self.HB * self.W * 4, dtype=torch.float32 if f32 else torch.uint8, device=dev)
         self.frame_no = 0
 
     def setup(self, volume, tf, camera, lights, env):
@@ -188,5 +191,6 @@ class RefCuda:
         return self.hdr.view(self.HB, self.W, 3)[: self.H]
 
     def ldr_image(self):
+        """u8 RGBA; for the float twin: the four products the kernel hands to u8vec4 (L*255), as floats."""
         self.torch.cuda.synchronize()
         return self.img.view(self.HB, self.W, 4)[: self.H]

@@ -1,0 +1,323 @@
+"""GPU parity of the path tracer (render_pathtracer, pathtracer.h:17) through the C ABI.
+
+Checkers: the reference's own unmodified kernel_pathtracer (oracle/_ref) on the same texture
+objects and seeds, and the CPU oracle.  Tolerances (BASELINE.json north_star):
+  * reference-twin mode (global majorant, XORWOW, same draw order): path for path the same walk,
+    so every pixel of every frame within 1e-4 of the reference's hdrBuffer;
+  * Philox / local-majorant modes: same estimator, different random numbers.  The Monte Carlo noise
+    floor is calibrated as RMSE(reference frames A, reference frames B) with disjoint seeds; the new
+    image must satisfy RMSE(new, reference) <= 1.15 x that floor, and the converged means must agree
+    per 16x16 tile within 4.5 sigma of the tile-mean estimates for >= 99.5% of the tiles.
+"""
+import numpy as np
+import pytest
+import torch
+
+from sunvolumerender_b200 import _lib as L
+from sunvolumerender_b200 import scene as S
+
+from _gpu_common import cpu_oracle, reference, rmse, setup, small_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(r, n, depth):
+    r.frame_no = 0
+    for _ in range(n):
+        r.render_pathtracer(depth)
+    torch.cuda.synchronize()
+    return r.hdr_image().cpu().numpy().copy()
+
+
+@pytest.mark.parametrize("shape", [1, 0])
+@pytest.mark.parametrize("depth", [1, 6])
+def test_twin_mode_matches_reference_path_for_path(renderer, shape, depth):
+    cfg = small_config(gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=depth)
+    setup(renderer, cfg)
+    renderer.set_option(L.OPT_PT_MODE, 0)
+    renderer.set_option(L.OPT_PT_KERNEL, shape)
+    ref = reference(renderer, cfg)
+    for nframes in (1, 4):
+        mine = _frames(renderer, nframes, depth)
+        ref.frame_no = 0
+        ref.render_pathtracer(nframes, depth)
+        theirs = ref.hdr_image().cpu().numpy()
+        assert theirs.max() > 0
+        d = np.abs(mine - theirs).max(axis=2)
+        # FMA contraction may differ between the two compilations; over a long walk a last-bit
+        # difference can flip one accept/reject and send that pixel down another path
+        assert (d <= 1e-4).mean() >= (1.0 if depth == 1 else 0.999), (nframes, d.max(), (d <= 1e-4).mean())
+        assert abs(mine.mean() - theirs.mean()) <= 1e-3 * theirs.mean()
+    # the tone-mapped image too (hdr_to_ldr, pathtracer.cu:282-290)
+    assert np.abs(renderer.ldr_image().cpu().numpy().astype(int) - ref.ldr_image().cpu().numpy().astype(int)).max() <= 1
+
+
+def test_twin_mode_matches_cpu_oracle(renderer):
+    cfg = small_config(n=48, w=64, h=64, gen=L.GEN_SPHERE, fmt=L.VOXEL_U16, depth=3)
+    vox = setup(renderer, cfg)
+    renderer.set_option(L.OPT_PT_MODE, 0)
+    mine = _frames(renderer, 2, 3)
+    hdr, _ = cpu_oracle(renderer, cfg, vox).pathtrace(3, 0, 2)
+    d = np.abs(mine - hdr).max(axis=2)
+    # IEEE libm vs fast-math flips a few accept/reject decisions; those pixels walk a different path
+    assert (d < 1e-3).mean() > 0.95
+    assert abs(mine.mean() - hdr.mean()) < 0.03 * hdr.mean()
+
+
+def test_twin_mode_batched_equals_frame_by_frame(renderer):
+    cfg = small_config(gen=L.GEN_SPHERE, fmt=L.VOXEL_U8, depth=2)
+    setup(renderer, cfg)
+    renderer.set_option(L.OPT_PT_MODE, 0)
+    one_by_one = _frames(renderer, 6, 2)
+    renderer.frame_no = 0
+    renderer.render_pathtracer_spp(6, 2)
+    torch.cuda.synchronize()
+    batched = renderer.hdr_image().cpu().numpy()
+    assert np.allclose(batched, one_by_one, rtol=1e-5, atol=1e-6)
+    # and a batch continues a running mean started frame by frame (pathtracer.cu:81-84)
+    _frames(renderer, 2, 2)
+    renderer.render_pathtracer_spp(4, 2)
+    torch.cuda.synchronize()
+    assert np.allclose(renderer.hdr_image().cpu().numpy(), one_by_one, rtol=1e-5, atol=1e-6)
+
+
+def _tile_means(img, tile=16):
+    H, W, C = img.shape
+    return img[: H // tile * tile, : W // tile * tile].reshape(H // tile, tile, W // tile, tile, C).mean(axis=(1, 3))
+
+
+@pytest.mark.parametrize("mode,estimator,shape", [(1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0)])
+def test_product_modes_are_statistically_the_reference(renderer, mode, estimator, shape):
+    depth, spp = 4, 512
+    cfg = small_config(gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=depth)
+    setup(renderer, cfg)
+    ref = reference(renderer, cfg)
+    ref.render_pathtracer(spp, depth)
+    ref_a = ref.hdr_image().cpu().numpy().copy()
+    # disjoint seeds: frames spp .. 2spp-1 accumulated into a fresh buffer via the running-mean restart
+    ref2 = reference(renderer, cfg)
+    ref2.frame_no = 0
+    ref2.render_pathtracer(2 * spp, depth)
+    ref_ab = ref2.hdr_image().cpu().numpy()
+    ref_b = 2.0 * ref_ab - ref_a  # mean of the second half
+    floor = rmse(ref_a, ref_b)
+
+    renderer.set_option(L.OPT_PT_MODE, mode)
+    renderer.set_option(L.OPT_SHADOW_ESTIMATOR, estimator)
+    renderer.set_option(L.OPT_PT_KERNEL, shape)
+    renderer.frame_no = 0
+    renderer.render_pathtracer_spp(spp, depth)
+    torch.cuda.synchronize()
+    mine = renderer.hdr_image().cpu().numpy()
+    assert np.isfinite(mine).all()
+    assert rmse(mine, ref_a) <= 1.15 * floor, (rmse(mine, ref_a), floor)
+
+    # converged means per 16x16 tile: |mean_new - mean_ref| <= 4.5 * sigma, sigma from the ref A/B split
+    tm, ta, tb = _tile_means(mine), _tile_means(ref_a), _tile_means(ref_b)
+    sigma = np.abs(ta - tb) / np.sqrt(2.0)          # one-sample estimate of a tile mean's std at spp samples
+    sigma = np.maximum(sigma, np.median(sigma) * 0.5 + 1e-6)
+    z = np.abs(tm - 0.5 * (ta + tb)) / (sigma * np.sqrt(1.5))
+    assert (z < 4.5).mean() >= 0.995, float((z < 4.5).mean())
+    assert abs(mine.mean() - ref_ab.mean()) < 0.01 * ref_ab.mean()
+
+
+def test_acceleration_toggles_are_bit_exact(renderer):
+    """Leaping, the camera-ray entry cache, the macrocell walk's kernel shape: none consumes a random
+    number or changes a collision, so the images are identical bit for bit."""
+    cfg = small_config(n=96, w=160, h=112, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=3)
+    setup(renderer, cfg)
+    imgs = []
+    for shape, leap, cache in ((1, 0, 0), (1, 1, 0), (1, 1, 1), (0, 1, 1), (0, 0, 0)):
+        renderer.set_option(L.OPT_PT_KERNEL, shape)
+        renderer.set_option(L.OPT_LEAP, leap)
+        renderer.set_option(L.OPT_PT_ENTRY_CACHE, cache)
+        renderer.frame_no = 0
+        renderer.render_pathtracer_spp(8, 3)
+        torch.cuda.synchronize()
+        imgs.append(renderer.hdr_image().clone())
+    assert float(imgs[0].max()) > 0
+    for im in imgs[1:]:
+        assert torch.equal(im, imgs[0])
+
+
+def test_deterministic_and_seeded(renderer):
+    cfg = small_config(gen=L.GEN_SPHERE, fmt=L.VOXEL_U8, depth=2)
+    setup(renderer, cfg)
+
+    def render():
+        renderer.frame_no = 0
+        renderer.render_pathtracer_spp(4, 2)
+        torch.cuda.synchronize()
+        return renderer.hdr_image().clone()
+
+    a, b = render(), render()
+    assert torch.equal(a, b)
+    renderer.set_option(L.OPT_SEED, 1234)
+    c = render()
+    assert not torch.equal(a, c)
+    # launch shape does not enter the random streams
+    renderer.set_option(L.OPT_SEED, 0x5EED)
+    renderer.set_option(L.OPT_PT_BLOCK, 256)
+    assert torch.equal(render(), a)
+    renderer.set_option(L.OPT_PT_BLOCK, 128)
+
+
+def test_sample_split_and_resolve_equal_single_render(renderer):
+    """The multi-GPU building blocks: partial sums over disjoint sample ranges add
+    up to the image of the whole range, up to float summation order."""
+    cfg = small_config(gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=2)
+    setup(renderer, cfg)
+    W, H = cfg.width, cfg.height
+    renderer.frame_no = 0
+    renderer.render_pathtracer_spp(12, 2)
+    torch.cuda.synchronize()
+    whole = renderer.hdr_image().clone()
+    whole_ldr = renderer.ldr_image().clone()
+    total = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
+    for first, count in S.split_samples(12, 3):
+        part = torch.zeros_like(total)
+        renderer.accumulate(part, 2, first, count, clear=True)
+        total += part
+    renderer.resolve(total)
+    torch.cuda.synchronize()
+    assert torch.allclose(renderer.hdr_image(), whole, rtol=1e-5, atol=1e-6)
+    assert (renderer.ldr_image().int() - whole_ldr.int()).abs().max() <= 1
+    assert float(total.view(H, W, 4)[..., 3].min()) == 12.0
+    # accumulate without clear adds on top
+    acc = torch.zeros_like(total)
+    renderer.accumulate(acc, 2, 0, 5, clear=True)
+    renderer.accumulate(acc, 2, 5, 7, clear=False)
+    torch.cuda.synchronize()
+    assert torch.allclose(acc, total, rtol=1e-5, atol=1e-5)
+
+
+def test_environment_light(renderer):
+    """The call the reference left commented out (pathtracer.cu:233), enabled by option."""
+    cfg = small_config(n=48, w=64, h=64, gen=L.GEN_SPHERE, fmt=L.VOXEL_U16, depth=2, env=True)
+    vox = setup(renderer, cfg)
+    renderer.set_area_lights([])
+    renderer.set_option(L.OPT_PT_MODE, 0)
+    mine = _frames(renderer, 4, 2)
+    assert mine[0, 0, 0] == pytest.approx(0.5)  # a corner ray misses the box and sees the constant sky
+    oracle = cpu_oracle(renderer, cfg, vox, env_enabled=True)
+    oracle.scene.numLights = 0
+    hdr, _ = oracle.pathtrace(2, 0, 4)
+    assert (np.abs(mine - hdr).max(axis=2) < 1e-3).mean() > 0.95
+    # with the option off and no lights the image is black, as the reference ships
+    renderer.set_option(L.OPT_ENV_ENABLED, 0)
+    assert _frames(renderer, 1, 2).max() == 0.0
+
+
+def test_no_lights_no_env_is_black_and_depth_zero_is_black(renderer):
+    cfg = small_config(gen=L.GEN_SPHERE, fmt=L.VOXEL_U8)
+    setup(renderer, cfg)
+    renderer.set_area_lights([])
+    for mode in (0, 1, 2):
+        renderer.set_option(L.OPT_PT_MODE, mode)
+        assert _frames(renderer, 1, 3).max() == 0.0
+    renderer.set_area_lights([S.default_area_light(cfg.extent)])
+    renderer.set_option(L.OPT_PT_MODE, 2)
+    assert _frames(renderer, 1, 0).max() == 0.0  # traceDepth 0: the bounce loop never runs
+
+
+def test_eight_lights_and_clamp(renderer):
+    cfg = small_config(gen=L.GEN_SPHERE, fmt=L.VOXEL_U8, depth=2)
+    setup(renderer, cfg)
+    lights = []
+    for i in range(9):  # one more than MAX_LIGHT_SOURCES: clamped to 8 (common.h:11)
+        l = S.default_area_light(cfg.extent)
+        ang = 2 * np.pi * i / 9
+        l.disk.center = L.Vec3(80 * np.cos(ang), 90.0, 80 * np.sin(ang))
+        lights.append(l)
+    renderer.set_area_lights(lights)
+    renderer.set_option(L.OPT_PT_MODE, 0)
+    mine = _frames(renderer, 2, 2)
+    from oracle import binding as B
+
+    ref = B.RefCuda(cfg.width, cfg.height)  # the reference itself would overrun its array with 9
+    ref.setup(renderer.volume, renderer.tf, renderer.camera, lights[:8], renderer.env)
+    ref.render_pathtracer(2, 2)
+    assert np.abs(mine - ref.hdr_image().cpu().numpy()).max() <= 1e-4
+
+
+def test_tone_map_matches_oracle(renderer, oracle_cpu):
+    cfg = small_config(gen=L.GEN_SPHERE, fmt=L.VOXEL_U8, depth=2)
+    vox = setup(renderer, cfg)
+    renderer.frame_no = 0
+    renderer.render_pathtracer_spp(8, 2)
+    torch.cuda.synchronize()
+    hdr = renderer.hdr_image().cpu().numpy()
+    expect = cpu_oracle(renderer, cfg, vox).tonemap(hdr)
+    got = renderer.ldr_image().cpu().numpy()
+    assert np.abs(got.astype(int) - expect.astype(int)).max() <= 1
+    assert (got[..., 3] == 255).all()
+
+
+def test_majorants_are_conservative(renderer):
+    """Every fetch the trackers can make inside a cell has opacity <= the cell's majorant; cells
+    marked empty really are; leap distances never reach a non-empty cell."""
+    import ctypes as C
+
+    cfg = small_config(n=64, gen=L.GEN_CT, fmt=L.VOXEL_U16, tf="default")
+    setup(renderer, cfg)
+    renderer.set_volume_params(density_scale=0.8)
+    renderer.frame_no = 0
+    renderer.render_pathtracer_spp(1, 1)  # builds the grid
+    dims = (C.c_int32 * 3)()
+    cell = C.c_int32()
+    L.check(renderer.lib.svr_grid_info(dims, C.byref(cell)))
+    gx, gy, gz = dims
+    maj = np.zeros((gz, gy, gx), np.float32)
+    L.check(renderer.lib.svr_grid_copy(C.c_void_p(maj.ctypes.data), None))
+    rng = np.random.default_rng(7)
+    m = 400000
+    uvw = rng.uniform(0, 1, (m, 3)).astype(np.float32)
+    d_uvw = torch.from_numpy(uvw).cuda()
+    d_i = torch.zeros(m, dtype=torch.float32, device="cuda")
+    L.check(renderer.lib.svr_debug_sample_volume(C.byref(renderer.volume), C.c_void_p(d_uvw.data_ptr()), m, C.c_void_p(d_i.data_ptr())))
+    d_x = (d_i * renderer.volume.densityScale).contiguous()
+    d_tf = torch.zeros(m * 4, dtype=torch.float32, device="cuda")
+    L.check(renderer.lib.svr_debug_sample_tf(C.byref(renderer.tf), C.c_void_p(d_x.data_ptr()), m, C.c_void_p(d_tf.data_ptr())))
+    sigma = d_tf.view(m, 4)[:, 3].cpu().numpy()
+    c = np.minimum((uvw * np.array([cfg.n / cell.value] * 3, np.float32)).astype(int), [gx - 1, gy - 1, gz - 1])
+    mj = maj[c[:, 2], c[:, 1], c[:, 0]]
+    assert (sigma <= np.maximum(mj, 0) + 1e-7).all()
+    assert (sigma[mj <= 0] == 0).all()
+    assert (mj > 0).any() and (mj < 0).any()
+    # leap distance d: every cell within Chebyshev distance d-1 is empty
+    occ = maj > 0
+    zs, ys, xs = np.nonzero(maj < -1)
+    for z, y, x in list(zip(zs, ys, xs))[:: max(1, len(zs) // 500)]:
+        rad = int(-maj[z, y, x]) - 1
+        sub = occ[max(z - rad, 0): z + rad + 1, max(y - rad, 0): y + rad + 1, max(x - rad, 0): x + rad + 1]
+        assert not sub.any()
+
+
+def test_config_c3_full_size_properties(renderer):
+    """At BASELINE.json's full size (512^3 u16, 1920x1080): size-independent properties -- the
+    acceleration structures change nothing, and the image agrees with the reference's own kernels
+    within the calibrated noise floor at equal spp."""
+    cfg = S.CONFIGS["C3"]
+    setup(renderer, cfg)
+    renderer.set_option(L.OPT_ENV_ENABLED, 0)  # the reference cannot add the sky (pathtracer.cu:233)
+    spp = 8
+    ref = reference(renderer, cfg)
+    ref.render_pathtracer(2 * spp, 1)
+    ref_ab = ref.hdr_image().cpu().numpy().copy()
+    ref1 = reference(renderer, cfg)
+    ref1.render_pathtracer(spp, 1)
+    ref_a = ref1.hdr_image().cpu().numpy()
+    ref_b = 2 * ref_ab - ref_a
+    floor = rmse(ref_a, ref_b)
+    imgs = []
+    for leap, cache in ((1, 1), (0, 0)):
+        renderer.set_option(L.OPT_LEAP, leap)
+        renderer.set_option(L.OPT_PT_ENTRY_CACHE, cache)
+        renderer.frame_no = 0
+        renderer.render_pathtracer_spp(spp, 1)
+        torch.cuda.synchronize()
+        imgs.append(renderer.hdr_image().clone())
+    assert torch.equal(imgs[0], imgs[1])
+    mine = imgs[0].cpu().numpy()
+    assert rmse(mine, ref_a) <= 1.15 * floor
+    assert abs(mine.mean() - ref_ab.mean()) < 0.02 * ref_ab.mean()

@@ -1,0 +1,105 @@
+"""GPU tests of the resource builders and synthetic generators behind the render path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from sunvolumerender_b200 import _lib as L
+from sunvolumerender_b200 import scene as S
+
+from _gpu_common import raycast_f32, setup, small_config
+
+pytestmark = pytest.mark.gpu
+
+
+def test_generators_are_deterministic_and_match_host_formula(renderer):
+    n = 32
+    a = renderer.generate_volume(L.GEN_SPHERE, L.VOXEL_U8, n).cpu().numpy().reshape(n, n, n)
+    b = renderer.generate_volume(L.GEN_SPHERE, L.VOXEL_U8, n).cpu().numpy().reshape(n, n, n)
+    assert np.array_equal(a, b)
+    host = S.sphere_volume(n, L.VOXEL_U8)
+    assert np.abs(a.astype(int) - host.astype(int)).max() <= 1  # fast-math sqrt/div vs numpy
+    ct = renderer.generate_volume(L.GEN_CT, L.VOXEL_U16, n, 1234).cpu().numpy().view(np.uint16)
+    ct2 = renderer.generate_volume(L.GEN_CT, L.VOXEL_U16, n, 99).cpu().numpy().view(np.uint16)
+    assert ct.max() > 40000 and (ct == 0).mean() > 0.2  # bone present, air exactly zero
+    assert not np.array_equal(ct, ct2)
+    cloud = renderer.generate_volume(L.GEN_CLOUD, L.VOXEL_F16, n, 42).cpu().numpy().view(np.float16)
+    assert 0 < cloud.max() <= 1.0 and cloud.min() == 0.0
+
+
+@pytest.mark.parametrize("fmt", [L.VOXEL_U8, L.VOXEL_U16, L.VOXEL_F32])
+def test_max_gradient_magnitude(renderer, fmt):
+    """VolumeReader.cpp:70-76 semantics: max central-difference gradient magnitude of the raw data."""
+    n = 24
+    rng = np.random.default_rng(3)
+    d = rng.uniform(0, 1, (n, n, n)).astype(np.float32)
+    vox = S.encode_voxels(d, fmt)
+    raw = vox.astype(np.float64) * {L.VOXEL_U8: 257.0, L.VOXEL_U16: 1.0, L.VOXEL_F32: 65535.0}[fmt]
+    sx, sy, sz = 1.0, 2.0, 0.5
+    p = np.pad(raw, 1, mode="edge")
+    gx = (p[1:-1, 1:-1, 2:] - p[1:-1, 1:-1, :-2]) * 0.5 / sx
+    gy = (p[1:-1, 2:, 1:-1] - p[1:-1, :-2, 1:-1]) * 0.5 / sy
+    gz = (p[2:, 1:-1, 1:-1] - p[:-2, 1:-1, 1:-1]) * 0.5 / sz
+    expect = np.sqrt(gx * gx + gy * gy + gz * gz).max()
+    dev = torch.from_numpy(vox.view(np.uint8).reshape(-1)).cuda()
+    out = C.c_float()
+    L.check(renderer.lib.svr_max_gradient_magnitude(C.c_void_p(dev.data_ptr()), fmt, n, n, n, sx, sy, sz, C.byref(out)))
+    assert out.value == pytest.approx(expect, rel=1e-4)
+
+
+def test_volume_from_host_equals_volume_from_device(renderer):
+    cfg = small_config(n=48, w=64, h=64, gen=L.GEN_CT, fmt=L.VOXEL_U16)
+    vox = setup(renderer, cfg)
+    a = raycast_f32(renderer).clone()
+    inv_a = renderer.volume.invMaxMagnitude
+    renderer.load_volume(vox, cfg.fmt, (cfg.n,) * 3)  # host numpy path (H2D inside the C ABI)
+    b = raycast_f32(renderer)
+    assert torch.equal(a, b)
+    assert renderer.volume.invMaxMagnitude == inv_a
+    v = renderer.volume
+    assert (v.bbox.vmin.x, v.bbox.vmax.x) == (-24.0, 24.0)
+    assert v.densityScale == 1.0 and v.gradientFactor == 0.5 and v.x_clip.x == -1.0
+
+
+def test_texture_fetch_matches_oracle_sampler(renderer, oracle_cpu):
+    """The hardware linear filter, with its 8-bit weights, against the oracle's software sampler --
+    this is what pins oracle/svr_oracle.cpp's filterMode 0."""
+    n = 16
+    rng = np.random.default_rng(5)
+    vox = rng.integers(0, 65536, (n, n, n), dtype=np.uint16)
+    renderer.load_volume(vox, L.VOXEL_U16, (n, n, n), max_grad_mag=1.0)
+    tf = S.tf_table("default")
+    renderer.set_transfer_function(tf)
+    m = 20000
+    uvw = rng.uniform(-0.1, 1.1, (m, 3)).astype(np.float32)
+    d_uvw = torch.from_numpy(uvw).cuda()
+    d_o = torch.zeros(m, dtype=torch.float32, device="cuda")
+    L.check(renderer.lib.svr_debug_sample_volume(C.byref(renderer.volume), C.c_void_p(d_uvw.data_ptr()), m, C.c_void_p(d_o.data_ptr())))
+    got = d_o.cpu().numpy()
+    o = oracle_cpu.CpuOracle(vox, L.VOXEL_U16, (n, n, n), renderer.volume, tf, S.default_camera((n,) * 3, 16, 16))
+    lib = oracle_cpu.cpu()
+    expect = np.array([lib.svr_oracle_tex3d(C.byref(o.scene), float(a), float(b), float(c)) for a, b, c in uvw], np.float32)
+    d = np.abs(got - expect)
+    assert (d < 2e-6).mean() > 0.995  # a weight lands on a rounding tie for a handful of samples
+    assert d.max() < 1.0 / 256 + 1e-6
+    xs = rng.uniform(-0.05, 1.05, 5000).astype(np.float32)
+    d_x = torch.from_numpy(xs).cuda()
+    d_t = torch.zeros(5000 * 4, dtype=torch.float32, device="cuda")
+    L.check(renderer.lib.svr_debug_sample_tf(C.byref(renderer.tf), C.c_void_p(d_x.data_ptr()), 5000, C.c_void_p(d_t.data_ptr())))
+    got_tf = d_t.view(5000, 4).cpu().numpy()
+    out = np.zeros(4, np.float32)
+    exp_tf = np.zeros((5000, 4), np.float32)
+    for i, x in enumerate(xs):
+        lib.svr_oracle_tf(C.byref(o.scene), float(x), out.ctypes.data)
+        exp_tf[i] = out
+    assert np.abs(got_tf - exp_tf).max() < 2e-6 + np.abs(np.diff(tf, axis=0)).max() / 256
+
+
+def test_error_paths_return_codes_not_exit(renderer):
+    lib = renderer.lib
+    vol = L.Volume()
+    assert lib.svr_volume_create(C.byref(vol), None, 0, L.VOXEL_U8, 4, 4, 4, 1.0, 1.0, 1.0, 1.0) != 0
+    assert b"svr_volume_create" in lib.svr_last_error()
+    assert lib.svr_pathtracer_accumulate(None, 1, 0, 1, 1) != 0
+    assert lib.svr_counters_reset() == 0
