@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(
         for (uint32_t n = 0; n < a.nSamples; ++n) {
             lc.add(SVR_CNT_PATHS, 1);
             Next next = path_begin<MODE>(s, ps, idx, idy, offset, a.firstSample + n, tSkip) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+            if (a.traceDepth == 0) next = NEXT_PATH_DONE;  // the bounce loop never runs (pathtracer.cu:216): the sample is black
             while (next != NEXT_PATH_DONE) {
                 float t = -FLT_MAX;
                 if (next == NEXT_TRACK) {
@@ -651,6 +652,7 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_sched_kernel
                     ++n;
                     tEvent = -FLT_MAX;
                     phase = tracking ? PH_MARCH : PH_EVENT;
+                    if (a.traceDepth == 0) phase = PH_GEN;  // the bounce loop never runs (pathtracer.cu:216): the sample is black
                 }
             }
         } else if (pick == PH_EVENT) {

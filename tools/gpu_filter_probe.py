@@ -1,7 +1,9 @@
-"""How does the texture unit quantise linear-filter weights?  Dumps tex3D of a ramp volume at fine
-coordinate steps and compares with candidate models; also the TF's tex1D.  Scratch tool whose result
-pins oracle/svr_oracle.cpp's software sampler (filterMode)."""
+"""How does the texture unit quantise linear-filter weights?  Fetches tex3D / tex1D at fine coordinate
+steps on known data and dumps (coordinates, results) to gpurun_out/filter_probe.npz, so the model in
+oracle/svr_oracle.cpp (filterMode) can be fitted offline.  Scratch tool; its result is committed as
+tests/golden/texture_filter.npz by tests/golden/make_golden.py."""
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -12,46 +14,57 @@ from sunvolumerender_b200 import _lib as L, scene as S  # noqa: E402
 from sunvolumerender_b200.render import Renderer  # noqa: E402
 
 r = Renderer(0)
+out = {}
+
+
+def fetch3(uvw):
+    m = uvw.shape[0]
+    d_uvw = torch.from_numpy(np.ascontiguousarray(uvw, np.float32)).cuda()
+    d_out = torch.zeros(m, dtype=torch.float32, device="cuda")
+    L.check(r.lib.svr_debug_sample_volume(C.byref(r.volume), C.c_void_p(d_uvw.data_ptr()), m, C.c_void_p(d_out.data_ptr())))
+    return d_out.cpu().numpy()
+
+
+rng = np.random.default_rng(0)
 for n in (4, 64, 512):
     vox = np.zeros((4, 4, n), np.float32)
     vox[:] = np.arange(n, dtype=np.float32)[None, None, :]
     r.load_volume(vox, L.VOXEL_F32, (n, 4, 4), max_grad_mag=1.0)
     m = 1 << 16
-    rng = np.random.default_rng(0)
-    xs = rng.uniform(0.5, n - 1.5, m).astype(np.float32)  # texel-space position of the sample
+    xs = rng.uniform(-1.0, n, m).astype(np.float32)
     u = ((xs + np.float32(0.5)) / np.float32(n)).astype(np.float32)
-    uvw = np.stack([u, np.full(m, 0.5 / 4, np.float32), np.full(m, 0.5 / 4, np.float32)], 1).astype(np.float32)
-    d_uvw = torch.from_numpy(uvw).cuda()
-    d_out = torch.zeros(m, dtype=torch.float32, device="cuda")
-    L.check(r.lib.svr_debug_sample_volume(C.byref(r.volume), C.c_void_p(d_uvw.data_ptr()), m, C.c_void_p(d_out.data_ptr())))
-    got = d_out.cpu().numpy().astype(np.float64)
-    xb = (u.astype(np.float32) * np.float32(n) - np.float32(0.5)).astype(np.float32).astype(np.float64)  # as the oracle computes it
-    xb_exact = u.astype(np.float64) * n - 0.5
-    cands = {
-        "round(frac*256)/256 (f32 xb)": np.floor(xb) + np.floor((xb - np.floor(xb)) * 256 + 0.5) / 256,
-        "floor(frac*256)/256 (f32 xb)": np.floor(xb) + np.floor((xb - np.floor(xb)) * 256) / 256,
-        "round(xb*256)/256 (exact xb)": np.floor(xb_exact * 256 + 0.5) / 256,
-        "floor(xb*256)/256 (exact xb)": np.floor(xb_exact * 256) / 256,
-        "round(u*n*256)/256 - 0.5": np.floor(u.astype(np.float64) * n * 256 + 0.5) / 256 - 0.5,
-        "floor(u*n*256)/256 - 0.5": np.floor(u.astype(np.float64) * n * 256) / 256 - 0.5,
-        "unquantised": xb_exact,
-    }
-    print(f"n={n}: result*256 integral? max dev {np.abs(got * 256 - np.round(got * 256)).max():.3e}")
-    for k, v in cands.items():
-        e = np.abs(got - v)
-        print(f"   {k:36s} max err {e.max():.3e}  mismatches(>1e-6) {(e > 1e-6).mean():.5f}")
-# TF: 1024 x float4 with .w = index
-tab = np.zeros((1024, 4), np.float32)
+    uvw = np.stack([u, np.full(m, 0.5 / 4, np.float32), np.full(m, 0.5 / 4, np.float32)], 1)
+    out[f"ramp{n}_u"] = u
+    out[f"ramp{n}_got"] = fetch3(uvw)
+for name, dt, fmt in (("u16", np.uint16, L.VOXEL_U16), ("u8", np.uint8, L.VOXEL_U8), ("f16", np.float16, L.VOXEL_F16)):
+    n = 16
+    if dt == np.float16:
+        vox = rng.uniform(0, 1, (n, n, n)).astype(np.float16)
+    else:
+        vox = rng.integers(0, np.iinfo(dt).max + 1, (n, n, n)).astype(dt)
+    r.load_volume(vox, fmt, (n, n, n), max_grad_mag=1.0)
+    m = 1 << 15
+    uvw = rng.uniform(-0.1, 1.1, (m, 3)).astype(np.float32)
+    out[f"{name}_vox"] = vox
+    out[f"{name}_uvw"] = uvw
+    out[f"{name}_got"] = fetch3(uvw)
+    # x only: y, z at texel centres
+    uvw1 = uvw.copy()
+    uvw1[:, 1] = (np.floor(uvw1[:, 1] * n).clip(0, n - 1) + 0.5) / n
+    uvw1[:, 2] = (np.floor(uvw1[:, 2] * n).clip(0, n - 1) + 0.5) / n
+    out[f"{name}_uvw1"] = uvw1
+    out[f"{name}_got1"] = fetch3(uvw1)
+tab = rng.uniform(0, 1, (1024, 4)).astype(np.float32)
 tab[:, 3] = np.arange(1024)
 r.set_transfer_function(tab)
 m = 1 << 16
-xs = np.random.default_rng(1).uniform(0.5, 1022.5, m).astype(np.float32)
-x = ((xs + np.float32(0.5)) / np.float32(1024)).astype(np.float32)
+x = rng.uniform(-0.05, 1.05, m).astype(np.float32)
 d_x = torch.from_numpy(x).cuda()
 d_o = torch.zeros(m * 4, dtype=torch.float32, device="cuda")
 L.check(r.lib.svr_debug_sample_tf(C.byref(r.tf), C.c_void_p(d_x.data_ptr()), m, C.c_void_p(d_o.data_ptr())))
-got = d_o.view(m, 4)[:, 3].cpu().numpy().astype(np.float64)
-xe = x.astype(np.float64) * 1024 - 0.5
-for k, v in {"round(xb*256)/256": np.floor(xe * 256 + 0.5) / 256, "floor(xb*256)/256": np.floor(xe * 256) / 256}.items():
-    e = np.abs(got - v)
-    print(f"TF {k:24s} max err {e.max():.3e} mismatches {(e > 1e-6).mean():.5f}")
+out["tf_tab"] = tab
+out["tf_x"] = x
+out["tf_got"] = d_o.view(m, 4).cpu().numpy()
+os.makedirs("gpurun_out", exist_ok=True)
+np.savez_compressed("gpurun_out/filter_probe.npz", **out)
+print("wrote gpurun_out/filter_probe.npz", {k: v.shape for k, v in out.items()})
