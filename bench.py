@@ -1,0 +1,493 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the render hot path (BASELINE.json: path samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3]
+
+One "step" = one pass of the path tracer over the whole frame: `spp` samples for every pixel of the
+workload (default C3, the configuration the metric is quoted on: 512^3 u16 volume, 1920x1080, Woodcock
+tracking, single scattering, area + environment light, 256 spp), accumulated into a float4 sum buffer,
+reduced over the ranks (N > 1: one NCCL sum-reduce of the per-GPU buffers onto rank 0) and resolved
+(divide + tone map) into the u8 image.  Weak scaling: every rank renders `spp` samples of its own
+(sample indices [rank*spp, (rank+1)*spp)), so the job is N*spp samples per pixel.
+
+  value     whole-job samples/s with the scene resident in HBM, CUDA events over exactly K steps,
+            max over ranks.
+  e2e       the same through the C ABI from HOST buffers: every step uploads the voxels from pinned
+            host memory into the volume's cudaArray (which drops and rebuilds the macrocell grid),
+            re-creates the transfer-function texture, re-publishes camera and lights, renders, and
+            reads the tone-mapped image and the float accumulator back into pinned host memory.
+  roofline  HBM: algorithmic bytes per launch (COUNTED taps x 8 voxels x bytes/voxel + TF lookups x 32 B
+            + framebuffer bytes) / the path-tracing kernel's mean launch duration
+            measured with CUDA events inside the timed region, against MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (port of the reference's device code, OpenMP over rows) on a bounded
+            sample of the same workload -- test infrastructure used as a yardstick, never the product.
+
+--impl reference: the reference has no CPU render path; its implementation of
+this path IS its CUDA kernels.  The arm runs them unmodified (oracle/_ref, compiled from
+/root/reference by oracle/Makefile) on one B200 through the reference's own entry points and frame
+protocol (render_pathtracer once per sample, three launches each).  `--ref-device cpu` times the
+CPU port instead.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "path_samples_per_sec"
+UNIT = "samples/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed regions (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        import torch
+
+        self.path = tempfile.mktemp(prefix="svr_clocks_", suffix=".csv")
+        self.proc = None
+        self.windows = []
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            ident = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        except Exception:
+            ident = str(device_index)
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100", "-i", ident],
+                stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def finish(self):
+        import datetime
+
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()  # the exact process we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        rows = []
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    p = [x.strip() for x in line.split(",")]
+                    if len(p) < 8:
+                        continue
+                    try:
+                        ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        rows.append((ts, float(p[1]), float(p[2]), float(p[3]), p[4:8]))
+                    except ValueError:
+                        continue
+            os.unlink(self.path)
+        except OSError:
+            pass
+        inside = [r for r in rows if any(t0 - 0.05 <= r[0] <= t1 + 0.05 for t0, t1 in self.windows)]
+        used = inside if inside else rows
+        if not used:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in used for i in range(4) if r[4][i].lower().startswith("active")})
+        return {
+            "sm_mhz": statistics.median(r[1] for r in used),
+            "sm_max_mhz": max(r[2] for r in used),
+            "power_w_max": max(r[3] for r in used),
+            "samples": len(used),
+            "samples_in_timed_region": len(inside),
+            "reasons": reasons,
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(cnt, voxel_bytes, npix, passes=1):
+    """taps x 8 voxels x B_v + TF lookups x 32 B + framebuffer bytes (one float4
+    read-modify-write of the accumulator per launch)."""
+    taps = cnt["track_taps"] + cnt["shadow_taps"] + cnt["shade_taps"]
+    return taps * 8 * voxel_bytes + cnt["tf_lookups"] * 32 + passes * npix * 32, taps
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from sunvolumerender_b200 import _lib as L
+    from sunvolumerender_b200 import distributed as D
+    from sunvolumerender_b200 import scene as S
+    from sunvolumerender_b200.render import Renderer, setup_config
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = S.CONFIGS[a.workload]
+    spp = a.spp or cfg.spp
+    depth = cfg.trace_depth
+    W, H = cfg.width, cfg.height
+    npix = W * H
+
+    r = Renderer(local)
+    vb = setup_config(r, cfg)  # synthetic voxels generated on the device (svr_generate_volume)
+    r.set_option(L.OPT_PT_MODE, a.pt_mode)
+    sum_buf = torch.zeros(npix * 4, dtype=torch.float32, device=dev)
+    first = rank * spp
+
+    def render_step(time_kernel=None):
+        if time_kernel is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        r.accumulate(sum_buf, depth, first, spp, clear=True)
+        if time_kernel is not None:
+            e1.record()
+            time_kernel.append((e0, e1))
+        if world > 1:
+            dist.reduce(sum_buf, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            r.resolve(sum_buf)
+
+    # ---- counted taps of one launch (same seeds as the timed launches => same counts)
+    r.set_option(L.OPT_COUNTERS, 1)
+    r.reset_counters()
+    r.accumulate(sum_buf, depth, first, spp, clear=True)
+    torch.cuda.synchronize()
+    cnt = r.counters()
+    r.set_option(L.OPT_COUNTERS, 0)
+
+    clocks = ClockSampler(local) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: scene resident in HBM
+    for _ in range(a.warmup):
+        render_step()
+    barrier()
+    launches0 = r.launch_count()
+    kernel_events = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    for _ in range(a.steps):
+        render_step(kernel_events)
+    ev1.record()
+    barrier()
+    t1 = time.time()
+    ms_local = ev0.elapsed_time(ev1)
+    launches = r.launch_count() - launches0
+    if clocks:
+        clocks.window(t0, t1)
+    ms = D.max_over_ranks(ms_local, dev)
+    kernel_ms = sum(x.elapsed_time(y) for x, y in kernel_events) / len(kernel_events)
+    value = npix * spp * world * a.steps / (ms * 1e-3)
+
+    # ---- e2e: everything from host buffers, results back on the host
+    host_vox = torch.empty(vb.numel(), dtype=torch.uint8, pin_memory=True)
+    host_vox.copy_(vb)
+    host_img = torch.empty(npix * 4, dtype=torch.uint8, pin_memory=True)
+    host_hdr = torch.empty(npix * 3, dtype=torch.float32, pin_memory=True)
+    tf_table = S.tf_table(cfg.tf)
+    cam = S.default_camera(cfg.extent, W, H)
+    lights = [S.default_area_light(cfg.extent)]
+    env = S.constant_env_light()
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        r.upload_volume(host_vox)                  # H2D voxels -> cudaArray; macrocell cache dropped
+        r.set_transfer_function(tf_table)          # H2D 16 KiB table -> new 1-D array + texture
+        r.set_camera(cam)
+        r.set_area_lights(lights)
+        r.set_env_light(env, enabled=cfg.env)
+        r.accumulate(sum_buf, depth, first, spp, clear=True)
+        if world > 1:
+            dist.reduce(sum_buf, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            r.resolve(sum_buf)
+            host_img.copy_(r.img, non_blocking=True)
+            host_hdr.copy_(r.hdr, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller looks at the image
+
+    for _ in range(max(1, min(a.warmup, 2))):
+        e2e_step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    t1 = time.time()
+    if clocks:
+        clocks.window(t0, t1)
+    e2e_ms = D.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    e2e_value = npix * spp * world * a.steps / (e2e_ms * 1e-3)
+    h2d = int(vb.numel() + tf_table.nbytes + 112 + 16 + 76 + 44 * len(lights) + 32)
+    d2h = int(host_img.numel() + host_hdr.numel() * 4)
+    img_nonzero = float((host_img.view(H, W, 4)[..., :3] > 0).float().mean()) if rank == 0 else 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    clk = clocks.finish()
+
+    # ---- roofline of the dominant kernel (the path-tracing launch)
+    peak, peak_src = measured_peak()
+    bytes_algo, taps = algorithmic_bytes(cnt, cfg.voxel_bytes, npix)
+    achieved = bytes_algo / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == a.workload and tj.get("spp") == spp and tj.get("pt_mode") == a.pt_mode:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "kernel": "pathtrace_mega_kernel<2>" if a.pt_mode == 2 else f"pathtrace_mega_kernel<{a.pt_mode}>",
+        "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "traffic": traffic, "peak_source": peak_src,
+        "bytes_algo_per_launch": int(bytes_algo), "taps_per_launch": int(taps), "tf_lookups_per_launch": int(cnt["tf_lookups"]),
+        "kernel_ms": round(kernel_ms, 4), "gtaps_per_s": round(taps / (kernel_ms * 1e-3) / 1e9, 3),
+        "kernel_share_of_step": round(kernel_ms / (ms / a.steps), 4),
+    }
+
+    # ---- CPU baseline: the oracle port on a bounded sample (rank 0, N = 1 only)
+    cpu_baseline = None
+    if world == 1 and not a.no_cpu_baseline:
+        cpu_baseline = cpu_port_sample(cfg, r, vb, a.cpu_seconds)
+
+    # ---- the reference's own CUDA kernels on this GPU, bounded sample (context for the 3x target)
+    ref_cuda = None
+    if world == 1 and not a.no_ref_cuda:
+        ref_cuda = reference_cuda_sample(cfg, r, 16)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{cfg.name}: {cfg.n}^3 {['u8', 'u16', 'f16', 'f32'][cfg.fmt]} procedural CT-like volume, {W}x{H} path tracing, "
+                        f"Woodcock tracking, traceDepth {depth}, one area light + constant environment light, {spp} spp per step per GPU",
+            "spp_per_step_per_gpu": spp, "samples_per_step": npix * spp * world,
+            "parallelism": f"spp-split x{world}, volume replicated, NCCL sum-reduce of float4 accumulators to rank 0" if world > 1 else "single GPU",
+            "estimator": {0: "global majorant + XORWOW (reference twin)", 1: "global majorant + Philox", 2: "macrocell local majorants + Philox"}[a.pt_mode],
+            "l2": f"volume {vb.numel() >> 20} MiB > 126 MB L2 and incoherent taps; no flush between steps",
+            "image_nonzero_fraction": round(img_nonzero, 4),
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "reference_cuda": ref_cuda,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_port_sample(cfg, r, vb, seconds, threads=None):
+    """The CPU oracle (test infrastructure) timed on an image-wide bounded sample: every 16th row, as
+    many frames as fit in about `seconds`."""
+    import numpy as np
+
+    from oracle import binding as B
+    from sunvolumerender_b200 import scene as S
+
+    if not os.path.exists(B.CPU_LIB):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "cpu"], stdout=subprocess.DEVNULL)
+    vox = vb.cpu().numpy().view(S.VOXEL_DTYPES[cfg.fmt]).reshape(cfg.n, cfg.n, cfg.n)
+    o = B.CpuOracle(vox, cfg.fmt, (cfg.n,) * 3, r.volume, S.tf_table(cfg.tf), r.camera, r.lights)
+    cores = B.cpu().svr_oracle_threads()
+    W, H = cfg.width, cfg.height
+    step = 16
+    rows = len(range(8, H, step))
+    t = time.perf_counter()
+    o.pathtrace(cfg.trace_depth, 0, 1, rows=(8, H), row_step=step)
+    dt1 = time.perf_counter() - t
+    frames = int(max(1, min(4096, seconds / max(dt1, 1e-3))))
+    t = time.perf_counter()
+    o.pathtrace(cfg.trace_depth, 1, frames, rows=(8, H), row_step=step)
+    dt = time.perf_counter() - t
+    return {
+        "value": W * rows * frames / dt, "unit": UNIT, "cores": int(cores), "kind": "port",
+        "sample": f"rows 8,24,..(every 16th: {rows} of {H}) x {W} px x {frames} frames of {cfg.name}, global majorant + XORWOW as the reference, {dt:.1f} s",
+    }
+
+
+def reference_cuda_sample(cfg, r, frames):
+    import torch
+
+    from oracle import binding as B
+
+    try:
+        ref = B.RefCuda(cfg.width, cfg.height)
+    except (FileNotFoundError, OSError) as e:
+        return {"unavailable": str(e)}
+    ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
+    ref.render_pathtracer(2, cfg.trace_depth)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(3):
+        ref.frame_no = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ref.render_pathtracer(frames, cfg.trace_depth)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return {"value": cfg.width * cfg.height * frames / (best * 1e-3), "unit": UNIT,
+            "sample": f"{frames} frames (render_pathtracer x{frames}, 3 launches each) of {cfg.name}, env light off (dead code in the reference), best of 3"}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return  # the reference is single-device: rank 0 alone runs it
+    import torch
+
+    from oracle import binding as B
+    from sunvolumerender_b200 import scene as S
+    from sunvolumerender_b200.render import Renderer, setup_config
+
+    cfg = S.CONFIGS[a.workload]
+    spp = a.spp or cfg.spp
+    W, H = cfg.width, cfg.height
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference", "unavailable": "no CUDA device: the reference's only implementation of the path is CUDA"}))
+        return
+    local = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    # scene resources (cudaArray + texture objects with the reference loaders' descriptors, synthetic voxels)
+    # come from this repo's resource builders; every pixel below is produced by the reference's kernels
+    r = Renderer(local)
+    vb = setup_config(r, cfg)
+    if a.ref_device == "cpu":
+        cb = cpu_port_sample(cfg, r, vb, max(10.0, a.cpu_seconds))
+        line = dict(base, value=cb["value"], ms_per_step=None,
+                    config={"workload": f"{cfg.name} (bounded sample: {cb['sample']})"},
+                    cpu_baseline=cb, e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
+    try:
+        ref = B.RefCuda(W, H, r32=a.ref_r32)
+    except (FileNotFoundError, OSError) as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref library for {W}x{H} not prebuilt: {e}"}))
+        return
+    ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
+    clocks = ClockSampler(local)
+
+    def step():
+        ref.frame_no = 0
+        ref.render_pathtracer(spp, cfg.trace_depth)  # Canvas::paintGL's loop: one render_pathtracer per sample
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    for _ in range(a.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    clocks.window(t0, t1)
+    ms = ev0.elapsed_time(ev1)
+    HB = ref.HB
+    value = W * H * spp * a.steps / (ms * 1e-3)
+    line = dict(
+        base, value=value, ms_per_step=ms / a.steps,
+        config={"workload": f"{cfg.name}: {cfg.n}^3 u16, {W}x{H} path tracing, traceDepth {cfg.trace_depth}, one area light (environment light is dead "
+                            f"code in the reference, pathtracer.cu:233), {spp} spp per step; the reference's unmodified kernels, sm_100, "
+                            f"-use_fast_math{' -maxrregcount=32' if a.ref_r32 else ''}; canvas {W}x{HB} (no bounds guard), {W}x{H} counted",
+                "spp_per_step_per_gpu": spp, "samples_per_step": W * H * spp},
+        e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        gpu_launches=3 * spp * a.steps,
+        clocks=clocks.finish(),
+        cpu_baseline={"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                      "sample": "the reference has no CPU path; this is its own CUDA implementation (oracle/_ref) on one B200, full workload"},
+    )
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--spp", type=int, default=0, help="samples per pixel per step per GPU (0 = the workload's)")
+    ap.add_argument("--pt-mode", type=int, default=2, choices=[0, 1, 2])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
+    ap.add_argument("--ref-r32", action="store_true", help="reference built with the shipped -maxrregcount=32")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 0)
+    world = env_int("WORLD_SIZE", 1)
+    if a.impl == "ours" and world != a.gpus and world == 1 and a.gpus > 1:
+        # launched without torchrun: re-launch ourselves the way the driver would
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

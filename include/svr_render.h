@@ -136,6 +136,11 @@ enum svr_voxel_format { SVR_VOXEL_U8 = 0, SVR_VOXEL_U16 = 1, SVR_VOXEL_F16 = 2, 
 int svr_volume_create(svr_volume* out, const void* data, int data_on_device, int format,
                       uint32_t nx, uint32_t ny, uint32_t nz, float sx, float sy, float sz, float maxGradMag);
 int svr_volume_destroy(svr_volume* vol);
+/* Re-uploads voxels (same dims and format, x-fastest) into the array behind vol->tex -- the second
+ * half of VolumeReader::CreateTextures (core/VolumeReader.cpp:146-161) for a volume that is already
+ * bound -- and drops the macrocell cache built from the old contents.  Asynchronous on the library
+ * stream when `data` is device or pinned host memory. */
+int svr_volume_upload(const svr_volume* vol, const void* data, int data_on_device);
 /* Drop cached macrocell data (keyed on the cudaArray handle); call after re-uploading voxels
  * into an existing array. */
 int svr_volume_invalidate_cache(void);

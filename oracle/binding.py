@@ -54,6 +54,7 @@ def cpu():
         lib.svr_oracle_set_threads.argtypes = [C.c_int]
         lib.svr_oracle_raycast.argtypes = [P, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.svr_oracle_pathtrace.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.svr_oracle_pathtrace_strided.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.svr_oracle_tonemap.argtypes = [C.c_void_p, C.c_float, C.c_uint64, C.c_void_p]
         lib.svr_oracle_tex3d.restype = C.c_float
         lib.svr_oracle_tex3d.argtypes = [P, C.c_float, C.c_float, C.c_float]
@@ -98,13 +99,13 @@ class CpuOracle:
         cpu().svr_oracle_raycast(C.byref(self.scene), step_size, W, y0, y1, rgba.ctypes.data, u8.ctypes.data, cnt.ctypes.data)
         return rgba, u8, cnt
 
-    def pathtrace(self, trace_depth, frame0, nframes, rows=None, hdr=None):
+    def pathtrace(self, trace_depth, frame0, nframes, rows=None, hdr=None, row_step=1):
         W, H = self.scene.camera.imageW, self.scene.camera.imageH
         y0, y1 = rows if rows else (0, H)
         if hdr is None:
             hdr = np.zeros((H, W, 3), np.float32)
         cnt = np.zeros(16, np.uint64)
-        cpu().svr_oracle_pathtrace(C.byref(self.scene), trace_depth, frame0, nframes, W, y0, y1, hdr.ctypes.data, cnt.ctypes.data)
+        cpu().svr_oracle_pathtrace_strided(C.byref(self.scene), trace_depth, frame0, nframes, W, y0, y1, row_step, hdr.ctypes.data, cnt.ctypes.data)
         return hdr, cnt
 
     def tonemap(self, hdr):

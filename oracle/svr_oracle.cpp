@@ -835,6 +835,15 @@ void svr_oracle_raycast(const svr_oracle_scene* scene, float stepSize, uint32_t 
 void svr_oracle_pathtrace(const svr_oracle_scene* scene, uint32_t traceDepth, uint32_t frameNo0, uint32_t nFrames,
                           uint32_t strideW, uint32_t y0, uint32_t y1, float* hdr, uint64_t* counters)
 {
+    svr_oracle_pathtrace_strided(scene, traceDepth, frameNo0, nFrames, strideW, y0, y1, 1, hdr, counters);
+}
+
+/* rows y0, y0+yStep, ... < y1 only: a bounded, image-wide sample for the CPU baseline timing */
+void svr_oracle_pathtrace_strided(const svr_oracle_scene* scene, uint32_t traceDepth, uint32_t frameNo0, uint32_t nFrames,
+                                  uint32_t strideW, uint32_t y0, uint32_t y1, uint32_t yStep, float* hdr, uint64_t* counters)
+{
+    if (yStep == 0) yStep = 1;
+    const int64_t nRows = y1 > y0 ? ((int64_t)(y1 - y0) + yStep - 1) / yStep : 0;
     const uint32_t W = scene->camera.imageW;
     uint64_t totals[SVR_ORACLE_CNT_COUNT] = {0};
 #pragma omp parallel num_threads(svr_oracle_threads())
@@ -843,7 +852,8 @@ void svr_oracle_pathtrace(const svr_oracle_scene* scene, uint32_t traceDepth, ui
         c.s = scene;
         memset(c.cnt, 0, sizeof(c.cnt));
 #pragma omp for schedule(dynamic, 1)
-        for (int64_t idy = (int64_t)y0; idy < (int64_t)y1; ++idy) {
+        for (int64_t row = 0; row < nRows; ++row) {
+            const int64_t idy = (int64_t)y0 + row * yStep;
             for (uint32_t idx = 0; idx < W; ++idx) {
                 uint32_t offset = (uint32_t)idy * strideW + idx;
                 float* acc = hdr + 3 * (size_t)offset;

@@ -49,6 +49,10 @@ void svr_oracle_raycast(const svr_oracle_scene* scene, float stepSize, uint32_t 
 void svr_oracle_pathtrace(const svr_oracle_scene* scene, uint32_t traceDepth, uint32_t frameNo0, uint32_t nFrames,
                           uint32_t strideW, uint32_t y0, uint32_t y1, float* hdr, uint64_t* counters);
 
+/* the same over rows y0, y0+yStep, ... < y1 only (bounded image-wide sample for the CPU baseline) */
+void svr_oracle_pathtrace_strided(const svr_oracle_scene* scene, uint32_t traceDepth, uint32_t frameNo0, uint32_t nFrames,
+                                  uint32_t strideW, uint32_t y0, uint32_t y1, uint32_t yStep, float* hdr, uint64_t* counters);
+
 /* pathtracer.cu:282-290 + tonemapping.h:13-27 */
 void svr_oracle_tonemap(const float* hdr, float exposure, uint64_t npix, uint8_t* outU8);
 

@@ -133,6 +133,7 @@ SIGNATURES = [
     ("svr_render_raycasting_rows", C.c_int, [_P, _P, C.POINTER(Volume), C.POINTER(TransferFunction), C.POINTER(Camera), C.c_float, C.c_uint32, C.c_uint32]),
     ("svr_volume_create", C.c_int, [C.POINTER(Volume), _P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float]),
     ("svr_volume_destroy", C.c_int, [C.POINTER(Volume)]),
+    ("svr_volume_upload", C.c_int, [C.POINTER(Volume), _P, C.c_int]),
     ("svr_volume_invalidate_cache", C.c_int, []),
     ("svr_tf_create", C.c_int, [C.POINTER(TransferFunction), _P, C.c_uint32]),
     ("svr_tf_destroy", C.c_int, [C.POINTER(TransferFunction)]),

@@ -302,6 +302,33 @@ extern "C" int svr_volume_create(svr_volume* out, const void* data, int data_on_
     return 0;
 }
 
+extern "C" int svr_volume_upload(const svr_volume* vol, const void* data, int data_on_device)
+{
+    if (!vol || !vol->tex || !data) return fail_msg("svr_volume_upload: bad argument");
+    HostState& st = state();
+    cudaResourceDesc rd;
+    SVR_TRY(cudaGetTextureObjectResourceDesc(&rd, vol->tex));
+    if (rd.resType != cudaResourceTypeArray) return fail_msg("svr_volume_upload: texture is not bound to a cudaArray");
+    cudaChannelFormatDesc ch;
+    cudaExtent ext;
+    unsigned int flags = 0;
+    SVR_TRY(cudaArrayGetInfo(&ch, &ext, &flags, rd.res.array.array));
+    const size_t bpe = (size_t)(ch.x + ch.y + ch.z + ch.w) / 8;
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.dstArray = rd.res.array.array;
+    cp.extent = ext;
+    cp.kind = data_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cp.srcPtr = make_cudaPitchedPtr(const_cast<void*>(data), ext.width * bpe, ext.width, ext.height);
+    SVR_TRY(cudaMemcpy3DAsync(&cp, st.stream));
+    if (rd.res.array.array == st.gridArray) {
+        // stream order keeps kernels already queued on the old grid ahead of the frees below
+        SVR_TRY(cudaStreamSynchronize(st.stream));
+        release_grid(st);
+    }
+    return 0;
+}
+
 extern "C" int svr_volume_destroy(svr_volume* vol)
 {
     if (!vol || !vol->tex) return 0;

@@ -88,6 +88,18 @@ class Renderer:
         self.lib.setup_volume(C.byref(vol))
         return vol
 
+    def upload_volume(self, data):
+        """Replace the voxels of the bound volume (same dims/format) from a host numpy array, a pinned
+        host tensor or a device tensor."""
+        if isinstance(data, torch.Tensor):
+            on_device, ptr = (1 if data.is_cuda else 0), _ptr(data)
+        else:
+            data = np.ascontiguousarray(data)
+            on_device, ptr = 0, C.c_void_p(data.ctypes.data)
+        L.check(self.lib.svr_volume_upload(C.byref(self.volume), ptr, on_device), "svr_volume_upload")
+        self.lib.setup_volume(C.byref(self.volume))
+        self.frame_no = 0
+
     def free_volume(self):
         if self.volume is not None:
             L.check(self.lib.svr_volume_destroy(C.byref(self.volume)), "svr_volume_destroy")
