@@ -149,6 +149,9 @@ int svr_volume_invalidate_cache(void);
  * (r,g,b,opacity) -> 1-D cudaArray texture, linear, clamp, normalised; maxOpacity = max opacity. */
 int svr_tf_create(svr_transfer_function* out, const float* host_rgba, uint32_t n);
 int svr_tf_destroy(svr_transfer_function* tf);
+/* New table contents (same size) into the array behind tf->tex; updates tf->maxOpacity.  The caller
+ * then publishes the struct with setup_transferfunction, as after any edit. */
+int svr_tf_upload(svr_transfer_function* tf, const float* host_rgba, uint32_t n);
 
 /* Mirrors Lights::SetEnvironmentLight (core/lights/lights.cpp:31-75): w x h float4 lat-long map. */
 int svr_env_create(svr_env_light* out, const float* host_rgba, uint32_t w, uint32_t h);

@@ -137,6 +137,7 @@ SIGNATURES = [
     ("svr_volume_invalidate_cache", C.c_int, []),
     ("svr_tf_create", C.c_int, [C.POINTER(TransferFunction), _P, C.c_uint32]),
     ("svr_tf_destroy", C.c_int, [C.POINTER(TransferFunction)]),
+    ("svr_tf_upload", C.c_int, [C.POINTER(TransferFunction), _P, C.c_uint32]),
     ("svr_env_create", C.c_int, [C.POINTER(EnvLight), _P, C.c_uint32, C.c_uint32]),
     ("svr_env_destroy", C.c_int, [C.POINTER(EnvLight)]),
     ("svr_generate_volume", C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32]),

@@ -321,11 +321,32 @@ extern "C" int svr_volume_upload(const svr_volume* vol, const void* data, int da
     cp.kind = data_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     cp.srcPtr = make_cudaPitchedPtr(const_cast<void*>(data), ext.width * bpe, ext.width, ext.height);
     SVR_TRY(cudaMemcpy3DAsync(&cp, st.stream));
-    if (rd.res.array.array == st.gridArray) {
-        // stream order keeps kernels already queued on the old grid ahead of the frees below
-        SVR_TRY(cudaStreamSynchronize(st.stream));
-        release_grid(st);
-    }
+    // same dims, new contents: the grid's allocations stay, its range stage reruns at the next render
+    if (rd.res.array.array == st.gridArray) st.rangeValid = false;
+    return 0;
+}
+
+// The table half of TransferFunction::TransferFunction (gui/transferfunction.cpp:17-44) for a texture
+// that already exists: the reference destroys and recreates array + texture object on every edit
+// (transferfunction.cpp:128-151); the contents are all that changes.
+extern "C" int svr_tf_upload(svr_transfer_function* tf, const float* host_rgba, uint32_t n)
+{
+    if (!tf || !tf->tex || !host_rgba) return fail_msg("svr_tf_upload: bad argument");
+    HostState& st = state();
+    cudaResourceDesc rd;
+    SVR_TRY(cudaGetTextureObjectResourceDesc(&rd, tf->tex));
+    if (rd.resType != cudaResourceTypeArray) return fail_msg("svr_tf_upload: texture is not bound to a cudaArray");
+    cudaChannelFormatDesc ch;
+    cudaExtent ext;
+    unsigned int flags = 0;
+    SVR_TRY(cudaArrayGetInfo(&ch, &ext, &flags, rd.res.array.array));
+    if (ext.width != n) return fail_msg("svr_tf_upload: table size differs from the bound array");
+    SVR_TRY(cudaMemcpy2DToArrayAsync(rd.res.array.array, 0, 0, host_rgba, sizeof(float) * 4 * n, sizeof(float) * 4 * n, 1,
+                                     cudaMemcpyHostToDevice, st.stream));
+    float maxOpacity = 0.f;
+    for (uint32_t i = 0; i < n; ++i) maxOpacity = fmaxf(maxOpacity, host_rgba[4 * i + 3]);
+    tf->maxOpacity = maxOpacity;
+    st.majorantValid = false;
     return 0;
 }
 

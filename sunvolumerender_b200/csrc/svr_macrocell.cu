@@ -189,6 +189,7 @@ void release_grid(HostState& st)
     st.dDist[0] = st.dDist[1] = nullptr;
     st.dOcc = nullptr;
     st.gridArray = nullptr;
+    st.rangeValid = false;
     st.majorantValid = false;
 }
 
@@ -208,7 +209,7 @@ int ensure_grid(DevScene* scene, bool force)
 
     const int cell = st.options[SVR_OPT_MACROCELL_SIZE];
     if (varr != st.gridArray || cell != st.gridCell || !st.dRange) {
-        // ---- stage 1: range grid
+        // ---- allocate for this (array, cell size)
         cudaChannelFormatDesc ch;
         cudaExtent ext;
         unsigned int flags = 0;
@@ -234,13 +235,18 @@ int ensure_grid(DevScene* scene, bool force)
         SVR_TRY(cudaMalloc(&st.dDist[0], padded));
         SVR_TRY(cudaMalloc(&st.dDist[1], padded));
         SVR_TRY(cudaMalloc(&st.dOcc, 6 * sizeof(int)));
+        st.gridArray = varr;
+        st.gridCell = cell;
+        st.rangeValid = false;
+    }
+    if (!st.rangeValid) {
+        // ---- stage 1: range grid (again after svr_volume_upload: same allocations, new voxels)
         dim3 g(st.gridDims.x, st.gridDims.y, st.gridDims.z);
         int threads = cell >= 8 ? 128 : 64;
         range_kernel<<<g, threads, 0, st.stream>>>(st.volPointTex, st.volDims, st.gridDims, cell, st.dRange);
         count_launch();
         SVR_TRY(cudaGetLastError());
-        st.gridArray = varr;
-        st.gridCell = cell;
+        st.rangeValid = true;
         st.majorantValid = false;
     }
 

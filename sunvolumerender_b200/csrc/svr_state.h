@@ -35,6 +35,7 @@ struct HostState {
     float4* dTfTable = nullptr;           // linear copy of the TF array
     int tfEntries = 0;
     cudaTextureObject_t volPointTex = 0;  // point-sampled view of gridArray
+    bool rangeValid = false;              // false until the range grid reflects the array's current voxels
     bool majorantValid = false;           // false after setup_volume/setup_transferfunction
     float majorantDensityScale = 0.f;
     cudaArray_t majorantTfArray = nullptr;

@@ -28,6 +28,7 @@ class Renderer:
         self.sync_stream()
         self.volume = None
         self.tf = None
+        self._tf_size = 0
         self.camera = None
         self.env = None
         self.lights = []
@@ -123,11 +124,18 @@ class Renderer:
 
     def set_transfer_function(self, table):
         table = np.ascontiguousarray(table, dtype=np.float32)
+        if self.tf is not None and self._tf_size == table.shape[0]:
+            # an edit of the bound table: new contents into the same array
+            L.check(self.lib.svr_tf_upload(C.byref(self.tf), C.c_void_p(table.ctypes.data), table.shape[0]), "svr_tf_upload")
+            self.lib.setup_transferfunction(C.byref(self.tf))
+            self.frame_no = 0
+            return self.tf
         if self.tf is not None:
             L.check(self.lib.svr_tf_destroy(C.byref(self.tf)), "svr_tf_destroy")
         tf = L.TransferFunction()
         L.check(self.lib.svr_tf_create(C.byref(tf), C.c_void_p(table.ctypes.data), table.shape[0]), "svr_tf_create")
         self.tf = tf
+        self._tf_size = table.shape[0]
         self.lib.setup_transferfunction(C.byref(tf))
         self.frame_no = 0
         return tf

@@ -103,3 +103,37 @@ def test_error_paths_return_codes_not_exit(renderer):
     assert b"svr_volume_create" in lib.svr_last_error()
     assert lib.svr_pathtracer_accumulate(None, 1, 0, 1, 1) != 0
     assert lib.svr_counters_reset() == 0
+
+
+def test_upload_into_bound_resources_equals_fresh_load(renderer):
+    """svr_volume_upload / svr_tf_upload replace contents behind the same handles (what bench.py's e2e
+    step does every step); derived data (macrocell ranges, majorants) must follow."""
+    cfg = small_config(n=48, w=96, h=64, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=2)
+    vox = setup(renderer, cfg)
+
+    def render():
+        renderer.frame_no = 0
+        renderer.render_pathtracer_spp(4, 2)
+        rc = raycast_f32(renderer).clone()
+        torch.cuda.synchronize()
+        return renderer.hdr_image().clone(), rc
+
+    pt_a, rc_a = render()
+    # different voxels and table through the same handles
+    other = (vox[::-1, :, ::-1] // 2).copy()
+    renderer.upload_volume(other)
+    renderer.set_transfer_function(S.tf_table("thin"))
+    pt_b, rc_b = render()
+    assert not torch.equal(pt_a, pt_b) and not torch.equal(rc_a, rc_b)
+    # fresh load of the same data gives the same images bit for bit
+    renderer.load_volume(other, cfg.fmt, (cfg.n,) * 3, max_grad_mag=1.0 / renderer.volume.invMaxMagnitude)
+    L.check(renderer.lib.svr_tf_destroy(C.byref(renderer.tf)))
+    renderer.tf = None  # force a new array + texture
+    renderer.set_transfer_function(S.tf_table("thin"))
+    pt_c, rc_c = render()
+    assert torch.equal(pt_b, pt_c) and torch.equal(rc_b, rc_c)
+    # and back again
+    renderer.upload_volume(torch.from_numpy(vox.copy()).cuda().view(torch.uint8))
+    renderer.set_transfer_function(S.tf_table(cfg.tf))
+    pt_d, rc_d = render()
+    assert torch.equal(pt_a, pt_d) and torch.equal(rc_a, rc_d)
