@@ -100,6 +100,9 @@ enum svr_option {
     SVR_OPT_PT_ENTRY_CACHE = 12,
     SVR_OPT_COUNT_
 };
+/* Defaults can also come from the environment, read once at first use, for hosts that only know the
+ * seven reference entry points: SVR_PT_MODE, SVR_SHADOW_ESTIMATOR, SVR_ENV_ENABLED, SVR_RC_SKIP,
+ * SVR_SEED, SVR_PT_KERNEL (same values as the options). */
 int svr_set_option(int key, int value);
 int svr_get_option(int key);
 

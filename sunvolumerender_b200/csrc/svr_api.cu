@@ -28,6 +28,20 @@ HostState& state()
         p->options[SVR_OPT_PT_KERNEL] = 1;  // megakernel: measured 2.5x faster than the phase-scheduled shape (profiles/r01)
         p->options[SVR_OPT_LEAP] = 1;
         p->options[SVR_OPT_PT_ENTRY_CACHE] = 1;
+        // A host that only knows the reference's seven entry points (gui/canvas.cpp) cannot call
+        // svr_set_option: the same switches are read once from the environment.
+        static const struct { const char* name; int key, lo, hi; } kEnv[] = {
+            {"SVR_PT_MODE", SVR_OPT_PT_MODE, 0, 2},           {"SVR_SHADOW_ESTIMATOR", SVR_OPT_SHADOW_ESTIMATOR, 0, 1},
+            {"SVR_ENV_ENABLED", SVR_OPT_ENV_ENABLED, 0, 1},   {"SVR_RC_SKIP", SVR_OPT_RC_SKIP, 0, 1},
+            {"SVR_SEED", SVR_OPT_SEED, INT32_MIN, INT32_MAX}, {"SVR_PT_KERNEL", SVR_OPT_PT_KERNEL, 0, 1},
+        };
+        for (const auto& e : kEnv) {
+            const char* v = getenv(e.name);
+            if (!v || !*v) continue;
+            long x = strtol(v, nullptr, 0);
+            if (x >= e.lo && x <= e.hi) p->options[e.key] = (int)x;
+            else fprintf(stderr, "libsvr_b200: ignoring %s=%s (out of range)\n", e.name, v);
+        }
         return p;
     }();
     return *s;
