@@ -85,8 +85,9 @@ enum svr_option {
     /* threads per block of the path tracer / ray caster (tuning) */
     SVR_OPT_PT_BLOCK = 7,
     SVR_OPT_RC_BLOCK = 8,
-    /* path-tracer kernel shape: 1 = megakernel (one path at a time per lane; default, measured
-     * fastest), 0 = phase-scheduled warp (generate / march / collide / event / bounce phases, the warp
+    /* path-tracer kernel shape: 2 = sample-parallel warp (the lanes of a warp take different samples of
+     * the same pixel), 1 = megakernel (one pixel per lane, samples one after the other),
+     * 0 = phase-scheduled warp (generate / march / collide / event / bounce phases, the warp
      * votes each round and runs the phase most lanes wait in) */
     SVR_OPT_PT_KERNEL = 9,
     /* phase-scheduled kernel: macrocell visits per MARCH round (0 = default 4) */
@@ -98,6 +99,11 @@ enum svr_option {
      * samples can be advanced through empty macrocells; 0 = every sample walks from the volume face.
      * Images are bit-identical either way (only empty cells are skipped). */
     SVR_OPT_PT_ENTRY_CACHE = 12,
+    /* sample-parallel kernel (SVR_OPT_PT_KERNEL = 2): pixels a warp renders one after the other (1..64),
+     * and the smallest batch (samples per pixel per launch) it is used for; smaller batches run the
+     * megakernel.  Images differ from the other shapes only in float summation order. */
+    SVR_OPT_PT_WARP_PIXELS = 13,
+    SVR_OPT_PT_WARP_MIN_SPP = 14,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

@@ -25,15 +25,19 @@ HostState& state()
         p->options[SVR_OPT_COUNTERS] = 0;
         p->options[SVR_OPT_PT_BLOCK] = 128;
         p->options[SVR_OPT_RC_BLOCK] = 128;
-        p->options[SVR_OPT_PT_KERNEL] = 1;  // megakernel: measured 2.5x faster than the phase-scheduled shape (profiles/r01)
+        // sample-parallel warp for batches of >= 32 spp (1.37x the megakernel on C3, profiles/r01), megakernel below;
+        // the phase-scheduled shape measured 2.5x slower than the megakernel
+        p->options[SVR_OPT_PT_KERNEL] = 2;
         p->options[SVR_OPT_LEAP] = 1;
         p->options[SVR_OPT_PT_ENTRY_CACHE] = 1;
+        p->options[SVR_OPT_PT_WARP_PIXELS] = 4;
+        p->options[SVR_OPT_PT_WARP_MIN_SPP] = 32;
         // A host that only knows the reference's seven entry points (gui/canvas.cpp) cannot call
         // svr_set_option: the same switches are read once from the environment.
         static const struct { const char* name; int key, lo, hi; } kEnv[] = {
             {"SVR_PT_MODE", SVR_OPT_PT_MODE, 0, 2},           {"SVR_SHADOW_ESTIMATOR", SVR_OPT_SHADOW_ESTIMATOR, 0, 1},
             {"SVR_ENV_ENABLED", SVR_OPT_ENV_ENABLED, 0, 1},   {"SVR_RC_SKIP", SVR_OPT_RC_SKIP, 0, 1},
-            {"SVR_SEED", SVR_OPT_SEED, INT32_MIN, INT32_MAX}, {"SVR_PT_KERNEL", SVR_OPT_PT_KERNEL, 0, 1},
+            {"SVR_SEED", SVR_OPT_SEED, INT32_MIN, INT32_MAX}, {"SVR_PT_KERNEL", SVR_OPT_PT_KERNEL, 0, 2},
         };
         for (const auto& e : kEnv) {
             const char* v = getenv(e.name);
@@ -154,7 +158,13 @@ extern "C" int svr_set_option(int key, int value)
             if (value != 64 && value != 128 && value != 256) return fail_msg("block size must be 64, 128 or 256");
             break;
         case SVR_OPT_PT_KERNEL:
-            if (value != 0 && value != 1) return fail_msg("SVR_OPT_PT_KERNEL must be 0 or 1");
+            if (value < 0 || value > 2) return fail_msg("SVR_OPT_PT_KERNEL must be 0, 1 or 2");
+            break;
+        case SVR_OPT_PT_WARP_PIXELS:
+            if (value < 1 || value > 64) return fail_msg("SVR_OPT_PT_WARP_PIXELS must be in 1..64");
+            break;
+        case SVR_OPT_PT_WARP_MIN_SPP:
+            if (value < 1) return fail_msg("SVR_OPT_PT_WARP_MIN_SPP must be >= 1");
             break;
         case SVR_OPT_PT_ROUNDS:
             if (value < 0) return fail_msg("SVR_OPT_PT_ROUNDS must be >= 0");

@@ -53,6 +53,7 @@ struct PtLaunch {
     int32_t clearSum;
     int32_t marchBurst;    // phase-scheduled kernel: macrocell visits per MARCH round
     int32_t entryCache;    // 1 = per-pixel camera-ray entry cache (mode 2)
+    int32_t warpPixels;    // sample-parallel kernel: pixels one warp renders one after the other
 };
 
 template <int MODE>
@@ -533,6 +534,38 @@ SVR_DEV bool occluded_at(const Trk& trk, float t) { return (t > trk.tMin) && (t 
 // ---------------------------------------------------------------------------------------------
 // kernel shape 1: megakernel (the reference's loop nest)
 // ---------------------------------------------------------------------------------------------
+// One path: the reference's loop nest for one (pixel, sample); returns the sample's radiance.
+template <int MODE, bool COUNT>
+SVR_DEV float3 trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE>& ps, uint32_t idx, uint32_t idy, uint32_t offset,
+                            uint32_t sample, float tSkip, LocalCounters<COUNT>& lc)
+{
+    lc.add(SVR_CNT_PATHS, 1);
+    Next next = path_begin<MODE>(s, ps, idx, idy, offset, sample, tSkip) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+    if (a.traceDepth == 0) next = NEXT_PATH_DONE;  // the bounce loop never runs (pathtracer.cu:216): the sample is black
+    while (next != NEXT_PATH_DONE) {
+        float t = -FLT_MAX;
+        if (next == NEXT_TRACK) {
+            const int slot = ps.shadow ? SVR_CNT_SHADOW_TAPS : SVR_CNT_TRACK_TAPS;
+            float* ratio = (ps.shadow && s.shadowEstimator) ? &ps.ratioT : nullptr;
+            while (true) {
+                VisitResult v = ps.trk.template visit<COUNT>(s, ps.ray, ps.rng, lc);
+                if (v == VISIT_CONTINUE) continue;
+                if (v == VISIT_ESCAPED) break;
+                if (ps.trk.template collide<COUNT>(s, ps.ray, ps.rng, lc, slot, ratio)) {
+                    t = ps.trk.t;
+                    break;
+                }
+                if (ratio && ratio_roulette(ps.ratioT, ps.rng)) break;
+            }
+        }
+        if (next == NEXT_BOUNCE || ps.shadow)
+            next = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, t), a.traceDepth, lc);
+        else
+            next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
+    }
+    return ps.L;
+}
+
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
@@ -546,34 +579,44 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(
         const float tSkip = (MODE == 2 && a.entryCache) ? camera_entry_cache(s, idx, idy) : 0.f;
         float3 sum = f3(0.f);
         PathState<MODE> ps;
-        for (uint32_t n = 0; n < a.nSamples; ++n) {
-            lc.add(SVR_CNT_PATHS, 1);
-            Next next = path_begin<MODE>(s, ps, idx, idy, offset, a.firstSample + n, tSkip) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
-            if (a.traceDepth == 0) next = NEXT_PATH_DONE;  // the bounce loop never runs (pathtracer.cu:216): the sample is black
-            while (next != NEXT_PATH_DONE) {
-                float t = -FLT_MAX;
-                if (next == NEXT_TRACK) {
-                    const int slot = ps.shadow ? SVR_CNT_SHADOW_TAPS : SVR_CNT_TRACK_TAPS;
-                    float* ratio = (ps.shadow && s.shadowEstimator) ? &ps.ratioT : nullptr;
-                    while (true) {
-                        VisitResult v = ps.trk.template visit<COUNT>(s, ps.ray, ps.rng, lc);
-                        if (v == VISIT_CONTINUE) continue;
-                        if (v == VISIT_ESCAPED) break;
-                        if (ps.trk.template collide<COUNT>(s, ps.ray, ps.rng, lc, slot, ratio)) {
-                            t = ps.trk.t;
-                            break;
-                        }
-                        if (ratio && ratio_roulette(ps.ratioT, ps.rng)) break;
-                    }
-                }
-                if (next == NEXT_BOUNCE || ps.shadow)
-                    next = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, t), a.traceDepth, lc);
-                else
-                    next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
-            }
-            sum += ps.L;
-        }
+        for (uint32_t n = 0; n < a.nSamples; ++n) sum += trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, tSkip, lc);
         write_pixel(s, a, offset, sum);
+    }
+    lc.flush(cnt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel shape 2: sample-parallel warp.  The 32 lanes of a warp take 32 different SAMPLES of the
+// same pixel (sample = lane, lane + 32, ...), one pixel after the other over a short run of pixels.
+// All lanes shoot (nearly) the same camera ray: they walk the same macrocells in lockstep and their
+// fetches fall into the same texels, every lane has the same expected work, and the unit of
+// scheduling is a few pixels instead of a 16 x 8 tile x all samples, so expensive image regions
+// spread over all SMs.  The pixel's sum is a fixed-order butterfly over the lanes: deterministic.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_warp_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 5) + warp;
+    LocalCounters<COUNT> lc;
+    if (idy < a.y1) {
+        PathState<MODE> ps;
+        for (uint32_t i = 0; i < (uint32_t)a.warpPixels; ++i) {
+            const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
+            if (idx >= s.cam.imageW) break;
+            const uint32_t offset = idy * s.cam.imageW + idx;
+            const float tSkip = (MODE == 2 && a.entryCache) ? camera_entry_cache(s, idx, idy) : 0.f;
+            float3 sum = f3(0.f);
+            for (uint32_t n = lane; n < a.nSamples; n += 32u) sum += trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, tSkip, lc);
+            __syncwarp();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+                sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+                sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+            }
+            if (lane == 0) write_pixel(s, a, offset, sum);
+        }
     }
     lc.flush(cnt);
 }
@@ -709,7 +752,10 @@ __global__ void resolve_kernel(const float4* __restrict__ sum, float* __restrict
 template <int MODE>
 void launch_mode(int shape, dim3 grid, int block, cudaStream_t stream, const DevScene& sc, const PtLaunch& a, Counters* cnt)
 {
-    if (shape == 1) {
+    if (shape == 2) {
+        if (cnt) pathtrace_warp_kernel<MODE, true><<<grid, block, 0, stream>>>(sc, a, cnt);
+        else pathtrace_warp_kernel<MODE, false><<<grid, block, 0, stream>>>(sc, a, cnt);
+    } else if (shape == 1) {
         if (cnt) pathtrace_mega_kernel<MODE, true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_mega_kernel<MODE, false><<<grid, block, 0, stream>>>(sc, a, cnt);
     } else {
@@ -744,9 +790,16 @@ int launch_pathtrace(PtLaunch a)
         if (!cnt) return fail_msg("render_pathtracer: counter allocation failed");
     }
     const int block = st.options[SVR_OPT_PT_BLOCK];
-    const int shape = st.options[SVR_OPT_PT_KERNEL];
-    const uint32_t tileH = (uint32_t)block / 16u;
-    dim3 grid((sc.cam.imageW + 15u) / 16u, ((a.y1 - a.y0) + tileH - 1u) / tileH);
+    int shape = st.options[SVR_OPT_PT_KERNEL];
+    // the sample-parallel shape needs a warp's worth of samples per pixel; below that one lane per pixel
+    if (shape == 2 && a.nSamples < (uint32_t)st.options[SVR_OPT_PT_WARP_MIN_SPP]) shape = 1;
+    a.warpPixels = st.options[SVR_OPT_PT_WARP_PIXELS];
+    uint32_t tileW = 16u, tileH = (uint32_t)block / 16u;
+    if (shape == 2) {
+        tileW = (uint32_t)a.warpPixels;
+        tileH = (uint32_t)block / 32u;
+    }
+    dim3 grid((sc.cam.imageW + tileW - 1u) / tileW, ((a.y1 - a.y0) + tileH - 1u) / tileH);
     switch (mode) {
         case 0: launch_mode<0>(shape, grid, block, st.stream, sc, a, cnt); break;
         case 1: launch_mode<1>(shape, grid, block, st.stream, sc, a, cnt); break;

@@ -17,7 +17,9 @@ def small_config(name="S", n=64, w=128, h=128, fmt=L.VOXEL_U8, gen=L.GEN_SPHERE,
 def setup(r, cfg):
     """Loads cfg into the renderer; returns the voxels as a host numpy array (z, y, x)."""
     r.set_option(L.OPT_PT_MODE, 2)
-    r.set_option(L.OPT_PT_KERNEL, 1)
+    r.set_option(L.OPT_PT_KERNEL, 2)
+    r.set_option(L.OPT_PT_WARP_PIXELS, 4)
+    r.set_option(L.OPT_PT_WARP_MIN_SPP, 32)
     r.set_option(L.OPT_SHADOW_ESTIMATOR, 0)
     r.set_option(L.OPT_RC_SKIP, 1)
     r.set_option(L.OPT_LEAP, 1)

@@ -112,7 +112,7 @@ def _product_batches(r, batches, per_batch, depth):
     return np.stack(out)
 
 
-@pytest.mark.parametrize("mode,estimator,shape", [(1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0)])
+@pytest.mark.parametrize("mode,estimator,shape", [(2, 0, 2), (2, 1, 2), (1, 0, 2), (1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0)])
 def test_product_modes_are_statistically_the_reference(renderer, mode, estimator, shape):
     """Philox / local-majorant / ratio-tracking modes draw different random numbers from the same
     estimator.  Both sides render K disjoint batches; per 16x16 tile the batch means give a mean and a
@@ -163,6 +163,33 @@ def test_acceleration_toggles_are_bit_exact(renderer):
     assert float(imgs[0].max()) > 0
     for im in imgs[1:]:
         assert torch.equal(im, imgs[0])
+
+
+def test_sample_parallel_shape_equals_megakernel_up_to_summation_order(renderer):
+    """Kernel shape 2 hands the samples of a pixel to the lanes of a warp: every sample is the same
+    pure function of (seed, pixel, sample), only the order of the float additions differs."""
+    cfg = small_config(n=96, w=150, h=101, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=3)
+    setup(renderer, cfg)
+    for mode, spp in ((2, 64), (2, 40), (0, 33), (1, 7)):
+        renderer.set_option(L.OPT_PT_MODE, mode)
+        renderer.set_option(L.OPT_PT_WARP_MIN_SPP, 1)
+        imgs = {}
+        for shape, wp, blk, cache in ((1, 4, 128, 1), (2, 4, 128, 1), (2, 1, 64, 0), (2, 7, 256, 1)):
+            renderer.set_option(L.OPT_PT_KERNEL, shape)
+            renderer.set_option(L.OPT_PT_WARP_PIXELS, wp)
+            renderer.set_option(L.OPT_PT_BLOCK, blk)
+            renderer.set_option(L.OPT_PT_ENTRY_CACHE, cache)
+            renderer.frame_no = 0
+            renderer.render_pathtracer_spp(spp, 3)
+            torch.cuda.synchronize()
+            imgs[(shape, wp, blk, cache)] = renderer.hdr_image().clone()
+        base = imgs[(1, 4, 128, 1)]
+        assert float(base.max()) > 0
+        assert torch.allclose(imgs[(2, 4, 128, 1)], base, rtol=2e-5, atol=1e-6)
+        # launch geometry and the entry cache do not enter the result at all
+        assert torch.equal(imgs[(2, 1, 64, 0)], imgs[(2, 4, 128, 1)])
+        assert torch.equal(imgs[(2, 7, 256, 1)], imgs[(2, 4, 128, 1)])
+    renderer.set_option(L.OPT_PT_BLOCK, 128)
 
 
 def test_deterministic_and_seeded(renderer):
