@@ -311,6 +311,8 @@ int ensure_grid(DevScene* scene, bool force)
     g.cell = st.gridCell;
     g.scale = f3((float)st.volDims.x / (float)st.gridCell, (float)st.volDims.y / (float)st.gridCell,
                  (float)st.volDims.z / (float)st.gridCell);
+    g.toCell = f3(vol.bbox.invSize) * g.scale;
+    g.cellOff = f3(vol.bbox.vmin) * g.toCell;
     return 0;
 }
 

@@ -36,6 +36,9 @@
 #ifndef SVR_PT_MIN_BLOCKS
 #define SVR_PT_MIN_BLOCKS 1
 #endif
+#ifndef SVR_PT_MAX_THREADS
+#define SVR_PT_MAX_THREADS 256
+#endif
 
 namespace svr {
 Counters* device_counters();
@@ -116,8 +119,8 @@ struct CellRay {
     float eps;  // ray-parameter step that moves 1e-3 cell along the fastest axis
     SVR_DEV void init(const DevScene& s, const Ray& ray)
     {
-        const float3 toCell = f3(s.vol.bbox.invSize) * s.grid.scale;
-        const float3 g0 = (ray.orig - f3(s.vol.bbox.vmin)) * toCell;
+        const float3 toCell = s.grid.toCell;
+        const float3 g0 = ray.orig * toCell - s.grid.cellOff;
         const float3 dg = ray.dir * toCell;
         // an axis the ray does not move along never produces a crossing: 0 * bound + FLT_MAX
         invDg.x = dg.x != 0.f ? 1.f / dg.x : 0.f;
@@ -145,8 +148,7 @@ struct CellRay {
     // cell containing the ray at parameter te, as floats and ints
     SVR_DEV void locate(const DevScene& s, const Ray& ray, float te, float3* cf, int* ix, int* iy, int* iz) const
     {
-        const float3 toCell = f3(s.vol.bbox.invSize) * s.grid.scale;
-        const float3 off = f3(s.vol.bbox.vmin) * toCell;
+        const float3 toCell = s.grid.toCell, off = s.grid.cellOff;
         cf->x = floorf(fmaf(fmaf(te, ray.dir.x, ray.orig.x), toCell.x, -off.x));
         cf->y = floorf(fmaf(fmaf(te, ray.dir.y, ray.orig.y), toCell.y, -off.y));
         cf->z = floorf(fmaf(fmaf(te, ray.dir.z, ray.orig.z), toCell.z, -off.z));
@@ -246,18 +248,28 @@ struct TrackOf<2> {
     typedef TrackLocal type;
 };
 
-// Per-pixel camera-ray entry cache (mode 2).  All samples of a pixel shoot nearly the same camera
-// ray: with a pinhole (aperture 0) they share the origin and differ by at most half a pixel diagonal
-// in direction, i.e. by less than one macrocell sideways anywhere inside the volume.  The pixel's
-// centre ray is walked ONCE with every empty cube shrunk by one cell; as long as it stays in empty
-// space, every jittered ray of the pixel is in empty space too.  Returns the parameter up to which
-// camera rays of this pixel may be advanced before they start walking cells: 0 when nothing can be
-// said, FLT_MAX when no sample of the pixel can ever reach a non-empty cell.  Only empty cells are
-// skipped and no random number is consumed, so images are bit-identical with the cache off.
-SVR_DEV float camera_entry_cache(const DevScene& s, uint32_t idx, uint32_t idy)
+// What is known about ALL camera rays of a pixel before any sample is drawn.  With a pinhole
+// (aperture 0) the samples of a pixel share the origin and differ by at most half a pixel diagonal in
+// direction, so one look along the pixel's centre ray bounds what every jittered ray can meet:
+//   lights : some camera ray of the pixel may hit an area-light disk (get_nearest_light_sample,
+//            pathtracer.cu:214-215, has to be evaluated);
+//   empty  : no camera ray of the pixel can reach a non-empty macrocell (mode 2): every sample escapes;
+//   tSkip  : parameter up to which every camera ray of the pixel runs through empty macrocells
+//            (mode 2; 0 when nothing can be said).
+// Only empty space is skipped and no random number is consumed, so images do not change.
+struct PixelInfo {
+    float tSkip;
+    bool lights, empty;
+};
+
+SVR_DEV PixelInfo classify_pixel(const DevScene& s, uint32_t idx, uint32_t idy, bool haveGrid, bool walk)
 {
+    PixelInfo pi;
+    pi.tSkip = 0.f;
+    pi.lights = s.numLights != 0;
+    pi.empty = false;
     const svr_camera& c = s.cam;
-    if (c.apeture != 0.f) return 0.f;
+    if (c.apeture != 0.f) return pi;
     Ray ray;
     {
         float nx = 2.f * (((float)idx + 0.5f) / ((float)c.imageW - 1.f)) - 1.f;
@@ -267,19 +279,53 @@ SVR_DEV float camera_entry_cache(const DevScene& s, uint32_t idx, uint32_t idy)
         ray.orig = f3(c.pos);
         ray.dir = normalize(nx * f3(c.u) + ny * f3(c.v) - f3(c.w));
     }
-    // walk the centre ray through the volume box grown by one cell (the grid's empty border), so that
-    // jittered rays that enter or leave the box slightly earlier / later are covered as well
+    // largest angle (radians, small) between the centre ray and any jittered ray of the pixel
+    const float hx = c.aspectRatio * c.tanFovxOverTwo / ((float)c.imageW - 1.f), hy = c.tanFovxOverTwo / ((float)c.imageH - 1.f);
+    const float alpha = sqrtf(hx * hx + hy * hy) * 1.05f;
+
+    // ---- lights: a ray hits a disk only if it passes within `radius` of the centre, in front of the origin
+    bool lights = false;
+    for (uint32_t i = 0; i < s.numLights; ++i) {
+        const float3 v = f3(s.lights[i].disk.center) - ray.orig;
+        const float dist = sqrtf(dot(v, v)), along = dot(v, ray.dir);
+        const float3 off = v - along * ray.dir;
+        const float reach = s.lights[i].disk.radius + dist * alpha * 1.1f;
+        // (NaN-safe: any comparison that fails keeps the light)
+        if (!(dot(off, off) > reach * reach) && !(along < -reach)) lights = true;
+    }
+    pi.lights = lights;
+    if (!haveGrid) return pi;
+
+    // ---- the macrocell grid along the centre ray
     CellRay cr;
     cr.init(s, ray);
-    float tA, tB;
-    cr.clip(f3(-1.f), f3((float)(s.grid.gx + 1), (float)(s.grid.gy + 1), (float)(s.grid.gz + 1)), &tA, &tB);
-    tA = fmaxf(tA, 0.f);
-    if (!(tA < tB)) return 0.f;  // centre ray misses even the grown box: a jittered ray may still clip a corner
-    // sideways spread of the pixel's rays at the far end must stay below one cell (in world units)
-    const float hx = c.aspectRatio * c.tanFovxOverTwo / ((float)c.imageW - 1.f), hy = c.tanFovxOverTwo / ((float)c.imageH - 1.f);
-    const float spread = tB * sqrtf(hx * hx + hy * hy) * 1.05f;
+    const int* occ = s.grid.occ;
+    const float3 lo = f3((float)__ldg(occ + 0), (float)__ldg(occ + 1), (float)__ldg(occ + 2));
+    const float3 hi = f3((float)(__ldg(occ + 3) + 1), (float)(__ldg(occ + 4) + 1), (float)(__ldg(occ + 5) + 1));
+    if (!(lo.x < hi.x)) {  // no occupied cell at all
+        pi.empty = true;
+        pi.tSkip = FLT_MAX;
+        return pi;
+    }
+    // sideways spread of the pixel's rays, in world units, at the farthest point of the occupied box
     const float3 cellWorld = f3((float)s.grid.cell) * f3(s.vol.spacing);
-    if (!(spread < 0.9f * fminf(fminf(cellWorld.x, cellWorld.y), cellWorld.z))) return 0.f;
+    const float minCell = fminf(fminf(cellWorld.x, cellWorld.y), cellWorld.z);
+    const float3 bc = f3(s.vol.bbox.vmin) + 0.5f * (lo + hi) * cellWorld - ray.orig;
+    const float3 bh = 0.5f * (hi - lo) * cellWorld;
+    const float farthest = sqrtf(dot(bc, bc)) + sqrtf(dot(bh, bh));
+    if (!(farthest * alpha < 0.9f * minCell)) return pi;
+    // occupied box grown by one cell: a jittered ray inside the occupied box keeps the centre ray inside this one
+    float tA, tB;
+    cr.clip(lo - f3(1.f), hi + f3(1.f), &tA, &tB);
+    tA = fmaxf(tA, 0.f);
+    if (!(tA < tB)) {
+        pi.empty = true;
+        pi.tSkip = FLT_MAX;
+        return pi;
+    }
+    if (!walk) return pi;
+    // walk the centre ray with every empty cube shrunk by one cell; as long as it stays in empty space,
+    // every jittered ray of the pixel is in empty space too
     float t = tA;
     for (int guard = 0; guard < 4096; ++guard) {
         const float te = t + cr.eps;
@@ -290,12 +336,17 @@ SVR_DEV float camera_entry_cache(const DevScene& s, uint32_t idx, uint32_t idy)
         iy = min(max(iy, -1), s.grid.gy);
         iz = min(max(iz, -1), s.grid.gz);
         const float m = s.grid.at(ix, iy, iz);
-        if (!(m <= -2.f)) return t;  // a non-empty cell is at most one cell away from the centre ray
+        if (!(m <= -2.f)) break;  // a non-empty cell is at most one cell away from the centre ray
         const float tE = cr.exit_t(cf, -m - 1.f);  // cube of radius d-2: the sideways cell stays inside the empty cube of radius d-1
-        if (tE >= tB) return FLT_MAX;
+        if (tE >= tB) {
+            pi.empty = true;
+            pi.tSkip = FLT_MAX;
+            return pi;
+        }
         t = fmaxf(tE, te);
     }
-    return t;
+    pi.tSkip = t;
+    return pi;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -378,6 +429,7 @@ struct PathState {
     float ratioT;     // ratio-tracking running transmittance
     ShadingType st;
     bool shadow;      // the tracked ray is a shadow ray
+    bool camLights;   // a camera ray of this pixel may hit a light (PixelInfo::lights)
 };
 
 // what a lane does next
@@ -409,7 +461,7 @@ SVR_DEV Next event_flight_end(const DevScene& s, PathState<MODE>& ps, float t, L
         // get_nearest_light_sample on the camera ray (pathtracer.cu:214-215, 220-229); the ray is still
         // the camera ray here, so the hit is evaluated at the event instead of living in registers
         LightHit ls;
-        if (nearest_light(s, ps.ray, &ls)) {
+        if (ps.camLights && nearest_light(s, ps.ray, &ls)) {
             float tt = t < 0.f ? FLT_MAX : t;
             if (ls.t < tt) {
                 float cosTerm = dot(ls.normal, -ps.ray.dir);
@@ -537,10 +589,16 @@ SVR_DEV bool occluded_at(const Trk& trk, float t) { return (t > trk.tMin) && (t 
 // One path: the reference's loop nest for one (pixel, sample); returns the sample's radiance.
 template <int MODE, bool COUNT>
 SVR_DEV float3 trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE>& ps, uint32_t idx, uint32_t idy, uint32_t offset,
-                            uint32_t sample, float tSkip, LocalCounters<COUNT>& lc)
+                            uint32_t sample, const PixelInfo& pi, LocalCounters<COUNT>& lc)
 {
     lc.add(SVR_CNT_PATHS, 1);
-    Next next = path_begin<MODE>(s, ps, idx, idy, offset, sample, tSkip) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+    if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
+        // every camera ray of this pixel escapes without meeting anything: the sample is the (constant) sky
+        if (a.traceDepth == 0 || !s.envEnabled) return f3(0.f);
+        return f3(s.env.defaultRadiance) * s.env.intensity;
+    }
+    ps.camLights = pi.lights;
+    Next next = path_begin<MODE>(s, ps, idx, idy, offset, sample, pi.tSkip) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
     if (a.traceDepth == 0) next = NEXT_PATH_DONE;  // the bounce loop never runs (pathtracer.cu:216): the sample is black
     while (next != NEXT_PATH_DONE) {
         float t = -FLT_MAX;
@@ -567,7 +625,7 @@ SVR_DEV float3 trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE
 }
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idx = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
@@ -576,10 +634,10 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(
     LocalCounters<COUNT> lc;
     if (inside) {
         const uint32_t offset = idy * s.cam.imageW + idx;
-        const float tSkip = (MODE == 2 && a.entryCache) ? camera_entry_cache(s, idx, idy) : 0.f;
+        const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
         float3 sum = f3(0.f);
         PathState<MODE> ps;
-        for (uint32_t n = 0; n < a.nSamples; ++n) sum += trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, tSkip, lc);
+        for (uint32_t n = 0; n < a.nSamples; ++n) sum += trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
         write_pixel(s, a, offset, sum);
     }
     lc.flush(cnt);
@@ -594,7 +652,7 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(
 // spread over all SMs.  The pixel's sum is a fixed-order butterfly over the lanes: deterministic.
 // ---------------------------------------------------------------------------------------------
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_warp_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtrace_warp_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 5) + warp;
@@ -605,9 +663,9 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_warp_kernel(
             const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
-            const float tSkip = (MODE == 2 && a.entryCache) ? camera_entry_cache(s, idx, idy) : 0.f;
+            const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
             float3 sum = f3(0.f);
-            for (uint32_t n = lane; n < a.nSamples; n += 32u) sum += trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, tSkip, lc);
+            for (uint32_t n = lane; n < a.nSamples; n += 32u) sum += trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
             __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -627,7 +685,7 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_warp_kernel(
 enum Phase { PH_GEN = 0, PH_MARCH = 1, PH_COLLIDE = 2, PH_EVENT = 3, PH_BOUNCE = 4, PH_DONE = 5 };
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_sched_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtrace_sched_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idx = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
@@ -641,7 +699,13 @@ __global__ void __launch_bounds__(256, SVR_PT_MIN_BLOCKS) pathtrace_sched_kernel
     uint32_t n = 0;
     int phase = inside ? PH_GEN : PH_DONE;
     float tEvent = -FLT_MAX;   // flight result handed to EVENT / BOUNCE
-    const float tSkip = (MODE == 2 && a.entryCache && inside) ? camera_entry_cache(s, idx, idy) : 0.f;
+    PixelInfo pi;
+    pi.tSkip = 0.f;
+    pi.lights = true;
+    pi.empty = false;
+    if (inside) pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
+    ps.camLights = pi.lights;
+    const float tSkip = pi.tSkip;
 
     while (true) {
         const unsigned mG = __ballot_sync(0xffffffffu, phase == PH_GEN);

@@ -23,6 +23,7 @@ struct DevGrid {
     int px, pxy;             // row and slice pitch of `cells`
     int cell;                // cell edge in voxels
     float3 scale;            // normalised texture coordinate -> cell coordinate (dims / cell)
+    float3 toCell, cellOff;  // world -> cell coordinate: p * toCell - cellOff  (toCell = invSize * scale, cellOff = vmin * toCell)
     SVR_DEV float at(int cx, int cy, int cz) const { return __ldg(cells + (cz * pxy + cy * px + cx)); }
 };
 
@@ -150,7 +151,10 @@ SVR_DEV Ray camera_ray_jittered(const svr_camera& c, uint32_t x, uint32_t y, Rng
     ny = ny * c.tanFovxOverTwo;
     nx = nx * c.focalLength;
     ny = ny * c.focalLength;
-    float2 a = uniform_sample_disk<EXACT_PI>(rng, c.apeture);
+    // EXACT_PI marks the reference-twin stream, which must consume the two lens draws even for a pinhole
+    // (sampling.h:28-29 via cuda_camera.h:80); the counter-based streams skip them when the aperture is closed
+    float2 a = make_float2(0.f, 0.f);
+    if (EXACT_PI || c.apeture != 0.f) a = uniform_sample_disk<EXACT_PI>(rng, c.apeture);
     Ray r;
     r.orig = f3(c.pos) + a.x * f3(c.u) + a.y * f3(c.v);
     r.dir = normalize((nx - a.x) * f3(c.u) + (ny - a.y) * f3(c.v) - c.focalLength * f3(c.w));

@@ -123,9 +123,15 @@ def test_product_modes_are_statistically_the_reference(renderer, mode, estimator
     cfg = small_config(gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=depth)
     setup(renderer, cfg)
     ref = reference(renderer, cfg)
-    rb, ref_all = _reference_batches(ref, 2 * K, per, depth)
-    ref_a, ref_b = rb[:K].mean(axis=0), rb[K:].mean(axis=0)
-    floor = rmse(ref_a, ref_b)
+    rb, ref_all = _reference_batches(ref, 4 * K, per, depth)
+    # Noise floor: four disjoint reference renders of K*per spp each.  The estimator is heavy tailed (a
+    # handful of firefly pixels carry most of the squared error, and the plain RMSE of two reference
+    # renders varies 2x from pairing to pairing), so radiance is clamped at the 99.5th percentile of the
+    # lit reference pixels and medians over the pairings are compared.
+    halves = [rb[i * K:(i + 1) * K].mean(axis=0) for i in range(4)]
+    cap = float(np.percentile(ref_all[ref_all > 0], 99.5))
+    crmse = lambda a, b: rmse(np.minimum(a, cap), np.minimum(b, cap))
+    floor = float(np.median([crmse(halves[i], halves[j]) for i in range(4) for j in range(i + 1, 4)]))
 
     renderer.set_option(L.OPT_PT_MODE, mode)
     renderer.set_option(L.OPT_SHADOW_ESTIMATOR, estimator)
@@ -133,7 +139,8 @@ def test_product_modes_are_statistically_the_reference(renderer, mode, estimator
     mb = _product_batches(renderer, K, per, depth)
     mine = mb.mean(axis=0)
     assert np.isfinite(mine).all()
-    assert rmse(mine, ref_a) <= 1.15 * floor, (rmse(mine, ref_a), floor)
+    err = float(np.median([crmse(mine, h) for h in halves]))
+    assert err <= 1.15 * floor, (err, floor)
 
     tm = np.stack([_tile_means(b) for b in mb])           # (K, th, tw, 3)
     tr = np.stack([_tile_means(b) for b in rb])           # (2K, th, tw, 3)
