@@ -112,30 +112,23 @@ def _product_batches(r, batches, per_batch, depth):
     return np.stack(out)
 
 
-@pytest.mark.parametrize("mode,estimator,shape", [(2, 0, 2), (2, 1, 2), (1, 0, 2), (1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0)])
-def test_product_modes_are_statistically_the_reference(renderer, mode, estimator, shape):
-    """Philox / local-majorant / ratio-tracking modes draw different random numbers from the same
-    estimator.  Both sides render K disjoint batches; per 16x16 tile the batch means give a mean and a
-    standard error, and the two means must agree: |m_new - m_ref| <= 4.5 * sqrt(se_new^2 + se_ref^2)
-    for >= 99.5% of the tiles (a Welch t statistic with ~14 degrees of freedom exceeds 4.5 with
-    probability 5e-4).  RMSE at equal spp must be within 1.15x the reference-vs-reference noise floor."""
-    depth, K, per = 4, 8, 64
-    cfg = small_config(gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=depth)
-    setup(renderer, cfg)
+def _statistical_parity(renderer, cfg, depth, K, per, configure, mean_tol=0.01):
+    """Both sides render disjoint batches of `per` spp (reference 4K of them, product K).  Checks:
+    (1) firefly-robust RMSE at equal spp (K*per) within 1.15x the reference-vs-reference noise floor --
+    radiance is clamped at the 99.5th percentile of the lit reference pixels and medians over the four
+    reference renders are compared, because a handful of firefly pixels carry most of the squared
+    error and the plain RMSE of two reference renders varies 2x from pairing to pairing;
+    (2) per 16x16 tile a Welch statistic on the batch means: |m_new - m_ref| <= 4.5 sqrt(se_new^2 +
+    se_ref^2) for >= 99.5% of the tiles; (3) image means within `mean_tol`."""
     ref = reference(renderer, cfg)
     rb, ref_all = _reference_batches(ref, 4 * K, per, depth)
-    # Noise floor: four disjoint reference renders of K*per spp each.  The estimator is heavy tailed (a
-    # handful of firefly pixels carry most of the squared error, and the plain RMSE of two reference
-    # renders varies 2x from pairing to pairing), so radiance is clamped at the 99.5th percentile of the
-    # lit reference pixels and medians over the pairings are compared.
+    del ref
     halves = [rb[i * K:(i + 1) * K].mean(axis=0) for i in range(4)]
     cap = float(np.percentile(ref_all[ref_all > 0], 99.5))
     crmse = lambda a, b: rmse(np.minimum(a, cap), np.minimum(b, cap))
     floor = float(np.median([crmse(halves[i], halves[j]) for i in range(4) for j in range(i + 1, 4)]))
 
-    renderer.set_option(L.OPT_PT_MODE, mode)
-    renderer.set_option(L.OPT_SHADOW_ESTIMATOR, estimator)
-    renderer.set_option(L.OPT_PT_KERNEL, shape)
+    configure()
     mb = _product_batches(renderer, K, per, depth)
     mine = mb.mean(axis=0)
     assert np.isfinite(mine).all()
@@ -143,14 +136,31 @@ def test_product_modes_are_statistically_the_reference(renderer, mode, estimator
     assert err <= 1.15 * floor, (err, floor)
 
     tm = np.stack([_tile_means(b) for b in mb])           # (K, th, tw, 3)
-    tr = np.stack([_tile_means(b) for b in rb])           # (2K, th, tw, 3)
+    tr = np.stack([_tile_means(b) for b in rb])           # (4K, th, tw, 3)
     se_m = tm.std(axis=0, ddof=1) / np.sqrt(tm.shape[0])
     se_r = tr.std(axis=0, ddof=1) / np.sqrt(tr.shape[0])
     den = np.sqrt(se_m ** 2 + se_r ** 2)
     num = np.abs(tm.mean(axis=0) - tr.mean(axis=0))
     z = np.where(den > 0, num / np.maximum(den, 1e-30), np.where(num > 0, np.inf, 0.0))
     assert (z < 4.5).mean() >= 0.995, float((z < 4.5).mean())
-    assert abs(mine.mean() - ref_all.mean()) < 0.01 * ref_all.mean()
+    assert abs(mine.mean() - ref_all.mean()) < mean_tol * ref_all.mean(), (mine.mean(), ref_all.mean())
+    return mine, ref_all
+
+
+@pytest.mark.parametrize("mode,estimator,shape", [(2, 0, 2), (2, 1, 2), (1, 0, 2), (1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0)])
+def test_product_modes_are_statistically_the_reference(renderer, mode, estimator, shape):
+    """Philox / local-majorant / ratio-tracking modes and all three kernel shapes draw different random
+    numbers from the same estimator as the reference's kernel_pathtracer."""
+    depth = 4
+    cfg = small_config(gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=depth)
+    setup(renderer, cfg)
+
+    def configure():
+        renderer.set_option(L.OPT_PT_MODE, mode)
+        renderer.set_option(L.OPT_SHADOW_ESTIMATOR, estimator)
+        renderer.set_option(L.OPT_PT_KERNEL, shape)
+
+    _statistical_parity(renderer, cfg, depth, 8, 64, configure)
 
 
 def test_acceleration_toggles_are_bit_exact(renderer):
@@ -384,3 +394,28 @@ def test_config_c3_full_size_properties(renderer):
     mine = imgs[0].cpu().numpy()
     assert rmse(mine, ref_a) <= 1.15 * floor
     assert abs(mine.mean() - ref_ab.mean()) < 0.02 * ref_ab.mean()
+    # the product configuration (sample-parallel kernel, 32-spp launches) against the reference, 256 spp
+    _statistical_parity(renderer, cfg, 1, 8, 32, lambda: None)
+
+
+def test_config_c4_full_size_statistics(renderer):
+    """C4: 1024^3 f16 high-albedo cloud, multiple scattering (traceDepth 32), 1920x1080 -- the regime
+    where paths are long, the volume (2 GiB) misses L2 and the macrocell majorants matter most."""
+    cfg = S.CONFIGS["C4"]
+    setup(renderer, cfg)
+    _statistical_parity(renderer, cfg, cfg.trace_depth, 8, 32, lambda: None, mean_tol=0.03)
+
+
+def test_config_c5_full_size_statistics(renderer):
+    """C5: 2048^3 u16 (16 GiB of voxels) at 3840x2160."""
+    if torch.cuda.get_device_properties(0).total_memory < 80 * 2 ** 30:
+        pytest.skip("needs ~40 GiB of device memory")
+    cfg = S.CONFIGS["C5"]
+    setup(renderer, cfg)
+    torch.cuda.empty_cache()
+    renderer.set_option(L.OPT_ENV_ENABLED, 0)  # the reference cannot add the sky (pathtracer.cu:233)
+    try:
+        _statistical_parity(renderer, cfg, 1, 4, 32, lambda: None, mean_tol=0.02)
+    finally:
+        setup(renderer, small_config())   # drop the 16 GiB array
+        torch.cuda.empty_cache()
