@@ -278,16 +278,18 @@ def run_ours(a):
     peak, peak_src = measured_peak()
     bytes_algo, taps = algorithmic_bytes(cnt, cfg.voxel_bytes, npix)
     achieved = bytes_algo / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    warp_shape = r.get_option(L.OPT_PT_KERNEL) == 2 and spp >= r.get_option(L.OPT_PT_WARP_MIN_SPP)
+    roofline_kernel = f"pathtrace_{'warp' if warp_shape else 'mega'}_kernel<{a.pt_mode},0>"
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
     try:
         with open(os.path.join(ROOT, "profiles", "r01", "traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("workload") == a.workload and tj.get("spp") == spp and tj.get("pt_mode") == a.pt_mode:
+        if tj.get("workload") == a.workload and tj.get("spp") == spp and tj.get("pt_mode") == a.pt_mode and tj.get("kernel") == roofline_kernel:
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {
-        "bound": "hbm", "kernel": "pathtrace_mega_kernel<2>" if a.pt_mode == 2 else f"pathtrace_mega_kernel<{a.pt_mode}>",
+        "bound": "hbm", "kernel": roofline_kernel,
         "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
         "traffic": traffic, "peak_source": peak_src,
         "bytes_algo_per_launch": int(bytes_algo), "taps_per_launch": int(taps), "tf_lookups_per_launch": int(cnt["tf_lookups"]),
@@ -304,6 +306,8 @@ def run_ours(a):
     ref_cuda = None
     if world == 1 and not a.no_ref_cuda:
         ref_cuda = reference_cuda_sample(cfg, r, 16)
+
+    raycast = raycast_lines(r) if world == 1 and not a.no_ref_cuda else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -324,6 +328,7 @@ def run_ours(a):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "reference_cuda": ref_cuda,
+        "raycast": raycast,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -357,6 +362,53 @@ def cpu_port_sample(cfg, r, vb, seconds, threads=None):
         "value": W * rows * frames / dt, "unit": UNIT, "cores": int(cores), "kind": "port",
         "sample": f"rows 8,24,..(every 16th: {rows} of {H}) x {W} px x {frames} frames of {cfg.name}, global majorant + XORWOW as the reference, {dt:.1f} s",
     }
+
+
+def raycast_lines(r):
+    """The metric's second half: ray-cast Mrays/s on C2 (256^3 u8, 1024x1024, front-to-back compositing
+    with the 1-D transfer function and gradient shading), ours and the reference's kernel_raycasting,
+    device-resident, best of 5 frames; plus the image difference between the two."""
+    import torch
+
+    from oracle import binding as B
+    from sunvolumerender_b200 import scene as S
+    from sunvolumerender_b200.render import setup_config
+
+    out = []
+    for tf in ("thin", "default"):
+        cfg = S.Config("C2", 256, 0, 1, 1024, 1024, tf)
+        setup_config(r, cfg)
+        step = S.raycast_step_size()
+        r.render_raycasting(step)
+        torch.cuda.synchronize()
+
+        def best_of(fn, n=5):
+            best = None
+            for _ in range(n):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            return best
+
+        ms = best_of(lambda: r.render_raycasting(step))
+        line = {"workload": f"C2: 256^3 u8 CT-like volume, 1024x1024, TF-{tf}", "value": cfg.width * cfg.height / (ms * 1e-3) / 1e6,
+                "unit": "Mrays/s", "ms_per_frame": ms}
+        try:
+            ref = B.RefCuda(cfg.width, cfg.height)
+            ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
+            ref.render_raycasting(step)
+            torch.cuda.synchronize()
+            rms = best_of(lambda: ref.render_raycasting(step))
+            line["reference_cuda"] = {"value": cfg.width * cfg.height / (rms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": rms}
+            line["max_u8_diff_vs_reference"] = int((r.ldr_image().int() - ref.ldr_image().int()).abs().max())
+        except (FileNotFoundError, OSError) as e:
+            line["reference_cuda"] = {"unavailable": str(e)}
+        out.append(line)
+    return out
 
 
 def reference_cuda_sample(cfg, r, frames):
