@@ -5,8 +5,10 @@
 // transfer-function / density-scale edit:
 //   1. range grid : per cell, min/max of every texel a trilinear fetch positioned inside the cell can
 //      touch.  A fetch at texel-space coordinate xb = u*N - 0.5 reads texels floor(xb) and
-//      floor(xb)+1, so positions inside cell c (u*N in [cC, (c+1)C)) read texels cC-1 .. (c+1)C;
-//      one more texel on each side absorbs the float rounding of world -> texture coordinates.
+//      floor(xb)+1, so positions inside cell c (u*N in [cC, (c+1)C)) read texels cC-1 .. (c+1)C.
+//      The same texels cover every position up to HALF A VOXEL outside the cell (u*N in
+//      [cC - 0.5, (c+1)C + 0.5)), which is orders of magnitude more slack than the float rounding of
+//      world -> cell and world -> texture coordinates needs (1e-5 voxel), so no further apron.
 //      Texels outside the array read 0 (border addressing, VolumeReader.cpp:164-166), and the
 //      fixed-point filter weights are a convex combination, so every filtered value lies in
 //      [min, max] of that footprint.
@@ -36,8 +38,8 @@ namespace {
 __global__ void range_kernel(cudaTextureObject_t pointTex, int3 vol, int3 grid, int cell, float2* out)
 {
     int cx = blockIdx.x, cy = blockIdx.y, cz = blockIdx.z;
-    int R = cell + 4;  // [cC-2, (c+1)C+1]
-    int x0 = cx * cell - 2, y0 = cy * cell - 2, z0 = cz * cell - 2;
+    int R = cell + 2;  // [cC-1, (c+1)C]
+    int x0 = cx * cell - 1, y0 = cy * cell - 1, z0 = cz * cell - 1;
     float mn = FLT_MAX, mx = -FLT_MAX;
     int total = R * R * R;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -302,6 +304,7 @@ int ensure_grid(DevScene* scene, bool force)
     DevGrid& g = scene->grid;
     g.px = st.gridDims.x + 2;
     g.pxy = g.px * (st.gridDims.y + 2);
+    g.pyF = (float)(st.gridDims.y + 2);
     g.cells = st.dMajorant + g.pxy + g.px + 1;  // interior cell (0,0,0)
     g.range = st.dRange;
     g.occ = st.dOcc;

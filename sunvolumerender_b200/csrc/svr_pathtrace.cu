@@ -113,57 +113,47 @@ struct TrackGlobal {
     }
 };
 
-// Cell-space description of a ray: a face at cell coordinate b is crossed at t = b * invDg - kk.
+// Cell-space description of a ray: g(t) = g0 + t * dg is the position in macrocell coordinates.
 struct CellRay {
-    float3 invDg, kk;
-    float eps;  // ray-parameter step that moves 1e-3 cell along the fastest axis
+    float3 g0, dg;
+    float3 invDg;  // 1 / dg; FLT_MAX on an axis the ray does not move along (its faces are never reached)
+    float eps;     // ray-parameter step that moves 1e-3 cell along the fastest axis
     SVR_DEV void init(const DevScene& s, const Ray& ray)
     {
         const float3 toCell = s.grid.toCell;
-        const float3 g0 = ray.orig * toCell - s.grid.cellOff;
-        const float3 dg = ray.dir * toCell;
-        // an axis the ray does not move along never produces a crossing: 0 * bound + FLT_MAX
-        invDg.x = dg.x != 0.f ? 1.f / dg.x : 0.f;
-        invDg.y = dg.y != 0.f ? 1.f / dg.y : 0.f;
-        invDg.z = dg.z != 0.f ? 1.f / dg.z : 0.f;
-        kk.x = dg.x != 0.f ? g0.x * invDg.x : -FLT_MAX;
-        kk.y = dg.y != 0.f ? g0.y * invDg.y : -FLT_MAX;
-        kk.z = dg.z != 0.f ? g0.z * invDg.z : -FLT_MAX;
+        g0 = ray.orig * toCell - s.grid.cellOff;
+        dg = ray.dir * toCell;
+        invDg.x = dg.x != 0.f ? 1.f / dg.x : FLT_MAX;
+        invDg.y = dg.y != 0.f ? 1.f / dg.y : FLT_MAX;
+        invDg.z = dg.z != 0.f ? 1.f / dg.z : FLT_MAX;
         eps = 1e-3f * fminf(fminf(dg.x != 0.f ? fabsf(invDg.x) : FLT_MAX, dg.y != 0.f ? fabsf(invDg.y) : FLT_MAX),
                             dg.z != 0.f ? fabsf(invDg.z) : FLT_MAX);
     }
-    // parameter interval inside the slab [lo, hi] (cell coordinates) on every axis
+    // parameter interval inside the slab [lo, hi] (cell coordinates) on every axis.  On a static axis
+    // both products are +-huge with the same sign outside the slab (empty interval) and opposite signs
+    // inside it (no constraint).
     SVR_DEV void clip(float3 lo, float3 hi, float* tA, float* tB) const
     {
-        const float ax = fmaf(lo.x, invDg.x, -kk.x), bx = fmaf(hi.x, invDg.x, -kk.x);
-        const float ay = fmaf(lo.y, invDg.y, -kk.y), by = fmaf(hi.y, invDg.y, -kk.y);
-        const float az = fmaf(lo.z, invDg.z, -kk.z), bz = fmaf(hi.z, invDg.z, -kk.z);
-        // a static axis yields (FLT_MAX, FLT_MAX): it constrains nothing here (the volume-box test did)
-        const float nx = invDg.x != 0.f ? fminf(ax, bx) : -FLT_MAX, fx = fmaxf(ax, bx);
-        const float ny = invDg.y != 0.f ? fminf(ay, by) : -FLT_MAX, fy = fmaxf(ay, by);
-        const float nz = invDg.z != 0.f ? fminf(az, bz) : -FLT_MAX, fz = fmaxf(az, bz);
-        *tA = fmaxf(fmaxf(nx, ny), nz);
-        *tB = fminf(fminf(fx, fy), fz);
+        const float ax = (lo.x - g0.x) * invDg.x, bx = (hi.x - g0.x) * invDg.x;
+        const float ay = (lo.y - g0.y) * invDg.y, by = (hi.y - g0.y) * invDg.y;
+        const float az = (lo.z - g0.z) * invDg.z, bz = (hi.z - g0.z) * invDg.z;
+        *tA = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        *tB = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
     }
-    // cell containing the ray at parameter te, as floats and ints
-    SVR_DEV void locate(const DevScene& s, const Ray& ray, float te, float3* cf, int* ix, int* iy, int* iz) const
+    // cell (as floats) containing the ray at parameter te
+    SVR_DEV float3 locate(float te) const
     {
-        const float3 toCell = s.grid.toCell, off = s.grid.cellOff;
-        cf->x = floorf(fmaf(fmaf(te, ray.dir.x, ray.orig.x), toCell.x, -off.x));
-        cf->y = floorf(fmaf(fmaf(te, ray.dir.y, ray.orig.y), toCell.y, -off.y));
-        cf->z = floorf(fmaf(fmaf(te, ray.dir.z, ray.orig.z), toCell.z, -off.z));
-        *ix = (int)cf->x;
-        *iy = (int)cf->y;
-        *iz = (int)cf->z;
+        return f3(floorf(fmaf(te, dg.x, g0.x)), floorf(fmaf(te, dg.y, g0.y)), floorf(fmaf(te, dg.z, g0.z)));
     }
-    // parameter at which the ray leaves the cube of `r` cells beyond cell cf on the far side
-    // (r = 1: the cell itself) and r - 1 cells on the near side
+    // parameter at which the ray leaves the cube of `r` cells beyond cell cf on the far side (r = 1: the
+    // cell itself) and r - 1 cells on the near side.  A function of the face alone, not of how the ray got
+    // here, so walks that start at different parameters (entry cache on / off) visit identical positions.
     SVR_DEV float exit_t(float3 cf, float r) const
     {
         const float n = 1.f - r;
-        const float tx = fmaf(cf.x + (invDg.x > 0.f ? r : n), invDg.x, -kk.x);
-        const float ty = fmaf(cf.y + (invDg.y > 0.f ? r : n), invDg.y, -kk.y);
-        const float tz = fmaf(cf.z + (invDg.z > 0.f ? r : n), invDg.z, -kk.z);
+        const float tx = (cf.x + (dg.x >= 0.f ? r : n) - g0.x) * invDg.x;
+        const float ty = (cf.y + (dg.y >= 0.f ? r : n) - g0.y) * invDg.y;
+        const float tz = (cf.z + (dg.z >= 0.f ? r : n) - g0.z) * invDg.z;
         return fminf(fminf(tx, ty), tz);
     }
 };
@@ -202,10 +192,8 @@ struct TrackLocal {
     SVR_DEV VisitResult visit(const DevScene& s, const Ray& ray, Philox&, LocalCounters<COUNT>& lc)
     {
         const float te = t + cr.eps;
-        float3 cf;
-        int ix, iy, iz;
-        cr.locate(s, ray, te, &cf, &ix, &iy, &iz);
-        const float m = s.grid.at(ix, iy, iz);
+        const float3 cf = cr.locate(te);
+        const float m = s.grid.at(cf);
         lc.add(SVR_CNT_CELLS, 1);
         // m > 0: majorant of this cell.  m < 0: empty, and so is the cube of radius -m-1 around it.
         const float sg = fmaxf(m, 0.f);
@@ -329,13 +317,11 @@ SVR_DEV PixelInfo classify_pixel(const DevScene& s, uint32_t idx, uint32_t idy, 
     float t = tA;
     for (int guard = 0; guard < 4096; ++guard) {
         const float te = t + cr.eps;
-        float3 cf;
-        int ix, iy, iz;
-        cr.locate(s, ray, te, &cf, &ix, &iy, &iz);
-        ix = min(max(ix, -1), s.grid.gx);
-        iy = min(max(iy, -1), s.grid.gy);
-        iz = min(max(iz, -1), s.grid.gz);
-        const float m = s.grid.at(ix, iy, iz);
+        float3 cf = cr.locate(te);
+        cf.x = fminf(fmaxf(cf.x, -1.f), (float)s.grid.gx);
+        cf.y = fminf(fmaxf(cf.y, -1.f), (float)s.grid.gy);
+        cf.z = fminf(fmaxf(cf.z, -1.f), (float)s.grid.gz);
+        const float m = s.grid.at(cf);
         if (!(m <= -2.f)) break;  // a non-empty cell is at most one cell away from the centre ray
         const float tE = cr.exit_t(cf, -m - 1.f);  // cube of radius d-2: the sideways cell stays inside the empty cube of radius d-1
         if (tE >= tB) {

@@ -4,8 +4,8 @@
 //    0, 0) followed by curand_uniform (pathtracer.cu:70-79, 205-206, 302).  With subsequence 0 and
 //    offset 0 cuRAND performs no skip-ahead, so the state is a closed form of the seed; only the
 //    six state words are kept (cuRAND's 48-byte state also carries Box-Muller fields).
-//  * Philox is the product stream: Philox2x32-10 (Salmon et al., SC'11), counter = (draw block,
-//    sample index), key = f(pixel, seed).  A path is a pure function of (seed, pixel, sample), so an
+//  * Philox is the product stream: Philox2x32-10 (Salmon et al., SC'11), counter = (sample index |
+//    draw block, f(pixel, seed)), fixed key.  A path is a pure function of (seed, pixel, sample), so an
 //    image does not depend on launch shape, on how samples are batched, or on how they are split
 //    across GPUs.
 #pragma once
@@ -60,34 +60,39 @@ struct XorwowCompat {
 };
 
 struct Philox {
-    uint32_t key, sample, block;
+    uint32_t c0;   // low counter word: sample index in the high 18 bits, draw-block number in the low 14
+    uint32_t c1;   // high counter word: pixel and seed
     uint32_t r1;   // second word of the current block
     uint32_t have; // 1 = r1 not yet consumed
 
     static constexpr uint32_t M = 0xD256D193u;  // Philox2x32 multiplier
     static constexpr uint32_t W = 0x9E3779B9u;  // Weyl key increment
+    static constexpr uint32_t K = 0x5EED5EEDu;  // the (fixed) key
+    static constexpr int BLOCK_BITS = 14;
 
+    // Philox2x32-10 is a keyed bijection of the 64-bit counter.  The stream identity (pixel, seed, sample)
+    // lives in the COUNTER and the key is a compile-time constant, so the ten round keys are immediates
+    // instead of ten registers.  A path that draws more than 2^14 blocks runs on into the counter range
+    // of the next sample index -- still deterministic, and far beyond what a path consumes.
     SVR_DEV void init(uint32_t seedKey, uint32_t pixel, uint32_t sample_)
     {
-        key = pixel * 0x9E3779B1u + seedKey;  // bijective in pixel for a fixed seed
-        sample = sample_;
-        block = 0;
+        c1 = pixel * 0x9E3779B1u + seedKey;  // bijective in pixel for a fixed seed
+        c0 = sample_ << BLOCK_BITS;
         have = 0;
         r1 = 0;
     }
     SVR_DEV void generate(uint32_t& o0, uint32_t& o1)
     {
-        uint32_t c0 = block++, c1 = sample, k = key;
+        uint32_t a = c0++, b = c1;
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
-            uint32_t hi = __umulhi(M, c0);
-            uint32_t lo = M * c0;
-            c0 = hi ^ k ^ c1;
-            c1 = lo;
-            k += W;
+            uint32_t hi = __umulhi(M, a);
+            uint32_t lo = M * a;
+            a = hi ^ (K + (uint32_t)i * W) ^ b;
+            b = lo;
         }
-        o0 = c0;
-        o1 = c1;
+        o0 = a;
+        o1 = b;
     }
     SVR_DEV uint32_t next_u32()
     {

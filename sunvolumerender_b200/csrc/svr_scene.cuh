@@ -24,7 +24,10 @@ struct DevGrid {
     int cell;                // cell edge in voxels
     float3 scale;            // normalised texture coordinate -> cell coordinate (dims / cell)
     float3 toCell, cellOff;  // world -> cell coordinate: p * toCell - cellOff  (toCell = invSize * scale, cellOff = vmin * toCell)
+    float pyF;               // rows per slice of `cells` (gy + 2), as a float
     SVR_DEV float at(int cx, int cy, int cz) const { return __ldg(cells + (cz * pxy + cy * px + cx)); }
+    // the same for integer-valued float coordinates; row index formed in fp32 (exact: rows * slices < 2^24)
+    SVR_DEV float at(float3 cf) const { return __ldg(cells + ((int)fmaf(cf.z, pyF, cf.y) * px + (int)cf.x)); }
 };
 
 struct DevScene {

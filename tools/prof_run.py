@@ -16,7 +16,7 @@ cfg = S.CONFIGS[sys.argv[2] if len(sys.argv) > 2 else "C3"]
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 spp = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-shape = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+shape = int(sys.argv[6]) if len(sys.argv) > 6 else 2
 view = sys.argv[7] if len(sys.argv) > 7 else "default"
 
 r = Renderer(0)
