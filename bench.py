@@ -170,6 +170,8 @@ def run_ours(a):
     r = Renderer(local)
     vb = setup_config(r, cfg)  # synthetic voxels generated on the device (svr_generate_volume)
     r.set_option(L.OPT_PT_MODE, a.pt_mode)
+    if a.cell:
+        r.set_option(L.OPT_MACROCELL_SIZE, a.cell)
     sum_buf = torch.zeros(npix * 4, dtype=torch.float32, device=dev)
     first = rank * spp
 
@@ -319,6 +321,7 @@ def run_ours(a):
             "spp_per_step_per_gpu": spp, "samples_per_step": npix * spp * world,
             "parallelism": f"spp-split x{world}, volume replicated, NCCL sum-reduce of float4 accumulators to rank 0" if world > 1 else "single GPU",
             "estimator": {0: "global majorant + XORWOW (reference twin)", 1: "global majorant + Philox", 2: "macrocell local majorants + Philox"}[a.pt_mode],
+            "macrocell": r.get_option(L.OPT_MACROCELL_SIZE),
             "l2": f"volume {vb.numel() >> 20} MiB > 126 MB L2 and incoherent taps; no flush between steps",
             "image_nonzero_fraction": round(img_nonzero, 4),
         },
@@ -522,6 +525,7 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel per step per GPU (0 = the workload's)")
     ap.add_argument("--pt-mode", type=int, default=2, choices=[0, 1, 2])
+    ap.add_argument("--cell", type=int, default=0, help="macrocell edge in voxels (0 = the library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")

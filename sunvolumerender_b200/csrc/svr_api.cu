@@ -154,6 +154,9 @@ extern "C" int svr_set_option(int key, int value)
             if (value != st.options[key]) release_grid(st);
             break;
         case SVR_OPT_PT_BLOCK:
+            // the path-tracing kernels are compiled for at most 128 threads per block (register budget)
+            if (value != 64 && value != 128) return fail_msg("path-tracer block size must be 64 or 128");
+            break;
         case SVR_OPT_RC_BLOCK:
             if (value != 64 && value != 128 && value != 256) return fail_msg("block size must be 64, 128 or 256");
             break;

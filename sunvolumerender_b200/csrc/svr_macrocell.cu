@@ -71,6 +71,63 @@ __global__ void range_kernel(cudaTextureObject_t pointTex, int3 vol, int3 grid, 
     }
 }
 
+// The same range grid for cell edges <= 16, a brick of cells per block: the brick's texels (plus the
+// one-texel apron) are fetched ONCE into shared memory -- 1.3-1.7 fetches per voxel instead of
+// (1 + 2/C)^3 -- and reduced separably (x, then y, then z).
+__global__ void __launch_bounds__(256) range_brick_kernel(cudaTextureObject_t pointTex, int3 grid, int cell, int3 brick, float2* out)
+{
+    extern __shared__ float smem[];
+    const int TX = brick.x * cell + 2, TY = brick.y * cell + 2, TZ = brick.z * cell + 2;
+    float* tex = smem;                                  // TX * TY * TZ texels
+    float2* rx = (float2*)(smem + TX * TY * TZ);        // brick.x * TY * TZ      (reduced along x)
+    float2* ry = rx + brick.x * TY * TZ;                // brick.x * brick.y * TZ (reduced along x, y)
+    const int cx0 = blockIdx.x * brick.x, cy0 = blockIdx.y * brick.y, cz0 = blockIdx.z * brick.z;
+    const int x0 = cx0 * cell - 1, y0 = cy0 * cell - 1, z0 = cz0 * cell - 1;
+    const int total = TX * TY * TZ;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int x = i % TX, y = (i / TX) % TY, z = i / (TX * TY);
+        // unnormalised point fetch at the texel centre; out-of-range reads the border value 0
+        tex[i] = tex3D<float>(pointTex, (float)(x0 + x) + 0.5f, (float)(y0 + y) + 0.5f, (float)(z0 + z) + 0.5f);
+    }
+    __syncthreads();
+    const int nx = brick.x * TY * TZ;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        int c = i % brick.x, y = (i / brick.x) % TY, z = i / (brick.x * TY);
+        const float* row = tex + (z * TY + y) * TX + c * cell;
+        float mn = row[0], mx = row[0];
+        for (int k = 1; k < cell + 2; ++k) {
+            mn = fminf(mn, row[k]);
+            mx = fmaxf(mx, row[k]);
+        }
+        rx[(z * TY + y) * brick.x + c] = make_float2(mn, mx);
+    }
+    __syncthreads();
+    const int ny = brick.x * brick.y * TZ;
+    for (int i = threadIdx.x; i < ny; i += blockDim.x) {
+        int c = i % brick.x, cy = (i / brick.x) % brick.y, z = i / (brick.x * brick.y);
+        float2 r = rx[(z * TY + cy * cell) * brick.x + c];
+        for (int k = 1; k < cell + 2; ++k) {
+            float2 v = rx[(z * TY + cy * cell + k) * brick.x + c];
+            r.x = fminf(r.x, v.x);
+            r.y = fmaxf(r.y, v.y);
+        }
+        ry[(z * brick.y + cy) * brick.x + c] = r;
+    }
+    __syncthreads();
+    const int nz = brick.x * brick.y * brick.z;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) {
+        int c = i % brick.x, cy = (i / brick.x) % brick.y, cz = i / (brick.x * brick.y);
+        float2 r = ry[((cz * cell) * brick.y + cy) * brick.x + c];
+        for (int k = 1; k < cell + 2; ++k) {
+            float2 v = ry[((cz * cell + k) * brick.y + cy) * brick.x + c];
+            r.x = fminf(r.x, v.x);
+            r.y = fmaxf(r.y, v.y);
+        }
+        int gx = cx0 + c, gy = cy0 + cy, gz = cz0 + cz;
+        if (gx < grid.x && gy < grid.y && gz < grid.z) out[((size_t)gz * grid.y + gy) * grid.x + gx] = r;
+    }
+}
+
 // level l, entry i: max(opacity[i .. min(i + 2^l, n) - 1])
 __global__ void tf_sparse_kernel(const float4* table, int n, int levels, float* sparse)
 {
@@ -132,47 +189,34 @@ __global__ void occ_init_kernel(int* occ)
     else if (threadIdx.x < 6) occ[threadIdx.x] = -1;
 }
 
-__global__ void dist_init_kernel(const float* majorant, size_t cells, uint8_t* dist)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cells) dist[i] = majorant[i] > 0.f ? 0 : 255;
-}
-
-// one Chebyshev dilation step: d'(c) = min(d(c), min over the 26 neighbours d + 1)
-__global__ void dist_pass_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int gx, int gy, int gz)
+// Chebyshev distance, in cells, from every cell to the nearest cell with a non-zero majorant, capped at
+// cap + 1.  d(c) = min over occupied c' of max(|dx|, |dy|, |dz|), and max distributes over min, so the
+// transform separates into three 1-D passes out[i] = min_j max(|i - j|, in[j]): 3 launches and <= 93
+// reads per cell instead of `cap` dilation passes of 27 reads each.
+//   FIRST: the input is the majorant grid itself (occupied = majorant > 0); LAST: the result is written back
+//   into the majorant grid as -(distance) for the empty cells.
+template <bool FIRST, bool LAST>
+__global__ void dist_axis_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, float* __restrict__ majorant, int gx, int gy,
+                                 int gz, int axis, int cap)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
     if (x >= gx || y >= gy) return;
-    size_t i = ((size_t)z * gy + y) * gx + x;
-    int best = src[i];
-    if (best != 0) {
-        int nb = 255;
-        for (int dz = -1; dz <= 1; ++dz) {
-            int zz = z + dz;
-            if (zz < 0 || zz >= gz) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                int yy = y + dy;
-                if (yy < 0 || yy >= gy) continue;
-                const uint8_t* row = src + ((size_t)zz * gy + yy) * gx;
-                for (int dx = -1; dx <= 1; ++dx) {
-                    int xx = x + dx;
-                    if (xx < 0 || xx >= gx) continue;
-                    nb = min(nb, (int)row[xx]);
-                }
-            }
-        }
-        if (nb < 255) best = min(best, nb + 1);
+    const size_t i = ((size_t)z * gy + y) * gx + x;
+    const int pos = axis == 0 ? x : (axis == 1 ? y : z), len = axis == 0 ? gx : (axis == 1 ? gy : gz);
+    const ptrdiff_t stride = axis == 0 ? 1 : (axis == 1 ? gx : (ptrdiff_t)gx * gy);
+    auto at = [&](ptrdiff_t j) -> int { return FIRST ? (majorant[j] > 0.f ? 0 : 255) : (int)src[j]; };
+    int best = at((ptrdiff_t)i);
+    for (int k = 1; k < best && k <= cap; ++k) {
+        int a = pos - k >= 0 ? at((ptrdiff_t)i - k * stride) : 255;
+        int b = pos + k < len ? at((ptrdiff_t)i + k * stride) : 255;
+        best = min(best, max(k, min(a, b)));
     }
-    dst[i] = (uint8_t)best;
-}
-
-// empty cells: majorant <- -(leap distance)
-__global__ void dist_store_kernel(const uint8_t* dist, size_t cells, float* majorant, int leap)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cells) return;
-    int d = dist[i];
-    if (d > 0) majorant[i] = leap ? -(float)min(d, SVR_LEAP_CAP + 1) : -1.f;
+    best = min(best, cap + 1);
+    if (LAST) {
+        if (best > 0) majorant[i] = -(float)best;
+    } else {
+        dst[i] = (uint8_t)best;
+    }
 }
 
 }  // namespace
@@ -243,9 +287,19 @@ int ensure_grid(DevScene* scene, bool force)
     }
     if (!st.rangeValid) {
         // ---- stage 1: range grid (again after svr_volume_upload: same allocations, new voxels)
-        dim3 g(st.gridDims.x, st.gridDims.y, st.gridDims.z);
-        int threads = cell >= 8 ? 128 : 64;
-        range_kernel<<<g, threads, 0, st.stream>>>(st.volPointTex, st.volDims, st.gridDims, cell, st.dRange);
+        if (cell <= 16) {
+            // brick = 32 x 8 x 8 voxels (32 x 16 x 16 for 16-voxel cells)
+            const int3 brick = make_int3(32 / cell, cell <= 8 ? 8 / cell : 1, cell <= 8 ? 8 / cell : 1);
+            const int TX = brick.x * cell + 2, TY = brick.y * cell + 2, TZ = brick.z * cell + 2;
+            const size_t shm = sizeof(float) * ((size_t)TX * TY * TZ + 2 * (size_t)brick.x * TY * TZ + 2 * (size_t)brick.x * brick.y * TZ);
+            dim3 g((st.gridDims.x + brick.x - 1) / brick.x, (st.gridDims.y + brick.y - 1) / brick.y, (st.gridDims.z + brick.z - 1) / brick.z);
+            if (shm > 48 * 1024)
+                SVR_TRY(cudaFuncSetAttribute(range_brick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            range_brick_kernel<<<g, 256, shm, st.stream>>>(st.volPointTex, st.gridDims, cell, brick, st.dRange);
+        } else {
+            dim3 g(st.gridDims.x, st.gridDims.y, st.gridDims.z);
+            range_kernel<<<g, 128, 0, st.stream>>>(st.volPointTex, st.volDims, st.gridDims, cell, st.dRange);
+        }
         count_launch();
         SVR_TRY(cudaGetLastError());
         st.rangeValid = true;
@@ -282,17 +336,12 @@ int ensure_grid(DevScene* scene, bool force)
         dim3 mb(32, 4, 1), mg((st.gridDims.x + 31) / 32, (st.gridDims.y + 3) / 4, st.gridDims.z);
         majorant_kernel<<<mg, mb, 0, st.stream>>>(st.dRange, st.gridDims, st.dTfSparse, n, vol.densityScale, st.dMajorant, st.dOcc);
         // ---- stage 3: leap distances for empty cells (border cells included)
-        const unsigned cb = (unsigned)((padded + 255) / 256);
-        dist_init_kernel<<<cb, 256, 0, st.stream>>>(st.dMajorant, padded, st.dDist[0]);
         dim3 pg((px + 31) / 32, (py + 3) / 4, pz);
-        int cur = 0;
-        const int passes = leap ? SVR_LEAP_CAP : 0;
-        for (int pass = 0; pass < passes; ++pass) {
-            dist_pass_kernel<<<pg, mb, 0, st.stream>>>(st.dDist[cur], st.dDist[cur ^ 1], px, py, pz);
-            cur ^= 1;
-        }
-        dist_store_kernel<<<cb, 256, 0, st.stream>>>(st.dDist[cur], padded, st.dMajorant, leap);
-        count_launch(5 + passes);
+        const int cap = leap ? SVR_LEAP_CAP : 0;
+        dist_axis_kernel<true, false><<<pg, mb, 0, st.stream>>>(nullptr, st.dDist[0], st.dMajorant, px, py, pz, 0, cap);
+        dist_axis_kernel<false, false><<<pg, mb, 0, st.stream>>>(st.dDist[0], st.dDist[1], nullptr, px, py, pz, 1, cap);
+        dist_axis_kernel<false, true><<<pg, mb, 0, st.stream>>>(st.dDist[1], nullptr, st.dMajorant, px, py, pz, 2, cap);
+        count_launch(6);
         SVR_TRY(cudaGetLastError());
         st.majorantValid = true;
         st.majorantDensityScale = vol.densityScale;

@@ -31,13 +31,15 @@
 #include "svr_rng.cuh"
 #include "svr_state.h"
 
-// Resident 256-thread blocks per SM the path-tracing kernels are compiled for: sets the register
-// budget (65536 / (256 * N)).  Chosen by measurement, see DESIGN.md.
+// Launch bounds of the path-tracing kernels: at most SVR_PT_MAX_THREADS threads per block and at least
+// SVR_PT_MIN_BLOCKS resident blocks per SM, i.e. a register budget of 65536 / (128 * 7) = 72 per thread
+// (28 warps per SM).  Chosen by measurement: unbounded the kernel takes 85
+// registers (20 warps per SM) and is 12% slower; at 64 registers it spills and gains nothing more.
 #ifndef SVR_PT_MIN_BLOCKS
-#define SVR_PT_MIN_BLOCKS 1
+#define SVR_PT_MIN_BLOCKS 7
 #endif
 #ifndef SVR_PT_MAX_THREADS
-#define SVR_PT_MAX_THREADS 256
+#define SVR_PT_MAX_THREADS 128
 #endif
 
 namespace svr {
@@ -117,7 +119,6 @@ struct TrackGlobal {
 struct CellRay {
     float3 g0, dg;
     float3 invDg;  // 1 / dg; FLT_MAX on an axis the ray does not move along (its faces are never reached)
-    float eps;     // ray-parameter step that moves 1e-3 cell along the fastest axis
     SVR_DEV void init(const DevScene& s, const Ray& ray)
     {
         const float3 toCell = s.grid.toCell;
@@ -126,9 +127,9 @@ struct CellRay {
         invDg.x = dg.x != 0.f ? 1.f / dg.x : FLT_MAX;
         invDg.y = dg.y != 0.f ? 1.f / dg.y : FLT_MAX;
         invDg.z = dg.z != 0.f ? 1.f / dg.z : FLT_MAX;
-        eps = 1e-3f * fminf(fminf(dg.x != 0.f ? fabsf(invDg.x) : FLT_MAX, dg.y != 0.f ? fabsf(invDg.y) : FLT_MAX),
-                            dg.z != 0.f ? fabsf(invDg.z) : FLT_MAX);
     }
+    // ray-parameter step that moves 1e-3 cell along the fastest axis
+    SVR_DEV float eps() const { return 1e-3f * fminf(fminf(fabsf(invDg.x), fabsf(invDg.y)), fabsf(invDg.z)); }
     // parameter interval inside the slab [lo, hi] (cell coordinates) on every axis.  On a static axis
     // both products are +-huge with the same sign outside the slab (empty interval) and opposite signs
     // inside it (no constraint).
@@ -164,7 +165,7 @@ struct CellRay {
 // face.  Occupied and empty cells run the same instructions, so lanes do not diverge inside the walk,
 // and no per-axis DDA state has to live in registers.
 struct TrackLocal {
-    float t, tMin, tMax;
+    float t, tMax;
     float tau;  // optical depth still to travel before the next tentative collision
     float sig;  // majorant of the cell the tentative collision lies in
     CellRay cr;
@@ -175,7 +176,7 @@ struct TrackLocal {
         if (!intersect_volume(s.vol, ray, &tNear, &tFar)) return false;
         // a NaN direction component slips through the slab test (fminf/fmaxf drop NaNs); it must not index the grid
         if (!(fabsf(ray.dir.x) + fabsf(ray.dir.y) + fabsf(ray.dir.z) < 4.f)) return false;
-        tMin = tNear < 0.f ? 1e-6f : tNear;
+        const float tMin = tNear < 0.f ? 1e-6f : tNear;
         cr.init(s, ray);
         // nothing can collide outside the box of non-empty cells, nor before the pixel's cached entry
         const int* occ = s.grid.occ;
@@ -191,7 +192,7 @@ struct TrackLocal {
     template <bool COUNT>
     SVR_DEV VisitResult visit(const DevScene& s, const Ray& ray, Philox&, LocalCounters<COUNT>& lc)
     {
-        const float te = t + cr.eps;
+        const float te = t + cr.eps();
         const float3 cf = cr.locate(te);
         const float m = s.grid.at(cf);
         lc.add(SVR_CNT_CELLS, 1);
@@ -316,7 +317,7 @@ SVR_DEV PixelInfo classify_pixel(const DevScene& s, uint32_t idx, uint32_t idy, 
     // every jittered ray of the pixel is in empty space too
     float t = tA;
     for (int guard = 0; guard < 4096; ++guard) {
-        const float te = t + cr.eps;
+        const float te = t + cr.eps();
         float3 cf = cr.locate(te);
         cf.x = fminf(fmaxf(cf.x, -1.f), (float)s.grid.gx);
         cf.y = fminf(fmaxf(cf.y, -1.f), (float)s.grid.gy);
@@ -406,7 +407,10 @@ struct PathState {
     typename RngOf<MODE>::type rng;
     typename TrackOf<MODE>::type trk;
     Ray ray;          // the ray being tracked (camera / bounce ray, or the shadow ray)
-    float3 L, T;
+    // L: radiance.  The reference-twin mode keeps the reference's order of additions -- L per path, paths
+    // summed (pathtracer.cu:208, 279) -- so L restarts with every path and `sum` collects the paths; the
+    // other modes add every contribution of every path of the pixel straight into L.
+    float3 L, sum, T;
     uint32_t k;
     // stash across the shadow ray
     VolumeSample vs;
@@ -429,7 +433,7 @@ SVR_DEV bool path_begin(const DevScene& s, PathState<MODE>& ps, uint32_t idx, ui
 {
     constexpr bool EXACT_PI = MODE == 0;
     ps.rng.init(s.seedKey, offset, sample);
-    ps.L = f3(0.f);
+    if (MODE == 0) ps.L = f3(0.f);
     ps.T = f3(1.f);
     ps.k = 0;
     ps.shadow = false;
@@ -566,22 +570,41 @@ SVR_DEV void write_pixel(const DevScene& s, const PtLaunch& a, uint32_t offset, 
 }
 
 // the flight's verdict for the binary transmittance estimator, transmittance.h:14-15
-template <class Trk>
-SVR_DEV bool occluded_at(const Trk& trk, float t) { return (t > trk.tMin) && (t < trk.tMax); }
+SVR_DEV bool occluded_at(const TrackGlobal& trk, float t) { return (t > trk.tMin) && (t < trk.tMax); }
+// local-majorant flights report either a collision strictly inside (tMin, tMax) or -FLT_MAX
+SVR_DEV bool occluded_at(const TrackLocal&, float t) { return t > -FLT_MAX; }
 
 // ---------------------------------------------------------------------------------------------
 // kernel shape 1: megakernel (the reference's loop nest)
 // ---------------------------------------------------------------------------------------------
-// One path: the reference's loop nest for one (pixel, sample); returns the sample's radiance.
+// Radiance accumulators of a pixel (see PathState::L)
+template <int MODE>
+SVR_DEV void pixel_begin(PathState<MODE>& ps)
+{
+    ps.L = f3(0.f);
+    ps.sum = f3(0.f);
+}
+template <int MODE>
+SVR_DEV void path_end(PathState<MODE>& ps)
+{
+    if (MODE == 0) ps.sum += ps.L;
+}
+template <int MODE>
+SVR_DEV float3 pixel_sum(const PathState<MODE>& ps) { return MODE == 0 ? ps.sum : ps.L; }
+
+// One path: the reference's loop nest for one (pixel, sample), added to the pixel's accumulators.
 template <int MODE, bool COUNT>
-SVR_DEV float3 trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE>& ps, uint32_t idx, uint32_t idy, uint32_t offset,
+SVR_DEV void trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE>& ps, uint32_t idx, uint32_t idy, uint32_t offset,
                             uint32_t sample, const PixelInfo& pi, LocalCounters<COUNT>& lc)
 {
     lc.add(SVR_CNT_PATHS, 1);
     if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
         // every camera ray of this pixel escapes without meeting anything: the sample is the (constant) sky
-        if (a.traceDepth == 0 || !s.envEnabled) return f3(0.f);
-        return f3(s.env.defaultRadiance) * s.env.intensity;
+        if (a.traceDepth != 0 && s.envEnabled) {
+            if (MODE == 0) ps.sum += f3(s.env.defaultRadiance) * s.env.intensity;
+            else ps.L += f3(s.env.defaultRadiance) * s.env.intensity;
+        }
+        return;
     }
     ps.camLights = pi.lights;
     Next next = path_begin<MODE>(s, ps, idx, idy, offset, sample, pi.tSkip) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
@@ -607,7 +630,7 @@ SVR_DEV float3 trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE
         else
             next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
     }
-    return ps.L;
+    path_end<MODE>(ps);
 }
 
 template <int MODE, bool COUNT>
@@ -621,10 +644,10 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     if (inside) {
         const uint32_t offset = idy * s.cam.imageW + idx;
         const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
-        float3 sum = f3(0.f);
         PathState<MODE> ps;
-        for (uint32_t n = 0; n < a.nSamples; ++n) sum += trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
-        write_pixel(s, a, offset, sum);
+        pixel_begin<MODE>(ps);
+        for (uint32_t n = 0; n < a.nSamples; ++n) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
+        write_pixel(s, a, offset, pixel_sum<MODE>(ps));
     }
     lc.flush(cnt);
 }
@@ -650,8 +673,9 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
             const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
-            float3 sum = f3(0.f);
-            for (uint32_t n = lane; n < a.nSamples; n += 32u) sum += trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
+            pixel_begin<MODE>(ps);
+            for (uint32_t n = lane; n < a.nSamples; n += 32u) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
+            float3 sum = pixel_sum<MODE>(ps);
             __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -681,7 +705,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     LocalCounters<COUNT> lc;
 
     PathState<MODE> ps;
-    float3 sum = f3(0.f);
+    pixel_begin<MODE>(ps);
     uint32_t n = 0;
     int phase = inside ? PH_GEN : PH_DONE;
     float tEvent = -FLT_MAX;   // flight result handed to EVENT / BOUNCE
@@ -753,7 +777,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
                 Next nx = event_flight_end<MODE, COUNT>(s, ps, tEvent, lc);
                 if (nx == NEXT_TRACK) phase = PH_MARCH;
                 else if (nx == NEXT_PATH_DONE) {
-                    sum += ps.L;
+                    path_end<MODE>(ps);
                     phase = PH_GEN;
                 } else {
                     // NEXT_BOUNCE: no shadow ray; NEXT_FLIGHT_MISSED: the shadow ray cannot collide
@@ -766,7 +790,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
                 Next nx = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, tEvent), a.traceDepth, lc);
                 if (nx == NEXT_TRACK) phase = PH_MARCH;
                 else if (nx == NEXT_PATH_DONE) {
-                    sum += ps.L;
+                    path_end<MODE>(ps);
                     phase = PH_GEN;
                 } else {
                     tEvent = -FLT_MAX;  // the bounce ray misses the (clipped) box
@@ -775,7 +799,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             }
         }
     }
-    if (inside) write_pixel(s, a, offset, sum);
+    if (inside) write_pixel(s, a, offset, pixel_sum<MODE>(ps));
     lc.flush(cnt);
 }
 

@@ -191,7 +191,7 @@ def test_sample_parallel_shape_equals_megakernel_up_to_summation_order(renderer)
         renderer.set_option(L.OPT_PT_MODE, mode)
         renderer.set_option(L.OPT_PT_WARP_MIN_SPP, 1)
         imgs = {}
-        for shape, wp, blk, cache in ((1, 4, 128, 1), (2, 4, 128, 1), (2, 1, 64, 0), (2, 7, 256, 1)):
+        for shape, wp, blk, cache in ((1, 4, 128, 1), (2, 4, 128, 1), (2, 1, 64, 0), (2, 7, 64, 1)):
             renderer.set_option(L.OPT_PT_KERNEL, shape)
             renderer.set_option(L.OPT_PT_WARP_PIXELS, wp)
             renderer.set_option(L.OPT_PT_BLOCK, blk)
@@ -205,7 +205,7 @@ def test_sample_parallel_shape_equals_megakernel_up_to_summation_order(renderer)
         assert torch.allclose(imgs[(2, 4, 128, 1)], base, rtol=2e-5, atol=1e-6)
         # launch geometry and the entry cache do not enter the result at all
         assert torch.equal(imgs[(2, 1, 64, 0)], imgs[(2, 4, 128, 1)])
-        assert torch.equal(imgs[(2, 7, 256, 1)], imgs[(2, 4, 128, 1)])
+        assert torch.equal(imgs[(2, 7, 64, 1)], imgs[(2, 4, 128, 1)])
     renderer.set_option(L.OPT_PT_BLOCK, 128)
 
 
@@ -226,7 +226,7 @@ def test_deterministic_and_seeded(renderer):
     assert not torch.equal(a, c)
     # launch shape does not enter the random streams
     renderer.set_option(L.OPT_SEED, 0x5EED)
-    renderer.set_option(L.OPT_PT_BLOCK, 256)
+    renderer.set_option(L.OPT_PT_BLOCK, 64)
     assert torch.equal(render(), a)
     renderer.set_option(L.OPT_PT_BLOCK, 128)
 
