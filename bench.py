@@ -144,6 +144,14 @@ def algorithmic_bytes(cnt, voxel_bytes, npix, passes=1):
     return taps * 8 * voxel_bytes + cnt["tf_lookups"] * 32 + passes * npix * 32, taps
 
 
+def grid_cell(r):
+    """Edge, in voxels, of the macrocell grid the library built for the scene (chosen automatically unless --cell)."""
+    dims, cell = (C.c_int32 * 3)(), C.c_int32()
+    if r.lib.svr_grid_info(dims, C.byref(cell)) != 0:
+        return None
+    return int(cell.value)
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -160,6 +168,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's own banner ("NCCL version ...") out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     cfg = S.CONFIGS[a.workload]
     spp = a.spp or cfg.spp
@@ -316,12 +327,13 @@ def run_ours(a):
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{cfg.name}: {cfg.n}^3 {['u8', 'u16', 'f16', 'f32'][cfg.fmt]} procedural CT-like volume, {W}x{H} path tracing, "
-                        f"Woodcock tracking, traceDepth {depth}, one area light + constant environment light, {spp} spp per step per GPU",
+            "workload": f"{cfg.name}: {cfg.n}^3 {['u8', 'u16', 'f16', 'f32'][cfg.fmt]} procedural {['sphere-falloff', 'CT-like', 'cloud'][cfg.gen]} volume, "
+                        f"{W}x{H} path tracing, Woodcock tracking, traceDepth {depth}, one area light"
+                        f"{' + constant environment light' if cfg.env else ''}, TF-{cfg.tf}, {spp} spp per step per GPU",
             "spp_per_step_per_gpu": spp, "samples_per_step": npix * spp * world,
             "parallelism": f"spp-split x{world}, volume replicated, NCCL sum-reduce of float4 accumulators to rank 0" if world > 1 else "single GPU",
             "estimator": {0: "global majorant + XORWOW (reference twin)", 1: "global majorant + Philox", 2: "macrocell local majorants + Philox"}[a.pt_mode],
-            "macrocell": r.get_option(L.OPT_MACROCELL_SIZE),
+            "macrocell": grid_cell(r),
             "l2": f"volume {vb.numel() >> 20} MiB > 126 MB L2 and incoherent taps; no flush between steps",
             "image_nonzero_fraction": round(img_nonzero, 4),
         },

@@ -74,7 +74,8 @@ enum svr_option {
     SVR_OPT_SHADOW_ESTIMATOR = 1,
     /* 0 = escaped paths add nothing (pathtracer.cu:233 is commented out); 1 = add envLight */
     SVR_OPT_ENV_ENABLED = 2,
-    /* macrocell edge in voxels (power of two, 4..32) */
+    /* macrocell edge in voxels: 0 (default) = chosen from the scene, about twice the mean free path inside
+     * the medium, re-evaluated when volume, transfer function or density scale change; or a power of two in 2..64 */
     SVR_OPT_MACROCELL_SIZE = 3,
     /* ray caster empty-space skipping through the macrocell grid: 0 off, 1 on (default) */
     SVR_OPT_RC_SKIP = 4,

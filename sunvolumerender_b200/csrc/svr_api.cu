@@ -19,7 +19,7 @@ HostState& state()
         p->options[SVR_OPT_PT_MODE] = 2;
         p->options[SVR_OPT_SHADOW_ESTIMATOR] = 0;
         p->options[SVR_OPT_ENV_ENABLED] = 0;
-        p->options[SVR_OPT_MACROCELL_SIZE] = 8;
+        p->options[SVR_OPT_MACROCELL_SIZE] = 0;  // chosen from the scene (svr_macrocell.cu: auto_cell)
         p->options[SVR_OPT_RC_SKIP] = 1;
         p->options[SVR_OPT_SEED] = 0x5EED;
         p->options[SVR_OPT_COUNTERS] = 0;
@@ -133,6 +133,9 @@ extern "C" int svr_set_device(int device)
     cudaFree(st.dTfSparse);
     cudaFree(st.dTfTable);
     cudaFree(st.dCounters);
+    cudaFree(st.dStats);
+    st.dStats = nullptr;
+    st.autoCell = 0;
     st.dTfSparse = nullptr;
     st.dTfTable = nullptr;
     st.tfEntries = 0;
@@ -150,8 +153,12 @@ extern "C" int svr_set_option(int key, int value)
             if (value < 0 || value > 2) return fail_msg("SVR_OPT_PT_MODE must be 0, 1 or 2");
             break;
         case SVR_OPT_MACROCELL_SIZE:
-            if (value < 2 || value > 64 || (value & (value - 1))) return fail_msg("SVR_OPT_MACROCELL_SIZE must be a power of two in 2..64");
-            if (value != st.options[key]) release_grid(st);
+            if (value != 0 && (value < 2 || value > 64 || (value & (value - 1))))
+                return fail_msg("SVR_OPT_MACROCELL_SIZE must be 0 (automatic) or a power of two in 2..64");
+            if (value != st.options[key]) {
+                release_grid(st);
+                st.autoCell = 0;
+            }
             break;
         case SVR_OPT_PT_BLOCK:
             // the path-tracing kernels are compiled for at most 128 threads per block (register budget)
@@ -350,6 +357,7 @@ extern "C" int svr_volume_upload(const svr_volume* vol, const void* data, int da
     SVR_TRY(cudaMemcpy3DAsync(&cp, st.stream));
     // same dims, new contents: the grid's allocations stay, its range stage reruns at the next render
     if (rd.res.array.array == st.gridArray) st.rangeValid = false;
+    st.uploadEpoch++;
     return 0;
 }
 
@@ -374,6 +382,7 @@ extern "C" int svr_tf_upload(svr_transfer_function* tf, const float* host_rgba, 
     for (uint32_t i = 0; i < n; ++i) maxOpacity = fmaxf(maxOpacity, host_rgba[4 * i + 3]);
     tf->maxOpacity = maxOpacity;
     st.majorantValid = false;
+    st.uploadEpoch++;
     return 0;
 }
 

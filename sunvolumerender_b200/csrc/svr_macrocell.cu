@@ -239,7 +239,30 @@ void release_grid(HostState& st)
     st.majorantValid = false;
 }
 
-int ensure_grid(DevScene* scene, bool force)
+// sum and count of the non-zero majorants (the statistic behind the automatic cell size)
+__global__ void majorant_stats_kernel(const float* __restrict__ majorant, size_t cells, double* sum, unsigned long long* count)
+{
+    float s = 0.f;
+    unsigned int c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (size_t)gridDim.x * blockDim.x) {
+        float m = majorant[i];
+        if (m > 0.f) {
+            s += m;
+            ++c;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0 && c) {
+        atomicAdd(sum, (double)s);
+        atomicAdd(count, (unsigned long long)c);
+    }
+}
+
+static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebuilt)
 {
     HostState& st = state();
     const svr_volume& vol = scene->vol;
@@ -253,7 +276,7 @@ int ensure_grid(DevScene* scene, bool force)
         return fail_msg("ensure_grid: textures must be bound to cudaArrays");
     cudaArray_t varr = vrd.res.array.array, tarr = trd.res.array.array;
 
-    const int cell = st.options[SVR_OPT_MACROCELL_SIZE];
+    if (majorantsRebuilt) *majorantsRebuilt = false;
     if (varr != st.gridArray || cell != st.gridCell || !st.dRange) {
         // ---- allocate for this (array, cell size)
         cudaChannelFormatDesc ch;
@@ -343,6 +366,7 @@ int ensure_grid(DevScene* scene, bool force)
         dist_axis_kernel<false, true><<<pg, mb, 0, st.stream>>>(st.dDist[1], nullptr, st.dMajorant, px, py, pz, 2, cap);
         count_launch(6);
         SVR_TRY(cudaGetLastError());
+        if (majorantsRebuilt) *majorantsRebuilt = true;
         st.majorantValid = true;
         st.majorantDensityScale = vol.densityScale;
         st.majorantTfArray = tarr;
@@ -365,6 +389,67 @@ int ensure_grid(DevScene* scene, bool force)
                  (float)st.volDims.z / (float)st.gridCell);
     g.toCell = f3(vol.bbox.invSize) * g.scale;
     g.cellOff = f3(vol.bbox.vmin) * g.toCell;
+    return 0;
+}
+
+// Macrocell edge from the scene (SVR_OPT_MACROCELL_SIZE = 0).  What a cell size costs is a trade between
+// visits (one per cell crossed) and null collisions (loose majorants in cells that straddle a boundary);
+// measured over the BASELINE configurations the fastest edge is about twice the mean free path inside
+// the medium (tools/gpu_cell_probe.py: opaque CT body, mean majorant 0.5 per voxel -> 4; cloud, 0.14 -> 16;
+// thin transfer function, 0.009 -> 32).  The statistic is the mean non-zero majorant of the current grid.
+static int auto_cell(HostState& st, int current, int* want)
+{
+    const size_t padded = (size_t)(st.gridDims.x + 2) * (st.gridDims.y + 2) * (st.gridDims.z + 2);
+    if (!st.dStats) SVR_TRY(cudaMalloc(&st.dStats, 16));
+    SVR_TRY(cudaMemsetAsync(st.dStats, 0, 16, st.stream));
+    majorant_stats_kernel<<<148 * 4, 256, 0, st.stream>>>(st.dMajorant, padded, (double*)st.dStats, (unsigned long long*)((char*)st.dStats + 8));
+    count_launch();
+    struct {
+        double sum;
+        unsigned long long count;
+    } h;
+    SVR_TRY(cudaMemcpyAsync(&h, st.dStats, 16, cudaMemcpyDeviceToHost, st.stream));
+    SVR_TRY(cudaStreamSynchronize(st.stream));
+    *want = current;
+    if (h.count == 0 || !(h.sum > 0.0)) return 0;  // nothing to track through: any size will do
+    const double ideal = log2(2.0 / (h.sum / (double)h.count));  // log2 of twice the mean free path, in voxels
+    // keep the current size unless the ideal is clearly nearer to another power of two (no flip-flopping
+    // between two sizes whose grids give slightly different statistics)
+    if (fabs(ideal - log2((double)current)) < 0.75) return 0;
+    int e = (int)floor(ideal + 0.5);
+    e = e < 2 ? 2 : (e > 5 ? 5 : e);
+    *want = 1 << e;
+    return 0;
+}
+
+int ensure_grid(DevScene* scene, bool force)
+{
+    HostState& st = state();
+    const int opt = st.options[SVR_OPT_MACROCELL_SIZE];
+    if (opt != 0) return build_grid(scene, force, opt, nullptr);
+    int cell = st.autoCell ? st.autoCell : 8;
+    int rc = build_grid(scene, force, cell, nullptr);
+    if (rc) return rc;
+    // re-evaluate when the scene behind the grid changed, not on every forced refresh (ray caster)
+    const bool sceneChanged = st.autoArray != st.gridArray || st.autoTfArray != st.majorantTfArray ||
+                              st.autoDensityScale != scene->vol.densityScale || st.autoEpoch != st.uploadEpoch;
+    if (st.autoCell && !sceneChanged) return 0;
+    // majorants grow with the cell they are taken over, so the statistic is looked at again on the grid of
+    // the size it suggested (at most twice; the 0.75-octave hysteresis in auto_cell settles it)
+    for (int round = 0; round < 3; ++round) {
+        int want = cell;
+        rc = auto_cell(st, cell, &want);
+        if (rc) return rc;
+        if (want == cell) break;
+        cell = want;
+        rc = build_grid(scene, force, cell, nullptr);
+        if (rc) return rc;
+    }
+    st.autoCell = cell;
+    st.autoArray = st.gridArray;
+    st.autoTfArray = st.majorantTfArray;
+    st.autoDensityScale = scene->vol.densityScale;
+    st.autoEpoch = st.uploadEpoch;
     return 0;
 }
 

@@ -40,6 +40,13 @@ struct HostState {
     float majorantDensityScale = 0.f;
     cudaArray_t majorantTfArray = nullptr;
 
+    // automatic macrocell size (SVR_OPT_MACROCELL_SIZE = 0): the choice and the scene it was made for
+    int autoCell = 0;
+    cudaArray_t autoArray = nullptr, autoTfArray = nullptr;
+    float autoDensityScale = 0.f;
+    unsigned autoEpoch = 0, uploadEpoch = 0;  // uploadEpoch counts svr_volume_upload / svr_tf_upload calls
+    void* dStats = nullptr;
+
     Counters* dCounters = nullptr;
     unsigned long long launches = 0;
     std::string lastError;

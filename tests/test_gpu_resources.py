@@ -137,3 +137,32 @@ def test_upload_into_bound_resources_equals_fresh_load(renderer):
     renderer.set_transfer_function(S.tf_table(cfg.tf))
     pt_d, rc_d = render()
     assert torch.equal(pt_a, pt_d) and torch.equal(rc_a, rc_d)
+
+
+def test_automatic_macrocell_size_follows_the_mean_free_path(renderer):
+    """SVR_OPT_MACROCELL_SIZE = 0: an opaque medium (mean free path ~2 voxels) gets 4-voxel cells, a thin
+    one large cells; the choice follows transfer-function edits and never changes a ray-cast image."""
+    cfg = small_config(n=64, w=96, h=96, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=1)
+    setup(renderer, cfg)
+
+    def cell_after_render():
+        renderer.frame_no = 0
+        renderer.render_pathtracer_spp(2, 1)
+        torch.cuda.synchronize()
+        dims, cell = (C.c_int32 * 3)(), C.c_int32()
+        L.check(renderer.lib.svr_grid_info(dims, C.byref(cell)))
+        return cell.value
+
+    renderer.set_option(L.OPT_MACROCELL_SIZE, 8)
+    fixed = raycast_f32(renderer).clone()
+    assert cell_after_render() == 8
+    renderer.set_option(L.OPT_MACROCELL_SIZE, 0)
+    assert cell_after_render() == 4                      # TF-default: opacity 0.5 per voxel inside the body
+    assert torch.equal(raycast_f32(renderer), fixed)     # skipping only removes exact zeros, whatever the cell size
+    renderer.set_transfer_function(S.tf_table("thin"))   # opacity <= 0.02: mean free path > 50 voxels
+    assert cell_after_render() == 32
+    renderer.set_transfer_function(S.tf_table("cloud"))
+    assert cell_after_render() in (8, 16)
+    renderer.set_volume_params(density_scale=0.05)       # thinner again through the density scale
+    assert cell_after_render() == 32
+    renderer.set_option(L.OPT_MACROCELL_SIZE, 8)
