@@ -44,7 +44,8 @@ def test_library_loads_and_binds():
     lib = L.load()
     assert lib.svr_version() == 100
     assert lib.svr_get_option(L.OPT_PT_MODE) == 2
-    assert lib.svr_get_option(L.OPT_MACROCELL_SIZE) == 8
+    assert lib.svr_get_option(L.OPT_MACROCELL_SIZE) == 0  # automatic
+    assert lib.svr_get_option(L.OPT_PT_KERNEL) == 2
     # option validation is host logic
     assert lib.svr_set_option(L.OPT_PT_MODE, 7) != 0
     assert b"SVR_OPT_PT_MODE" in lib.svr_last_error()
