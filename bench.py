@@ -386,6 +386,7 @@ def raycast_lines(r):
     import torch
 
     from oracle import binding as B
+    from sunvolumerender_b200 import _lib as L
     from sunvolumerender_b200 import scene as S
     from sunvolumerender_b200.render import setup_config
 
@@ -410,8 +411,24 @@ def raycast_lines(r):
             return best
 
         ms = best_of(lambda: r.render_raycasting(step))
+        # counted work of one frame (taps = trilinear fetches: 1 per step + 6 per shaded step, raycasting.cu:33,37)
+        r.set_option(L.OPT_COUNTERS, 1)
+        r.reset_counters()
+        r.render_raycasting(step)
+        torch.cuda.synchronize()
+        cnt = r.counters()
+        r.set_option(L.OPT_COUNTERS, 0)
+        # texture-unit ceiling on this volume: coherent, dependence-free tex3D taps (svr_microbench_taps)
+        sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+        taps_out = C.c_uint64(0)
+        tex_ms = best_of(lambda: L.check(r.lib.svr_microbench_taps(C.byref(r.volume), 0, 1 << 20, 512, C.c_void_p(sink.data_ptr()), C.byref(taps_out))), 3)
+        peak = taps_out.value / (tex_ms * 1e-3) / 1e9
         line = {"workload": f"C2: 256^3 u8 CT-like volume, 1024x1024, TF-{tf}", "value": cfg.width * cfg.height / (ms * 1e-3) / 1e6,
-                "unit": "Mrays/s", "ms_per_frame": ms}
+                "unit": "Mrays/s", "ms_per_frame": ms, "steps": cnt["steps"], "steps_skipped_as_empty": cnt["skipped"],
+                "taps": cnt["shade_taps"], "tf_lookups": cnt["tf_lookups"],
+                "roofline": {"bound": "l1tex", "achieved": cnt["shade_taps"] / (ms * 1e-3) / 1e9, "peak": peak, "unit": "Gtaps/s",
+                             "frac": cnt["shade_taps"] / (ms * 1e-3) / 1e9 / peak,
+                             "peak_source": "measured here: 2^20 threads x 512 coherent tex3D taps on the same volume"}}
         try:
             ref = B.RefCuda(cfg.width, cfg.height)
             ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)

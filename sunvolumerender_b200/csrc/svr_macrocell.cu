@@ -422,12 +422,13 @@ static int auto_cell(HostState& st, int current, int* want)
     return 0;
 }
 
-int ensure_grid(DevScene* scene, bool force)
+int ensure_grid(DevScene* scene, bool force, int maxAutoCell)
 {
     HostState& st = state();
     const int opt = st.options[SVR_OPT_MACROCELL_SIZE];
     if (opt != 0) return build_grid(scene, force, opt, nullptr);
     int cell = st.autoCell ? st.autoCell : 8;
+    if (cell > maxAutoCell) cell = maxAutoCell;
     int rc = build_grid(scene, force, cell, nullptr);
     if (rc) return rc;
     // re-evaluate when the scene behind the grid changed, not on every forced refresh (ray caster)
@@ -440,6 +441,7 @@ int ensure_grid(DevScene* scene, bool force)
         int want = cell;
         rc = auto_cell(st, cell, &want);
         if (rc) return rc;
+        if (want > maxAutoCell) want = maxAutoCell;
         if (want == cell) break;
         cell = want;
         rc = build_grid(scene, force, cell, nullptr);

@@ -123,7 +123,7 @@ int launch_raycast(uint32_t* img, float4* outf, const svr_volume* volume, const 
     const bool count = st.options[SVR_OPT_COUNTERS] != 0;
     if (skip) {
         // the TF content may have changed behind the same handles: refresh the majorants every call
-        int rc = ensure_grid(&sc, /*force=*/true);
+        int rc = ensure_grid(&sc, /*force=*/true, /*maxAutoCell=*/8);
         if (rc) return rc;
     } else {
         memset(&sc.grid, 0, sizeof(sc.grid));

@@ -83,7 +83,9 @@ int fail_msg(const char* msg);
 // Builds / refreshes the macrocell grid for (vol, tf) and fills scene->grid, scene->volDim.
 // `force` rebuilds the majorants even when the cache key matches (ray caster: the TF content can
 // change behind an unchanged handle, gui/transferfunction.cpp:128-151).
-int ensure_grid(DevScene* scene, bool force);
+// `maxAutoCell` caps the automatic cell size: delta tracking through a thin medium wants large cells, the
+// ray caster (which only skips empty space with the grid) never gains from cells above 8 voxels.
+int ensure_grid(DevScene* scene, bool force, int maxAutoCell = 32);
 
 inline void count_launch(int n = 1) { state().launches += (unsigned long long)n; }
 
