@@ -154,6 +154,47 @@ SIGNATURES = [
 ]
 
 
+# ---- include/svr_volume_io.h
+MET_UCHAR, MET_CHAR, MET_USHORT, MET_SHORT, MET_UINT, MET_INT, MET_FLOAT, MET_DOUBLE = range(8)
+
+
+class MetaImageHeader(C.Structure):  # svr_metaimage_header
+    _fields_ = [
+        ("ndims", C.c_uint32),
+        ("dim", C.c_uint32 * 3),
+        ("spacing", C.c_float * 3),
+        ("element_type", C.c_int32),
+        ("channels", C.c_uint32),
+        ("msb", C.c_int32),
+        ("compressed", C.c_int32),
+        ("header_size", C.c_int64),
+        ("compressed_size", C.c_uint64),
+        ("data_offset", C.c_uint64),
+        ("data_file", C.c_char * 1024),
+    ]
+
+
+class VolumeStats(C.Structure):  # svr_volume_stats
+    _fields_ = [
+        ("dim", C.c_uint32 * 3),
+        ("spacing", C.c_float * 3),
+        ("data_min", C.c_float),
+        ("data_max", C.c_float),
+        ("max_gradient_magnitude", C.c_float),
+        ("histogram_bins", C.c_uint32),
+        ("histogram_total", C.c_uint64),
+    ]
+
+
+SIGNATURES_IO = [
+    ("svr_metaimage_read_header", C.c_int, [C.c_char_p, C.POINTER(MetaImageHeader)]),
+    ("svr_volume_from_raw", C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float,
+                                      C.POINTER(Volume), C.POINTER(VolumeStats), _P, C.c_uint32]),
+    ("svr_volume_load_metaimage", C.c_int, [C.c_char_p, C.POINTER(Volume), C.POINTER(VolumeStats), _P, C.c_uint32]),
+    ("svr_volume_download", C.c_int, [C.POINTER(Volume), _P, C.c_uint64]),
+]
+
+
 class SvrError(RuntimeError):
     pass
 
@@ -172,7 +213,7 @@ def load():
             "sunvolumerender_b200 has no CPU or PyTorch fallback."
         )
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
-    for name, res, args in SIGNATURES:
+    for name, res, args in SIGNATURES + SIGNATURES_IO:
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args

@@ -89,6 +89,38 @@ class Renderer:
         self.lib.setup_volume(C.byref(vol))
         return vol
 
+    def load_metaimage(self, path, histogram_capacity=65536):
+        """Canvas::LoadVolume on a MetaImage file (gui/canvas.cpp:27-41 -> core/VolumeReader.cpp:13-94):
+        returns (stats, histogram)."""
+        self.free_volume()
+        vol, stats = L.Volume(), L.VolumeStats()
+        hist = np.zeros(histogram_capacity, np.uint32)
+        L.check(self.lib.svr_volume_load_metaimage(str(path).encode(), C.byref(vol), C.byref(stats), C.c_void_p(hist.ctypes.data), histogram_capacity),
+                "svr_volume_load_metaimage")
+        self.volume = vol
+        self.lib.setup_volume(C.byref(vol))
+        self.frame_no = 0
+        return stats, hist[: min(stats.histogram_bins, histogram_capacity)]
+
+    def load_raw(self, data, met_type, dims, spacing=(1.0, 1.0, 1.0), msb=False, histogram_capacity=65536):
+        """The preprocessing half of VolumeReader::Read for voxels already in host memory (any MetaImage element type)."""
+        self.free_volume()
+        data = np.ascontiguousarray(data)
+        vol, stats = L.Volume(), L.VolumeStats()
+        hist = np.zeros(histogram_capacity, np.uint32)
+        L.check(self.lib.svr_volume_from_raw(C.c_void_p(data.ctypes.data), met_type, 1 if msb else 0, dims[0], dims[1], dims[2],
+                                             spacing[0], spacing[1], spacing[2], C.byref(vol), C.byref(stats), C.c_void_p(hist.ctypes.data), histogram_capacity),
+                "svr_volume_from_raw")
+        self.volume = vol
+        self.lib.setup_volume(C.byref(vol))
+        self.frame_no = 0
+        return stats, hist[: min(stats.histogram_bins, histogram_capacity)]
+
+    def download_volume(self, dims, dtype=np.uint16):
+        out = np.zeros((dims[2], dims[1], dims[0]), dtype)
+        L.check(self.lib.svr_volume_download(C.byref(self.volume), C.c_void_p(out.ctypes.data), out.nbytes), "svr_volume_download")
+        return out
+
     def upload_volume(self, data):
         """Replace the voxels of the bound volume (same dims/format) from a host numpy array, a pinned
         host tensor or a device tensor."""

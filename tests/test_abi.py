@@ -13,8 +13,8 @@ from sunvolumerender_b200 import _lib as L
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_functions():
-    src = open(os.path.join(ROOT, "include", "svr_render.h")).read()
+def _declared_functions(header="svr_render.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"^\s*(?:[A-Za-z_][\w\s\*]*?)\b([A-Za-z_]\w*)\s*\([^;{]*\)\s*;", src, flags=re.M)
     return sorted(set(names))
@@ -24,6 +24,7 @@ def test_header_and_binding_agree():
     declared = _declared_functions()
     bound = sorted(n for n, _, _ in L.SIGNATURES)
     assert declared == bound
+    assert _declared_functions("svr_volume_io.h") == sorted(n for n, _, _ in L.SIGNATURES_IO)
 
 
 def test_reference_boundary_symbols_present():
@@ -36,7 +37,7 @@ def test_library_exports_every_declared_symbol():
     assert os.path.exists(L.LIB_PATH), "build with `make lib`"
     out = subprocess.check_output(["nm", "-D", "--defined-only", L.LIB_PATH], text=True)
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
-    missing = [n for n in _declared_functions() if n not in exported]
+    missing = [n for n in _declared_functions() + _declared_functions("svr_volume_io.h") if n not in exported]
     assert not missing, missing
 
 

@@ -5,7 +5,10 @@
 // CUDA events and writes the image as PPM (tone-mapped u8) and PFM (float accumulator).
 //
 //   svr_headless [--config C1|C2|C3|C4] [--mode pt|rc] [--spp N] [--depth D] [--batched 0|1]
-//                [--pt-mode 0|1|2] [--n N --w W --h H] [--out prefix] [--reps R]
+//                [--pt-mode 0|1|2] [--n N --w W --h H] [--out prefix] [--reps R] [--volume file.mhd|.mha]
+//
+// --volume loads a MetaImage file the way Canvas::LoadVolume does (core/VolumeReader.cpp:13-94) instead of
+// generating the configuration's synthetic volume; camera and light are framed on its extent.
 //
 // --batched 1 (default) renders the N samples in one svr_render_pathtracer_spp call; --batched 0
 // calls the reference entry point render_pathtracer N times with frameNo = 0..N-1, exactly the
@@ -20,6 +23,7 @@
 #include <vector>
 
 #include "svr_render.h"
+#include "svr_volume_io.h"
 
 #define CK(x)                                                                                   \
     do {                                                                                        \
@@ -75,7 +79,7 @@ static void tf_table(const std::string& kind, std::vector<float>& t)
 int main(int argc, char** argv)
 {
     Config cfg = kConfigs[0];
-    std::string mode = "pt", out = "svr_out";
+    std::string mode = "pt", out = "svr_out", volumePath;
     int batched = 1, ptMode = 2, reps = 3, sppArg = -1, depthArg = -1;
     for (int i = 1; i + 1 < argc; i += 2) {
         std::string k = argv[i], v = argv[i + 1];
@@ -93,12 +97,14 @@ int main(int argc, char** argv)
         else if (k == "--w") cfg.w = atoi(v.c_str());
         else if (k == "--h") cfg.h = atoi(v.c_str());
         else if (k == "--out") out = v;
+        else if (k == "--volume") volumePath = v;
         else if (k == "--reps") reps = atoi(v.c_str());
         else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
     }
     if (sppArg > 0) cfg.spp = sppArg;
     if (depthArg >= 0) cfg.depth = depthArg;
-    const int W = cfg.w, H = cfg.h, N = cfg.n;
+    const int W = cfg.w, H = cfg.h;
+    int N = cfg.n;
     const size_t npix = (size_t)W * H;
 
     SVR(svr_set_device(0));
@@ -106,13 +112,23 @@ int main(int argc, char** argv)
     SVR(svr_set_option(SVR_OPT_ENV_ENABLED, cfg.env));
 
     // ---- Canvas::LoadVolume (gui/canvas.cpp:27-41) with a synthetic volume instead of a MetaImage file
-    const size_t bpv = cfg.format == SVR_VOXEL_U8 ? 1 : (cfg.format == SVR_VOXEL_F32 ? 4 : 2);
-    void* dVox = nullptr;
-    CK(cudaMalloc(&dVox, (size_t)N * N * N * bpv));
-    SVR(svr_generate_volume(dVox, cfg.kind, cfg.format, N, cfg.seed));
     svr_volume vol;
-    SVR(svr_volume_create(&vol, dVox, 1, cfg.format, N, N, N, 1.f, 1.f, 1.f, 0.f));
-    CK(cudaFree(dVox));
+    if (!volumePath.empty()) {
+        svr_volume_stats vs;
+        SVR(svr_volume_load_metaimage(volumePath.c_str(), &vol, &vs, nullptr, 0));
+        const float ex = vs.dim[0] * vs.spacing[0], ey = vs.dim[1] * vs.spacing[1], ez = vs.dim[2] * vs.spacing[2];
+        N = (int)fmaxf(ex, fmaxf(ey, ez));  // the extent the camera and the light are framed on (gui/canvas.cpp:191-197)
+        fprintf(stderr, "loaded %s: %u x %u x %u, spacing %g %g %g, range [%g, %g], max |grad| %g, %u histogram bins\n", volumePath.c_str(),
+                vs.dim[0], vs.dim[1], vs.dim[2], vs.spacing[0], vs.spacing[1], vs.spacing[2], vs.data_min, vs.data_max,
+                vs.max_gradient_magnitude, vs.histogram_bins);
+    } else {
+        const size_t bpv = cfg.format == SVR_VOXEL_U8 ? 1 : (cfg.format == SVR_VOXEL_F32 ? 4 : 2);
+        void* dVox = nullptr;
+        CK(cudaMalloc(&dVox, (size_t)N * N * N * bpv));
+        SVR(svr_generate_volume(dVox, cfg.kind, cfg.format, N, cfg.seed));
+        SVR(svr_volume_create(&vol, dVox, 1, cfg.format, N, N, N, 1.f, 1.f, 1.f, 0.f));
+        CK(cudaFree(dVox));
+    }
     setup_volume(&vol);
 
     std::vector<float> table;
@@ -165,7 +181,8 @@ int main(int argc, char** argv)
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    const float stepSize = 0.5f * sqrtf(3.f);  // VolumeReader::GetElementBoundingSphereRadius, unit spacing
+    // VolumeReader::GetElementBoundingSphereRadius (core/VolumeReader.cpp:198-201): half the voxel diagonal
+    const float stepSize = 0.5f * sqrtf(vol.spacing.x * vol.spacing.x + vol.spacing.y * vol.spacing.y + vol.spacing.z * vol.spacing.z);
     float best = 1e30f;
     for (int rep = 0; rep < reps + 1; ++rep) {  // first pass warms up (and builds the macrocell grid)
         CK(cudaEventRecord(e0, 0));
