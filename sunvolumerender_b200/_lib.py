@@ -195,6 +195,23 @@ SIGNATURES_IO = [
 ]
 
 
+# ---- include/svr_tf_io.h
+class TfOpacityNode(C.Structure):  # svr_tf_opacity_node: vtkPiecewiseFunction node, 4 doubles
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("midpoint", C.c_double), ("sharpness", C.c_double)]
+
+
+class TfColorNode(C.Structure):  # svr_tf_color_node: vtkColorTransferFunction node, 6 doubles
+    _fields_ = [("x", C.c_double), ("r", C.c_double), ("g", C.c_double), ("b", C.c_double), ("midpoint", C.c_double), ("sharpness", C.c_double)]
+
+
+SIGNATURES_TF = [
+    ("svr_tf_build_table", C.c_int, [C.POINTER(TfOpacityNode), C.c_uint32, C.POINTER(TfColorNode), C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_float)]),
+    ("svr_tf_default_nodes", C.c_int, [C.POINTER(TfOpacityNode), C.POINTER(C.c_uint32), C.POINTER(TfColorNode), C.POINTER(C.c_uint32)]),
+    ("svr_tf_file_write", C.c_int, [C.c_char_p, C.POINTER(TfOpacityNode), C.c_uint32, C.POINTER(TfColorNode), C.c_uint32]),
+    ("svr_tf_file_read", C.c_int, [C.c_char_p, C.POINTER(TfOpacityNode), C.POINTER(C.c_uint32), C.POINTER(TfColorNode), C.POINTER(C.c_uint32)]),
+]
+
+
 class SvrError(RuntimeError):
     pass
 
@@ -213,7 +230,7 @@ def load():
             "sunvolumerender_b200 has no CPU or PyTorch fallback."
         )
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
-    for name, res, args in SIGNATURES + SIGNATURES_IO:
+    for name, res, args in SIGNATURES + SIGNATURES_IO + SIGNATURES_TF:
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args

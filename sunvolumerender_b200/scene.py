@@ -120,6 +120,33 @@ def tf_table(kind="default", n=TF_TABLE_SIZE):
     return np.ascontiguousarray(t)
 
 
+def build_tf_table(opacity_nodes, color_nodes, n=TF_TABLE_SIZE):
+    """TransferFunction's composite table from node lists (gui/transferfunction.cpp:17-29) through the C
+    ABI (svr_tf_build_table): opacity nodes (x, y[, midpoint, sharpness]), colour nodes (x, r, g, b[,
+    midpoint, sharpness]).  Returns (table n x 4 float32, maxOpacity)."""
+    import ctypes as C
+
+    lib = L.load()
+    on = (L.TfOpacityNode * max(1, len(opacity_nodes)))(*[L.TfOpacityNode(*(tuple(p) + (0.5, 0.0))[:4]) for p in opacity_nodes])
+    cn = (L.TfColorNode * max(1, len(color_nodes)))(*[L.TfColorNode(*(tuple(p) + (0.5, 0.0))[:6]) for p in color_nodes])
+    table = np.zeros((n, 4), np.float32)
+    mx = C.c_float()
+    L.check(lib.svr_tf_build_table(on, len(opacity_nodes), cn, len(color_nodes), C.c_void_p(table.ctypes.data), n, C.byref(mx)), "svr_tf_build_table")
+    return table, float(mx.value)
+
+
+def default_tf_nodes():
+    """The start-up transfer function of the application (gui/mainwindow.cpp:46-62) as node lists."""
+    import ctypes as C
+
+    lib = L.load()
+    on, cn = (L.TfOpacityNode * 16)(), (L.TfColorNode * 16)()
+    no, nc = C.c_uint32(16), C.c_uint32(16)
+    L.check(lib.svr_tf_default_nodes(on, C.byref(no), cn, C.byref(nc)), "svr_tf_default_nodes")
+    return ([(o.x, o.y, o.midpoint, o.sharpness) for o in on[: no.value]],
+            [(c.x, c.r, c.g, c.b, c.midpoint, c.sharpness) for c in cn[: nc.value]])
+
+
 def raycast_step_size(spacing=(1.0, 1.0, 1.0)):
     """VolumeReader::GetElementBoundingSphereRadius, core/VolumeReader.cpp:198-201 (passed at gui/canvas.cpp:92)."""
     return 0.5 * math.sqrt(sum(s * s for s in spacing))

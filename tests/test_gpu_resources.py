@@ -166,3 +166,38 @@ def test_automatic_macrocell_size_follows_the_mean_free_path(renderer):
     renderer.set_volume_params(density_scale=0.05)       # thinner again through the density scale
     assert cell_after_render() == 32
     renderer.set_option(L.OPT_MACROCELL_SIZE, 8)
+
+
+def test_application_default_transfer_function_renders_like_the_reference(renderer):
+    """The start-up transfer function of the application (gui/mainwindow.cpp:46-62: a sharpness-0.5 opacity
+    ramp, not the linear stand-in of the synthetic configurations), built by svr_tf_build_table, edited in
+    place, against the reference's kernels on the same table."""
+    from _gpu_common import reference
+
+    cfg = small_config(n=64, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=2)
+    setup(renderer, cfg)
+    op, col = S.default_tf_nodes()
+    table, mx = S.build_tf_table(op, col)
+    renderer.set_transfer_function(table)                      # in-place upload into the bound texture
+    assert renderer.tf.maxOpacity == pytest.approx(mx)
+    ref = reference(renderer, cfg, f32=True)
+    ref.render_raycasting(S.raycast_step_size())
+    mine = raycast_f32(renderer).cpu().numpy()
+    assert np.abs(mine - ref.ldr_image().cpu().numpy() / 255.0).max() <= 1e-4
+    # an edit of one opacity node (what dragging a point in the CTK widget does) is picked up by both renderers
+    op[5] = (0.5, 0.05, 0.5, 0.0)
+    table2, _ = S.build_tf_table(op, col)
+    renderer.set_transfer_function(table2)
+    ref = reference(renderer, cfg, f32=True)
+    ref.render_raycasting(S.raycast_step_size())
+    mine2 = raycast_f32(renderer).cpu().numpy()
+    assert np.abs(mine2 - ref.ldr_image().cpu().numpy() / 255.0).max() <= 1e-4
+    assert np.abs(mine2 - mine).max() > 1e-2
+    renderer.set_option(L.OPT_PT_MODE, 0)
+    renderer.frame_no = 0
+    renderer.render_pathtracer(2)
+    ref2 = reference(renderer, cfg)
+    ref2.render_pathtracer(1, 2)
+    torch.cuda.synchronize()
+    d = np.abs(renderer.hdr_image().cpu().numpy() - ref2.hdr_image().cpu().numpy()).max(axis=2)
+    assert (d <= 1e-4).mean() >= 0.999

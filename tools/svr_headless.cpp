@@ -5,10 +5,12 @@
 // CUDA events and writes the image as PPM (tone-mapped u8) and PFM (float accumulator).
 //
 //   svr_headless [--config C1|C2|C3|C4] [--mode pt|rc] [--spp N] [--depth D] [--batched 0|1]
-//                [--pt-mode 0|1|2] [--n N --w W --h H] [--out prefix] [--reps R] [--volume file.mhd|.mha]
+//                [--pt-mode 0|1|2] [--n N --w W --h H] [--out prefix] [--reps R] [--volume file.mhd|.mha] [--tf file.tf|app]
 //
 // --volume loads a MetaImage file the way Canvas::LoadVolume does (core/VolumeReader.cpp:13-94) instead of
 // generating the configuration's synthetic volume; camera and light are framed on its extent.
+// --tf loads a transfer function saved by the application (gui/transferfunction.cpp:55-88); `app` is the
+// application's start-up transfer function (gui/mainwindow.cpp:46-62).
 //
 // --batched 1 (default) renders the N samples in one svr_render_pathtracer_spp call; --batched 0
 // calls the reference entry point render_pathtracer N times with frameNo = 0..N-1, exactly the
@@ -23,6 +25,7 @@
 #include <vector>
 
 #include "svr_render.h"
+#include "svr_tf_io.h"
 #include "svr_volume_io.h"
 
 #define CK(x)                                                                                   \
@@ -79,7 +82,7 @@ static void tf_table(const std::string& kind, std::vector<float>& t)
 int main(int argc, char** argv)
 {
     Config cfg = kConfigs[0];
-    std::string mode = "pt", out = "svr_out", volumePath;
+    std::string mode = "pt", out = "svr_out", volumePath, tfPath;
     int batched = 1, ptMode = 2, reps = 3, sppArg = -1, depthArg = -1;
     for (int i = 1; i + 1 < argc; i += 2) {
         std::string k = argv[i], v = argv[i + 1];
@@ -98,6 +101,7 @@ int main(int argc, char** argv)
         else if (k == "--h") cfg.h = atoi(v.c_str());
         else if (k == "--out") out = v;
         else if (k == "--volume") volumePath = v;
+        else if (k == "--tf") tfPath = v;
         else if (k == "--reps") reps = atoi(v.c_str());
         else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
     }
@@ -133,6 +137,16 @@ int main(int argc, char** argv)
 
     std::vector<float> table;
     tf_table(cfg.tf, table);
+    if (!tfPath.empty()) {
+        svr_tf_opacity_node on[256];
+        svr_tf_color_node cn[256];
+        uint32_t no = 256, nc = 256;
+        if (tfPath == "app") SVR(svr_tf_default_nodes(on, &no, cn, &nc));
+        else SVR(svr_tf_file_read(tfPath.c_str(), on, &no, cn, &nc));
+        float maxOpacity = 0.f;
+        SVR(svr_tf_build_table(on, no, cn, nc, table.data(), SVR_TF_TABLE_SIZE, &maxOpacity));
+        fprintf(stderr, "transfer function %s: %u opacity nodes, %u colour nodes, max opacity %g\n", tfPath.c_str(), no, nc, maxOpacity);
+    }
     svr_transfer_function tf;
     SVR(svr_tf_create(&tf, table.data(), SVR_TF_TABLE_SIZE));
     setup_transferfunction(&tf);
