@@ -185,7 +185,7 @@ def test_application_default_transfer_function_renders_like_the_reference(render
     mine = raycast_f32(renderer).cpu().numpy()
     assert np.abs(mine - ref.ldr_image().cpu().numpy() / 255.0).max() <= 1e-4
     # an edit of one opacity node (what dragging a point in the CTK widget does) is picked up by both renderers
-    op[5] = (0.5, 0.05, 0.5, 0.0)
+    op[2], op[3] = (0.2, 0.02, 0.5, 0.0), (0.3, 0.02, 0.5, 0.9)   # the skin (intensity 0.25) turns nearly transparent
     table2, _ = S.build_tf_table(op, col)
     renderer.set_transfer_function(table2)
     ref = reference(renderer, cfg, f32=True)
