@@ -1,0 +1,30 @@
+/*
+ * svr_env_io.h -- C ABI of the environment-map input stage: what Lights::SetEnvironmentLight(filename)
+ * does with stb_image (core/lights/lights.cpp:31-75): a Radiance RGBE (.hdr) picture -> w x h float4
+ * lat-long texture (wrap, linear, normalised coordinates) -> cudaEnvironmentLight.
+ * Functions return 0 on success; svr_last_error() has the text otherwise.
+ */
+#ifndef SVR_ENV_IO_H
+#define SVR_ENV_IO_H
+
+#include "svr_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Decodes a Radiance .hdr file (#?RADIANCE / #?RGBE, FORMAT=32-bit_rle_rgbe, "-Y h +X w", flat or
+ * new-style run-length scanlines) to linear floats, channel = mantissa byte * 2^(exponent - 136) as
+ * stbi_loadf does.  Call with rgb_out == NULL to get the size; then with room for 3 * w * h floats.
+ * Host only: needs no GPU. */
+int svr_hdr_read(const char* path, float* rgb_out, uint32_t* w, uint32_t* h);
+
+/* Lights::SetEnvironmentLight(filename) (core/lights/lights.cpp:31-75): reads the file, expands RGB to
+ * float4 (alpha 0), creates the 2-D array + texture object and fills *out as cudaEnvironmentLight::Set(tex)
+ * does (intensity 1, offset 0).  Destroy with svr_env_destroy (svr_render.h). */
+int svr_env_load_hdr(const char* path, svr_env_light* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVR_ENV_IO_H */

@@ -115,20 +115,21 @@ class CpuOracle:
         return out
 
 
-def ref_lib_path(width, height, r32=False, f32=False):
+def ref_lib_path(width, height, r32=False, f32=False, env=False):
     h16 = (height + 15) // 16 * 16
-    suffix = "_r32" if r32 else ("_f32" if f32 else "")
+    suffix = "_r32" if r32 else ("_f32" if f32 else ("_env" if env else ""))
     return os.path.join(REF_DIR, f"libsvr_ref_{width}x{h16}{suffix}.so")
 
 
 _ref_cache = {}
 
 
-def ref(width, height, r32=False, f32=False):
+def ref(width, height, r32=False, f32=False, env=False):
     """The reference's own kernels for a WIDTH x HEIGHT canvas (HEIGHT rounded up to 16: the launch
     has no bounds guard, pathtracer.cu:294-295).  r32 = built with the shipped -maxrregcount=32;
-    f32 = float twin (img holds 4 floats per pixel, see glm_shim).  None when not prebuilt."""
-    path = ref_lib_path(width, height, r32, f32)
+    f32 = float twin (img holds 4 floats per pixel, see glm_shim); env = environment-light twin (the line
+    commented out at pathtracer.cu:233 re-enabled, see oracle/Makefile).  None when not prebuilt."""
+    path = ref_lib_path(width, height, r32, f32, env)
     if path in _ref_cache:
         return _ref_cache[path]
     if not os.path.exists(path):
@@ -148,14 +149,14 @@ class RefCuda:
     render_pathtracer per frame with frameNo = 0, 1, ... (canvas.cpp:96,116), or render_raycasting.
     Texture objects come from the caller (same descriptors as the reference's loaders)."""
 
-    def __init__(self, width, height, r32=False, f32=False, device=None):
+    def __init__(self, width, height, r32=False, f32=False, device=None, env=False):
         import torch
 
         self.torch = torch
         self.f32 = f32
-        self.lib = ref(width, height, r32, f32)
+        self.lib = ref(width, height, r32, f32, env)
         if self.lib is None:
-            raise FileNotFoundError(ref_lib_path(width, height, r32, f32))
+            raise FileNotFoundError(ref_lib_path(width, height, r32, f32, env))
         self.W, self.H = width, height
         self.HB = self.lib.buffer_height
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())

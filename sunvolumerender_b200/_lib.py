@@ -212,6 +212,13 @@ SIGNATURES_TF = [
 ]
 
 
+# ---- include/svr_env_io.h
+SIGNATURES_ENV = [
+    ("svr_hdr_read", C.c_int, [C.c_char_p, _P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("svr_env_load_hdr", C.c_int, [C.c_char_p, C.POINTER(EnvLight)]),
+]
+
+
 class SvrError(RuntimeError):
     pass
 
@@ -230,7 +237,7 @@ def load():
             "sunvolumerender_b200 has no CPU or PyTorch fallback."
         )
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
-    for name, res, args in SIGNATURES + SIGNATURES_IO + SIGNATURES_TF:
+    for name, res, args in SIGNATURES + SIGNATURES_IO + SIGNATURES_TF + SIGNATURES_ENV:
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args

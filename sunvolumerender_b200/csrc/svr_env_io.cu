@@ -1,0 +1,145 @@
+// svr_env_io.cu -- Radiance RGBE (.hdr) reader and the environment-light builder on top of it
+// (include/svr_env_io.h; core/lights/lights.cpp:31-75, which calls stbi_loadf).  Host code.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/svr_env_io.h"
+#include "svr_state.h"
+
+namespace svr {
+namespace {
+
+bool read_line(FILE* f, std::string* out)
+{
+    out->clear();
+    int c;
+    while ((c = fgetc(f)) != EOF) {
+        if (c == '\n') return true;
+        if (out->size() < 1024) out->push_back((char)c);
+    }
+    return !out->empty();
+}
+
+// byte * 2^(e - 136); exponent byte 0 means black
+inline void rgbe_to_float(const unsigned char* p, float* out)
+{
+    if (p[3] != 0) {
+        const float f = ldexpf(1.0f, (int)p[3] - (128 + 8));
+        out[0] = p[0] * f;
+        out[1] = p[1] * f;
+        out[2] = p[2] * f;
+    } else {
+        out[0] = out[1] = out[2] = 0.f;
+    }
+}
+
+int decode(FILE* f, uint32_t w, uint32_t h, float* out)
+{
+    const size_t npix = (size_t)w * h;
+    std::vector<unsigned char> line((size_t)w * 4);
+    auto flat_from = [&](size_t firstPixel, const unsigned char* head) -> int {
+        // the whole rest of the picture is uncompressed RGBE quads; `head` (if any) already holds one pixel
+        size_t i = firstPixel;
+        if (head) {
+            rgbe_to_float(head, out + 3 * i);
+            ++i;
+        }
+        unsigned char px[4];
+        for (; i < npix; ++i) {
+            if (fread(px, 1, 4, f) != 4) return fail_msg("svr_hdr_read: truncated pixel data");
+            rgbe_to_float(px, out + 3 * i);
+        }
+        return 0;
+    };
+    if (w < 8 || w >= 32768) return flat_from(0, nullptr);
+    for (uint32_t y = 0; y < h; ++y) {
+        unsigned char hd[4];
+        if (fread(hd, 1, 4, f) != 4) return fail_msg("svr_hdr_read: truncated scanline header");
+        if (hd[0] != 2 || hd[1] != 2 || (hd[2] & 0x80)) {
+            // not a run-length scanline: these four bytes are a pixel, and so is everything after them
+            if (y != 0) return fail_msg("svr_hdr_read: mixed flat and run-length scanlines");
+            return flat_from(0, hd);
+        }
+        if ((((uint32_t)hd[2] << 8) | hd[3]) != w) return fail_msg("svr_hdr_read: scanline length differs from the picture width");
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = 0;
+            while (x < w) {
+                int count = fgetc(f);
+                if (count == EOF) return fail_msg("svr_hdr_read: truncated run");
+                if (count > 128) {
+                    int value = fgetc(f);
+                    count -= 128;
+                    if (value == EOF || x + (uint32_t)count > w) return fail_msg("svr_hdr_read: corrupt run");
+                    for (int z = 0; z < count; ++z) line[(size_t)(x++) * 4 + k] = (unsigned char)value;
+                } else {
+                    if (count == 0 || x + (uint32_t)count > w) return fail_msg("svr_hdr_read: corrupt literal run");
+                    for (int z = 0; z < count; ++z) {
+                        int value = fgetc(f);
+                        if (value == EOF) return fail_msg("svr_hdr_read: truncated literal run");
+                        line[(size_t)(x++) * 4 + k] = (unsigned char)value;
+                    }
+                }
+            }
+        }
+        for (uint32_t x = 0; x < w; ++x) rgbe_to_float(&line[(size_t)x * 4], out + 3 * ((size_t)y * w + x));
+    }
+    return 0;
+}
+
+}  // namespace
+}  // namespace svr
+
+using namespace svr;
+
+extern "C" int svr_hdr_read(const char* path, float* rgb_out, uint32_t* w, uint32_t* h)
+{
+    if (!path || !w || !h) return fail_msg("svr_hdr_read: bad argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail_msg((std::string("svr_hdr_read: unable to load environment map: ") + path).c_str());
+    int rc = 0;
+    std::string line;
+    bool format = false;
+    if (!read_line(f, &line) || (line != "#?RADIANCE" && line != "#?RGBE")) rc = fail_msg("svr_hdr_read: not a Radiance HDR file");
+    while (!rc) {
+        if (!read_line(f, &line) && feof(f)) {
+            rc = fail_msg("svr_hdr_read: header ends before the resolution line");
+            break;
+        }
+        if (line.empty()) break;
+        if (line == "FORMAT=32-bit_rle_rgbe") format = true;
+    }
+    if (!rc && !format) rc = fail_msg("svr_hdr_read: unsupported format (only FORMAT=32-bit_rle_rgbe)");
+    if (!rc) {
+        unsigned hh = 0, ww = 0;
+        if (!read_line(f, &line) || sscanf(line.c_str(), "-Y %u +X %u", &hh, &ww) != 2 || !hh || !ww)
+            rc = fail_msg("svr_hdr_read: unsupported data layout (only -Y h +X w)");
+        else {
+            *w = ww;
+            *h = hh;
+            if (rgb_out) rc = decode(f, ww, hh, rgb_out);
+        }
+    }
+    fclose(f);
+    return rc;
+}
+
+extern "C" int svr_env_load_hdr(const char* path, svr_env_light* out)
+{
+    if (!out) return fail_msg("svr_env_load_hdr: bad argument");
+    uint32_t w = 0, h = 0;
+    int rc = svr_hdr_read(path, nullptr, &w, &h);
+    if (rc) return rc;
+    std::vector<float> rgb((size_t)w * h * 3), rgba((size_t)w * h * 4);
+    rc = svr_hdr_read(path, rgb.data(), &w, &h);
+    if (rc) return rc;
+    for (size_t i = 0; i < (size_t)w * h; ++i) {  // lights.cpp:47-53
+        rgba[4 * i + 0] = rgb[3 * i + 0];
+        rgba[4 * i + 1] = rgb[3 * i + 1];
+        rgba[4 * i + 2] = rgb[3 * i + 2];
+        rgba[4 * i + 3] = 0.f;
+    }
+    return svr_env_create(out, rgba.data(), w, h);
+}

@@ -193,6 +193,18 @@ class Renderer:
         self.set_option(L.OPT_ENV_ENABLED, 1 if enabled else 0)
         self.frame_no = 0
 
+    def load_env_map(self, path, intensity=1.0, offset=(0.0, 0.0), enabled=True):
+        """Lights::SetEnvironmentLight(filename) + SetEnvironmentLightIntensity / Offset (core/lights/lights.cpp:31-90)."""
+        env = L.EnvLight()
+        L.check(self.lib.svr_env_load_hdr(str(path).encode(), C.byref(env)), "svr_env_load_hdr")
+        if getattr(self, "_env_owned", None) is not None:
+            self.lib.svr_env_destroy(C.byref(self._env_owned))
+        self._env_owned = env
+        env.intensity = intensity
+        env.offset = L.Vec2(*offset)
+        self.set_env_light(env, enabled)
+        return env
+
     # ---- rendering
     def render_pathtracer(self, trace_depth=1):
         """One reference-style frame: one sample per pixel, frame counter advanced by the caller
@@ -238,6 +250,9 @@ class Renderer:
         if self.tf is not None:
             self.lib.svr_tf_destroy(C.byref(self.tf))
             self.tf = None
+        if getattr(self, "_env_owned", None) is not None:
+            self.lib.svr_env_destroy(C.byref(self._env_owned))
+            self._env_owned = None
 
 
 def setup_config(r, cfg, volume_bytes=None):

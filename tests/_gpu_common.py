@@ -32,8 +32,9 @@ def setup(r, cfg):
     return vox
 
 
-def reference(r, cfg, f32=False, r32=False):
-    ref = B.RefCuda(cfg.width, cfg.height, r32=r32, f32=f32)
+def reference(r, cfg, f32=False, r32=False, env=False):
+    """env=True: the environment-light twin (pathtracer.cu:233 re-enabled at build time, oracle/Makefile)."""
+    ref = B.RefCuda(cfg.width, cfg.height, r32=r32, f32=f32, env=env)
     ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
     return ref
 
