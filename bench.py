@@ -13,9 +13,10 @@ reduced over the ranks (N > 1: one NCCL sum-reduce of the per-GPU buffers onto r
   value     whole-job samples/s with the scene resident in HBM, CUDA events over exactly K steps,
             max over ranks.
   e2e       the same through the C ABI from HOST buffers: every step uploads the voxels from pinned
-            host memory into the volume's cudaArray (which drops and rebuilds the macrocell grid),
-            re-creates the transfer-function texture, re-publishes camera and lights, renders, and
-            reads the tone-mapped image and the float accumulator back into pinned host memory.
+            host memory into the volume's cudaArray (which invalidates and rebuilds the macrocell grid;
+            N > 1: one PCIe upload on rank 0 + an NCCL broadcast over NVLink), re-uploads the
+            transfer-function table, re-publishes camera and lights, renders, and reads the tone-mapped
+            image and the float accumulator back into pinned host memory.
   roofline  HBM: algorithmic bytes per launch (COUNTED taps x 8 voxels x bytes/voxel + TF lookups x 32 B
             + framebuffer bytes) / the path-tracing kernel's mean launch duration
             measured with CUDA events inside the timed region, against MEASURED_PEAKS.json.
@@ -247,8 +248,18 @@ def run_ours(a):
     env = S.constant_env_light()
     torch.cuda.synchronize()
 
+    # N > 1: the voxels cross PCIe ONCE (rank 0) and reach the other GPUs over NVLink (NCCL broadcast) instead of
+    # N uploads competing for host memory bandwidth; every rank then copies device-to-device into its cudaArray
+    stage = torch.empty_like(vb) if world > 1 else None
+
     def e2e_step():
-        r.upload_volume(host_vox)                  # H2D voxels -> cudaArray; macrocell cache dropped
+        if world > 1:
+            if rank == 0:
+                stage.copy_(host_vox, non_blocking=True)
+            dist.broadcast(stage, src=0)
+            r.upload_volume(stage)
+        else:
+            r.upload_volume(host_vox)              # H2D voxels -> cudaArray; macrocell cache dropped
         r.set_transfer_function(tf_table)          # H2D 16 KiB table -> new 1-D array + texture
         r.set_camera(cam)
         r.set_area_lights(lights)
@@ -331,7 +342,8 @@ def run_ours(a):
                         f"{W}x{H} path tracing, Woodcock tracking, traceDepth {depth}, one area light"
                         f"{' + constant environment light' if cfg.env else ''}, TF-{cfg.tf}, {spp} spp per step per GPU",
             "spp_per_step_per_gpu": spp, "samples_per_step": npix * spp * world,
-            "parallelism": f"spp-split x{world}, volume replicated, NCCL sum-reduce of float4 accumulators to rank 0" if world > 1 else "single GPU",
+            "parallelism": f"spp-split x{world}, volume replicated (e2e: one H2D + NCCL broadcast), NCCL sum-reduce of float4 accumulators to rank 0"
+                           if world > 1 else "single GPU",
             "estimator": {0: "global majorant + XORWOW (reference twin)", 1: "global majorant + Philox", 2: "macrocell local majorants + Philox"}[a.pt_mode],
             "macrocell": grid_cell(r),
             "l2": f"volume {vb.numel() >> 20} MiB > 126 MB L2 and incoherent taps; no flush between steps",
