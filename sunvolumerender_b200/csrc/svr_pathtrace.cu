@@ -118,7 +118,11 @@ struct TrackGlobal {
 // Cell-space description of a ray: g(t) = g0 + t * dg is the position in macrocell coordinates.
 struct CellRay {
     float3 g0, dg;
-    float3 invDg;  // 1 / dg; FLT_MAX on an axis the ray does not move along (its faces are never reached)
+    float3 invDg;  // 1 / dg; FLT_MAX on an axis the ray does not move along (clip(): no constraint inside the slab)
+    // exit_t(): the far face of the cube of r cells around cell c lies at f + 1/2 with f = c +- (r - 1/2) and
+    // is crossed at (f + 1/2 - g0) / dg = f * k + h, one FMA.  An axis the ray does not move along has
+    // k = 0, h = FLT_MAX: its faces are never reached.
+    float3 k, h;
     SVR_DEV void init(const DevScene& s, const Ray& ray)
     {
         const float3 toCell = s.grid.toCell;
@@ -127,6 +131,12 @@ struct CellRay {
         invDg.x = dg.x != 0.f ? 1.f / dg.x : FLT_MAX;
         invDg.y = dg.y != 0.f ? 1.f / dg.y : FLT_MAX;
         invDg.z = dg.z != 0.f ? 1.f / dg.z : FLT_MAX;
+        k.x = dg.x != 0.f ? invDg.x : 0.f;
+        k.y = dg.y != 0.f ? invDg.y : 0.f;
+        k.z = dg.z != 0.f ? invDg.z : 0.f;
+        h.x = dg.x != 0.f ? (0.5f - g0.x) * invDg.x : FLT_MAX;
+        h.y = dg.y != 0.f ? (0.5f - g0.y) * invDg.y : FLT_MAX;
+        h.z = dg.z != 0.f ? (0.5f - g0.z) * invDg.z : FLT_MAX;
     }
     // ray-parameter step that moves 1e-3 cell along the fastest axis
     SVR_DEV float eps() const { return 1e-3f * fminf(fminf(fabsf(invDg.x), fabsf(invDg.y)), fabsf(invDg.z)); }
@@ -151,11 +161,10 @@ struct CellRay {
     // here, so walks that start at different parameters (entry cache on / off) visit identical positions.
     SVR_DEV float exit_t(float3 cf, float r) const
     {
-        const float n = 1.f - r;
-        const float tx = (cf.x + (dg.x >= 0.f ? r : n) - g0.x) * invDg.x;
-        const float ty = (cf.y + (dg.y >= 0.f ? r : n) - g0.y) * invDg.y;
-        const float tz = (cf.z + (dg.z >= 0.f ? r : n) - g0.z) * invDg.z;
-        return fminf(fminf(tx, ty), tz);
+        // the face's coordinate minus 1/2, exact (an integer plus or minus a half-integer)
+        const float rr = r - 0.5f;
+        const float fx = cf.x + copysignf(rr, k.x), fy = cf.y + copysignf(rr, k.y), fz = cf.z + copysignf(rr, k.z);
+        return fminf(fminf(fmaf(fx, k.x, h.x), fmaf(fy, k.y, h.y)), fmaf(fz, k.z, h.z));
     }
 };
 
@@ -674,6 +683,15 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             const uint32_t offset = idy * s.cam.imageW + idx;
             const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
             pixel_begin<MODE>(ps);
+            if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
+                // every sample of this pixel is the constant sky (see trace_sample): the same additions, nothing else
+                const float3 sky = (a.traceDepth != 0 && s.envEnabled) ? f3(s.env.defaultRadiance) * s.env.intensity : f3(0.f);
+                for (uint32_t n = lane; n < a.nSamples; n += 32u) {
+                    lc.add(SVR_CNT_PATHS, 1);
+                    if (MODE == 0) ps.sum += sky;
+                    else ps.L += sky;
+                }
+            } else
             for (uint32_t n = lane; n < a.nSamples; n += 32u) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
             float3 sum = pixel_sum<MODE>(ps);
             __syncwarp();

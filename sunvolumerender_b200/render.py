@@ -86,6 +86,7 @@ class Renderer:
             "svr_volume_create",
         )
         self.volume = vol
+        self._vol_nbytes = nx * ny * nz * L.VOXEL_BYTES[fmt]
         self.lib.setup_volume(C.byref(vol))
         return vol
 
@@ -132,6 +133,12 @@ class Renderer:
         L.check(self.lib.svr_volume_upload(C.byref(self.volume), ptr, on_device), "svr_volume_upload")
         self.lib.setup_volume(C.byref(self.volume))
         self.frame_no = 0
+
+    def volume_nbytes(self):
+        """Size in bytes of the bound volume's voxels (volumes made by load_volume)."""
+        if getattr(self, "_vol_nbytes", None) is None:
+            raise RuntimeError("volume_nbytes: no volume loaded with load_volume")
+        return self._vol_nbytes
 
     def free_volume(self):
         if self.volume is not None:
@@ -253,6 +260,77 @@ class Renderer:
         if getattr(self, "_env_owned", None) is not None:
             self.lib.svr_env_destroy(C.byref(self._env_owned))
             self._env_owned = None
+
+
+class VolumeStream:
+    """A sequence of host-resident volumes (a time series: same dimensions and voxel format) rendered one after the
+    other, with the NEXT volume's host-to-device transfer overlapped with the CURRENT volume's rendering.
+
+        vs = VolumeStream(renderer)
+        vs.prefetch(host_volume[0])
+        for i in range(n):
+            vs.bind()                                  # volume i becomes the renderer's volume (device-to-device + setup_volume)
+            ...setup_* calls of the frame...
+            if i + 1 < n: vs.prefetch(host_volume[i + 1])  # PCIe transfer runs beside the launches below
+            renderer.accumulate(...) / render_pathtracer_spp(...)
+
+    The voxels cross PCIe on a copy stream into one of two linear staging buffers in HBM; bind() copies the
+    staged voxels into the bound volume's cudaArray on the render stream (svr_volume_upload, data_on_device = 1:
+    256 MiB in about 0.15 ms), so the caller's cudaArray / texture object never change.  With world_size > 1 the
+    voxels cross PCIe once, on rank `src`, and reach the other GPUs with an NCCL broadcast over NVLink.
+    prefetch() must come AFTER the frame's setup_* calls: like the reference's (pathtracer.cu:34-68) they
+    cudaDeviceSynchronize, which would wait for the transfer.
+    """
+
+    def __init__(self, renderer, nbytes=None, group=None, src=0):
+        import torch.distributed as dist
+
+        self.r = renderer
+        self.group, self.src = group, src
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else None
+        self.rank = dist.get_rank(group) if self.dist else 0
+        dev = renderer.device
+        if nbytes is None:
+            nbytes = renderer.volume_nbytes()
+        self.stage = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        for t in self.stage:
+            t.record_stream(self.copy_stream)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # staging buffer filled (copy stream)
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]   # staging buffer copied into the array (render stream)
+        self.head = 0      # next slot to fill
+        self.tail = 0      # next slot to bind
+        self.inflight = 0
+
+    def prefetch(self, host_volume):
+        """Start the transfer of the next volume (a pinned host uint8 tensor on rank `src`; ignored elsewhere)."""
+        if self.inflight >= 2:
+            raise RuntimeError("VolumeStream.prefetch: both staging buffers are in flight; bind() first")
+        slot = self.head
+        stage = self.stage[slot]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])  # the slot's previous contents have left for the array
+            if self.rank == self.src:
+                stage.copy_(host_volume.view(torch.uint8).reshape(-1), non_blocking=True)
+            if self.dist:
+                self.dist.broadcast(stage, src=self.src, group=self.group)
+            self.ready[slot].record(self.copy_stream)
+        self.head ^= 1
+        self.inflight += 1
+
+    def bind(self):
+        """Make the oldest prefetched volume the renderer's volume."""
+        if self.inflight == 0:
+            raise RuntimeError("VolumeStream.bind: nothing prefetched")
+        slot = self.tail
+        main = torch.cuda.current_stream(self.r.device)
+        main.wait_event(self.ready[slot])
+        L.check(self.r.lib.svr_volume_upload(C.byref(self.r.volume), _ptr(self.stage[slot]), 1), "svr_volume_upload")
+        self.consumed[slot].record(main)
+        self.r.lib.setup_volume(C.byref(self.r.volume))
+        self.r.frame_no = 0
+        self.tail ^= 1
+        self.inflight -= 1
 
 
 def setup_config(r, cfg, volume_bytes=None):

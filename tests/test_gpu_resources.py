@@ -139,6 +139,49 @@ def test_upload_into_bound_resources_equals_fresh_load(renderer):
     assert torch.equal(pt_a, pt_d) and torch.equal(rc_a, rc_d)
 
 
+def test_volume_stream_equals_direct_uploads(renderer):
+    """render.VolumeStream (the transfer of frame i+1 overlapped with the rendering of frame i, what bench.py's
+    e2e loop does) renders a sequence of volumes to the same images, bit for bit, as uploading each one directly."""
+    from sunvolumerender_b200.render import VolumeStream
+
+    cfg = small_config(n=48, w=96, h=64, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=2)
+    vox = setup(renderer, cfg)
+    frames = [vox.copy(), (vox[::-1, :, ::-1] // 2).copy(), (vox[:, ::-1, :] // 3 * 2).copy(), vox.copy()]
+
+    def render():
+        renderer.frame_no = 0
+        renderer.render_pathtracer_spp(64, 2)  # the sample-parallel kernel
+        return renderer.hdr_image().clone()
+
+    direct = []
+    for f in frames:
+        renderer.upload_volume(f)
+        direct.append(render())
+    torch.cuda.synchronize()
+    assert not torch.equal(direct[0], direct[1]) and not torch.equal(direct[1], direct[2])
+
+    pinned = [torch.from_numpy(f).view(torch.uint8).reshape(-1).pin_memory() for f in frames]
+    vs = VolumeStream(renderer)
+    with pytest.raises(RuntimeError):
+        vs.bind()
+    vs.prefetch(pinned[0])
+    streamed = []
+    for i in range(len(frames)):
+        vs.bind()
+        renderer.set_transfer_function(S.tf_table(cfg.tf))  # a frame's setup_* calls come before the prefetch
+        if i + 1 < len(frames):
+            vs.prefetch(pinned[i + 1])
+        streamed.append(render())
+    torch.cuda.synchronize()
+    for a, b in zip(direct, streamed):
+        assert torch.equal(a, b)
+    vs.prefetch(pinned[0])
+    vs.prefetch(pinned[1])
+    with pytest.raises(RuntimeError):
+        vs.prefetch(pinned[2])
+    torch.cuda.synchronize()
+
+
 def test_automatic_macrocell_size_follows_the_mean_free_path(renderer):
     """SVR_OPT_MACROCELL_SIZE = 0: an opaque medium (mean free path ~2 voxels) gets 4-voxel cells, a thin
     one large cells; the choice follows transfer-function edits and never changes a ray-cast image."""
