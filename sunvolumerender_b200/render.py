@@ -282,13 +282,17 @@ class VolumeStream:
     cudaDeviceSynchronize, which would wait for the transfer.
     """
 
-    def __init__(self, renderer, nbytes=None, group=None, src=0):
+    def __init__(self, renderer, nbytes=None, group=None, src=0, fanout="nvlink"):
+        """fanout (world_size > 1): "nvlink" = rank `src` uploads, NCCL broadcast to the others; "pcie" = every rank
+        uploads its own host copy over its own PCIe link (no collective, no SMs: copy engines only)."""
         import torch.distributed as dist
 
+        if fanout not in ("nvlink", "pcie"):
+            raise ValueError("VolumeStream: fanout must be 'nvlink' or 'pcie'")
         self.r = renderer
         self.group, self.src = group, src
-        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else None
-        self.rank = dist.get_rank(group) if self.dist else 0
+        self.dist = dist if (fanout == "nvlink" and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else None
+        self.rank = dist.get_rank(group) if self.dist else src
         dev = renderer.device
         if nbytes is None:
             nbytes = renderer.volume_nbytes()
