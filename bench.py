@@ -253,19 +253,19 @@ def run_ours(a):
 
         # Frames stream through the renderer the way a time series of volumes would: while frame i renders, the
         # voxels of frame i+1 cross PCIe on a copy stream into a staging buffer (render.VolumeStream); N > 1: they
-        # cross PCIe ONCE (rank 0) and reach the other GPUs over NVLink (NCCL broadcast on its own communicator)
-        # instead of N uploads competing for host memory bandwidth.  Every step still uploads its own inputs and
-        # reads its own results back inside the timed region: K prefetches, K binds, K read-backs for K steps.
+        # cross PCIe ONCE (rank 0) and reach the other GPUs over NVLink -- pushed by copy engines into peer-mapped
+        # staging buffers ("p2p"), or with an NCCL broadcast ("nvlink") -- instead of N uploads competing for host
+        # memory bandwidth ("pcie").  Every step still uploads its own inputs and reads its own results back
+        # inside the timed region: K prefetches, K binds, K read-backs for K steps.
         from sunvolumerender_b200.render import VolumeStream
 
         bgroup = None
         if world > 1 and a.e2e_fanout == "nvlink":
-            # the broadcast runs beside the render kernel, whose 10^5 queued blocks would otherwise keep a same-priority
-            # NCCL kernel waiting until its tail: give the broadcast's communicator a high-priority stream
             opts = dist.ProcessGroupNCCL.Options()
             opts.is_high_priority_stream = True
-            bgroup = dist.new_group(pg_options=opts)
+            bgroup = dist.new_group(pg_options=opts)  # the broadcast gets its own communicator and stream
         vs = VolumeStream(r, vb.numel(), group=bgroup, fanout=a.e2e_fanout)
+        fanout = vs.fanout
 
         def e2e_step(prefetch_next, serial=False):
             if serial:
@@ -275,9 +275,9 @@ def run_ours(a):
             r.set_camera(cam)
             r.set_area_lights(lights)
             r.set_env_light(env, enabled=cfg.env)
-            if prefetch_next and not serial:
-                vs.prefetch(host_vox)                  # H2D (+ broadcast) of the NEXT frame, beside this frame's launches
             r.accumulate(sum_buf, depth, first, spp, clear=True)
+            if prefetch_next and not serial:
+                vs.prefetch(host_vox)                  # H2D (+ fan-out) of the NEXT frame, beside this frame's render kernel
             if world > 1:
                 dist.reduce(sum_buf, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
@@ -308,12 +308,13 @@ def run_ours(a):
             clocks.window(*win)
         e2e_value = npix * spp * world * a.steps / (e2e_ms * 1e-3)
         small = tf_table.nbytes + 112 + 16 + 76 + 44 * len(lights) + 32  # table + scene PODs, every rank
-        h2d = int(vb.numel() * (world if a.e2e_fanout == "pcie" else 1) + small * world)
+        h2d = int(vb.numel() * (world if fanout == "pcie" else 1) + small * world)
         d2h = int(host_img.numel() + host_hdr.numel() * 4)
         img_nonzero = float((host_img.view(H, W, 4)[..., :3] > 0).float().mean()) if rank == 0 else 0.0
+        vs.close()
         return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
                 "pipeline": "frame i+1's H2D overlaps frame i's render (VolumeStream); every step uploads and reads back",
-                "ms_per_step_without_overlap": e2e_serial_ms}, img_nonzero
+                "ms_per_step_without_overlap": e2e_serial_ms, "fanout": fanout}, img_nonzero
 
     if a.no_e2e or (vb.numel() > (2 << 30) and not a.force_e2e):
         # a 16 GiB volume per rank would pin 16 GiB of host memory per rank: opt in with --force-e2e
@@ -371,7 +372,7 @@ def run_ours(a):
                         f"{W}x{H} path tracing, Woodcock tracking, traceDepth {depth}, one area light"
                         f"{' + constant environment light' if cfg.env else ''}, TF-{cfg.tf}, {spp} spp per step per GPU",
             "spp_per_step_per_gpu": spp, "samples_per_step": npix * spp * world,
-            "parallelism": f"spp-split x{world}, volume replicated (e2e: {'one H2D + NCCL broadcast' if a.e2e_fanout == 'nvlink' else 'one H2D per rank'}), NCCL sum-reduce of float4 accumulators to rank 0"
+            "parallelism": f"spp-split x{world}, volume replicated (e2e fan-out: {(e2e or {}).get('fanout')}), NCCL sum-reduce of float4 accumulators to rank 0"
                            if world > 1 else "single GPU",
             "estimator": {0: "global majorant + XORWOW (reference twin)", 1: "global majorant + Philox", 2: "macrocell local majorants + Philox"}[a.pt_mode],
             "macrocell": grid_cell(r),
@@ -596,8 +597,9 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel per step per GPU (0 = the workload's)")
     ap.add_argument("--pt-mode", type=int, default=2, choices=[0, 1, 2])
     ap.add_argument("--cell", type=int, default=0, help="macrocell edge in voxels (0 = the library default)")
-    ap.add_argument("--e2e-fanout", default="nvlink", choices=["nvlink", "pcie"],
-                    help="N > 1, e2e: how the voxels reach every GPU (one PCIe upload + NCCL broadcast, or one PCIe upload per rank)")
+    ap.add_argument("--e2e-fanout", default="p2p", choices=["p2p", "nvlink", "pcie"],
+                    help="N > 1, e2e: how the voxels reach every GPU: one PCIe upload + copy-engine pushes over NVLink (p2p), "
+                         "one PCIe upload + NCCL broadcast (nvlink), or one PCIe upload per rank (pcie)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-e2e", action="store_true", help="run the e2e leg for volumes above 2 GiB too (pins that much host memory per rank)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -126,6 +126,22 @@ int svr_render_pathtracer_spp(svr_u8vec4* img, const svr_render_params* renderPa
 int svr_pathtracer_accumulate(svr_vec4* sum, uint32_t traceDepth, uint32_t firstSample, uint32_t nSamples, int clear);
 int svr_pathtracer_resolve(svr_u8vec4* img, svr_vec3* hdrOut, const svr_vec4* sum);
 
+/* Staging buffers for streaming volumes to replicated scenes (the volume is replicated
+ * per GPU; the reference is single-device, main.cpp:7-33, and has no counterpart).  One process per GPU:
+ * every process allocates linear staging buffers (svr_stage_alloc = cudaMalloc), exports them to the
+ * process that uploads (svr_stage_export = cudaIpcGetMemHandle, 64 bytes to send over any channel), which
+ * imports them from ITS device (svr_stage_import = cudaIpcOpenMemHandle with lazy peer access, so the
+ * mapping is a peer mapping over NVLink) and fills them with svr_stage_copy (cudaMemcpyAsync, kind
+ * default: pinned host, local or imported peer memory -- copy engines only, no SMs, so the transfer runs
+ * beside a render kernel that occupies every SM).  svr_volume_upload(vol, stage, 1) then moves the staged
+ * voxels into the volume's cudaArray.  `stream` is a cudaStream_t. */
+int svr_stage_alloc(void** dev_ptr, uint64_t bytes);
+int svr_stage_free(void* dev_ptr);
+int svr_stage_export(const void* dev_ptr, unsigned char handle_out[64]);
+int svr_stage_import(const unsigned char handle[64], void** peer_ptr);
+int svr_stage_release(void* peer_ptr);
+int svr_stage_copy(void* dst, const void* src, uint64_t bytes, void* stream);
+
 /* Ray caster variants: float RGBA before quantisation (parity is checked on these), and a row
  * range [y0, y1) for the image-tile split across GPUs.  out/img are full-frame buffers. */
 int svr_render_raycasting_f32(svr_vec4* out, const svr_volume* volume, const svr_transfer_function* tf,

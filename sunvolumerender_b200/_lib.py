@@ -135,6 +135,12 @@ SIGNATURES = [
     ("svr_volume_create", C.c_int, [C.POINTER(Volume), _P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float]),
     ("svr_volume_destroy", C.c_int, [C.POINTER(Volume)]),
     ("svr_volume_upload", C.c_int, [C.POINTER(Volume), _P, C.c_int]),
+    ("svr_stage_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    ("svr_stage_free", C.c_int, [_P]),
+    ("svr_stage_export", C.c_int, [_P, C.POINTER(C.c_ubyte * 64)]),
+    ("svr_stage_import", C.c_int, [C.POINTER(C.c_ubyte * 64), C.POINTER(C.c_void_p)]),
+    ("svr_stage_release", C.c_int, [_P]),
+    ("svr_stage_copy", C.c_int, [_P, _P, C.c_uint64, _P]),
     ("svr_volume_invalidate_cache", C.c_int, []),
     ("svr_tf_create", C.c_int, [C.POINTER(TransferFunction), _P, C.c_uint32]),
     ("svr_tf_destroy", C.c_int, [C.POINTER(TransferFunction)]),

@@ -361,6 +361,55 @@ extern "C" int svr_volume_upload(const svr_volume* vol, const void* data, int da
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Staging buffers for streamed, replicated volumes (include/svr_render.h)
+// ------------------------------------------------------------------------------------------------
+extern "C" int svr_stage_alloc(void** dev_ptr, uint64_t bytes)
+{
+    if (!dev_ptr || !bytes) return fail_msg("svr_stage_alloc: bad argument");
+    SVR_TRY(cudaMalloc(dev_ptr, (size_t)bytes));
+    return 0;
+}
+
+extern "C" int svr_stage_free(void* dev_ptr)
+{
+    if (dev_ptr) SVR_TRY(cudaFree(dev_ptr));
+    return 0;
+}
+
+extern "C" int svr_stage_export(const void* dev_ptr, unsigned char handle_out[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!dev_ptr || !handle_out) return fail_msg("svr_stage_export: bad argument");
+    cudaIpcMemHandle_t h;
+    SVR_TRY(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int svr_stage_import(const unsigned char handle[64], void** peer_ptr)
+{
+    if (!handle || !peer_ptr) return fail_msg("svr_stage_import: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    // opened from the CURRENT device: the mapping is a peer mapping (NVLink) when the buffer lives on another GPU
+    SVR_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int svr_stage_release(void* peer_ptr)
+{
+    if (peer_ptr) SVR_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+
+extern "C" int svr_stage_copy(void* dst, const void* src, uint64_t bytes, void* stream)
+{
+    if (!dst || !src) return fail_msg("svr_stage_copy: bad argument");
+    SVR_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+
 // The table half of TransferFunction::TransferFunction (gui/transferfunction.cpp:17-44) for a texture
 // that already exists: the reference destroys and recreates array + texture object on every edit
 // (transferfunction.cpp:128-151); the contents are all that changes.

@@ -276,49 +276,158 @@ class VolumeStream:
 
     The voxels cross PCIe on a copy stream into one of two linear staging buffers in HBM; bind() copies the
     staged voxels into the bound volume's cudaArray on the render stream (svr_volume_upload, data_on_device = 1:
-    256 MiB in about 0.15 ms), so the caller's cudaArray / texture object never change.  With world_size > 1 the
-    voxels cross PCIe once, on rank `src`, and reach the other GPUs with an NCCL broadcast over NVLink.
+    256 MiB in about 0.3 ms), so the caller's cudaArray / texture object never change.
     prefetch() must come AFTER the frame's setup_* calls: like the reference's (pathtracer.cu:34-68) they
     cudaDeviceSynchronize, which would wait for the transfer.
+
+    One process per GPU, world_size > 1 (every rank constructs the stream and calls prefetch / bind in the same
+    order; the volume is replicated) -- `fanout` says how the voxels reach every GPU:
+      "p2p"    rank `src` uploads once over PCIe and pushes the staged voxels into the other ranks' staging buffers
+               with copy engines over NVLink (CUDA IPC peer mappings, svr_stage_*; no SMs, so the pushes run beside a
+               render kernel that fills every SM).  Cross-process ordering: interprocess CUDA events plus one
+               host-side (gloo) barrier per prefetch, which guarantees an event's record has been CALLED before a
+               peer waits on it.  Falls back to "nvlink" when CUDA IPC is unavailable.
+      "nvlink" rank `src` uploads, then an NCCL broadcast (an SM kernel: beside a full-machine render kernel it only
+               gets scheduled in that kernel's tail).
+      "pcie"   every rank uploads its own host copy over its own PCIe link (no collective).
     """
 
-    def __init__(self, renderer, nbytes=None, group=None, src=0, fanout="nvlink"):
-        """fanout (world_size > 1): "nvlink" = rank `src` uploads, NCCL broadcast to the others; "pcie" = every rank
-        uploads its own host copy over its own PCIe link (no collective, no SMs: copy engines only)."""
+    def __init__(self, renderer, nbytes=None, group=None, src=0, fanout="p2p", host_group=None):
         import torch.distributed as dist
 
-        if fanout not in ("nvlink", "pcie"):
-            raise ValueError("VolumeStream: fanout must be 'nvlink' or 'pcie'")
+        if fanout not in ("p2p", "nvlink", "pcie"):
+            raise ValueError("VolumeStream: fanout must be 'p2p', 'nvlink' or 'pcie'")
         self.r = renderer
+        self.lib = renderer.lib
         self.group, self.src = group, src
-        self.dist = dist if (fanout == "nvlink" and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else None
-        self.rank = dist.get_rank(group) if self.dist else src
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.fanout = fanout if multi else "local"
+        self.dist = dist if multi else None
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else src
         dev = renderer.device
-        if nbytes is None:
-            nbytes = renderer.volume_nbytes()
-        self.stage = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.nbytes = int(nbytes if nbytes is not None else renderer.volume_nbytes())
         self.copy_stream = torch.cuda.Stream(device=dev)
-        for t in self.stage:
-            t.record_stream(self.copy_stream)
-        self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # staging buffer filled (copy stream)
-        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]   # staging buffer copied into the array (render stream)
         self.head = 0      # next slot to fill
         self.tail = 0      # next slot to bind
         self.inflight = 0
+        self.stage = None
+        self.stage_ptr = [None, None]
+        self.peer_ptr = {}
+        if self.fanout == "p2p":
+            self.host_group = host_group if host_group is not None else dist.new_group(backend="gloo")
+            if not self._setup_p2p():
+                self.fanout = "nvlink"
+        if self.fanout != "p2p":
+            self.stage = [torch.empty(self.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+            for t in self.stage:
+                t.record_stream(self.copy_stream)
+            self.stage_ptr = [C.c_void_p(t.data_ptr()) for t in self.stage]
+            self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # staging buffer filled (copy stream)
+            self.consumed = [torch.cuda.Event(), torch.cuda.Event()]   # staging buffer copied into the array (render stream)
+
+    # ---- "p2p": exportable staging buffers, peer mappings on the uploading rank, interprocess events
+    def _setup_p2p(self):
+        dist, lib, dev = self.dist, self.lib, self.r.device
+        ok, handles, consumed_h = True, [], []
+        try:
+            for i in range(2):
+                p = C.c_void_p(0)
+                L.check(lib.svr_stage_alloc(C.byref(p), self.nbytes), "svr_stage_alloc")
+                self.stage_ptr[i] = p
+                h = (C.c_ubyte * 64)()
+                L.check(lib.svr_stage_export(p, C.byref(h)), "svr_stage_export")
+                handles.append(bytes(h))
+            self.consumed = [torch.cuda.Event(interprocess=True), torch.cuda.Event(interprocess=True)]
+            consumed_h = [e.ipc_handle() for e in self.consumed]
+        except Exception:
+            ok = False
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (ok, handles, consumed_h), group=self.host_group)
+        ok = all(e[0] for e in everyone)
+        landed_h = [None, None]
+        if ok and self.rank == self.src:
+            try:
+                for r in range(self.world):
+                    if r == self.src:
+                        continue
+                    ptrs = []
+                    for hb in everyone[r][1]:
+                        q = C.c_void_p(0)
+                        h = (C.c_ubyte * 64).from_buffer_copy(hb)
+                        L.check(lib.svr_stage_import(C.byref(h), C.byref(q)), "svr_stage_import")
+                        ptrs.append(q)
+                    self.peer_ptr[r] = ptrs
+                self.peer_consumed = {r: [torch.cuda.Event.from_ipc_handle(dev, h) for h in everyone[r][2]]
+                                      for r in range(self.world) if r != self.src}
+                self.ready = [torch.cuda.Event(interprocess=True), torch.cuda.Event(interprocess=True)]
+                landed_h = [e.ipc_handle() for e in self.ready]
+            except Exception:
+                ok = False
+        box = [(ok, landed_h)]
+        dist.broadcast_object_list(box, src=self.src, group=self.host_group)
+        ok, landed_h = box[0]
+        if ok and self.rank != self.src:
+            try:
+                self.ready = [torch.cuda.Event.from_ipc_handle(dev, h) for h in landed_h]
+            except Exception:
+                ok = False
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=self.host_group)
+        if not all(flags):
+            self._release_p2p()
+            return False
+        return True
+
+    def _release_p2p(self):
+        for ptrs in self.peer_ptr.values():
+            for q in ptrs:
+                self.lib.svr_stage_release(q)
+        self.peer_ptr = {}
+        for i, p in enumerate(self.stage_ptr):
+            if p is not None and self.stage is None:
+                self.lib.svr_stage_free(p)
+            self.stage_ptr[i] = None
+
+    def close(self):
+        """Collective for fanout "p2p": peer mappings are released before their owners free the buffers."""
+        torch.cuda.synchronize(self.r.device)
+        if self.fanout == "p2p":
+            for ptrs in self.peer_ptr.values():
+                for q in ptrs:
+                    self.lib.svr_stage_release(q)
+            self.peer_ptr = {}
+            self.dist.barrier(group=self.host_group)
+            self._release_p2p()
+        self.stage = None
 
     def prefetch(self, host_volume):
-        """Start the transfer of the next volume (a pinned host uint8 tensor on rank `src`; ignored elsewhere)."""
+        """Start the transfer of the next volume (a pinned host uint8 tensor; read on rank `src` only, unless
+        fanout is "pcie").  Collective when world_size > 1."""
         if self.inflight >= 2:
             raise RuntimeError("VolumeStream.prefetch: both staging buffers are in flight; bind() first")
         slot = self.head
-        stage = self.stage[slot]
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.consumed[slot])  # the slot's previous contents have left for the array
-            if self.rank == self.src:
-                stage.copy_(host_volume.view(torch.uint8).reshape(-1), non_blocking=True)
-            if self.dist:
-                self.dist.broadcast(stage, src=self.src, group=self.group)
-            self.ready[slot].record(self.copy_stream)
+        cs = self.copy_stream
+        uploads = self.fanout in ("local", "pcie") or self.rank == self.src
+        with torch.cuda.stream(cs):
+            cs.wait_event(self.consumed[slot])  # the slot's previous contents have left for the array
+            if self.fanout == "p2p":
+                if uploads:
+                    for evs in self.peer_consumed.values():
+                        cs.wait_event(evs[slot])
+                    src_ptr = C.c_void_p(host_volume.data_ptr())
+                    L.check(self.lib.svr_stage_copy(self.stage_ptr[slot], src_ptr, self.nbytes, C.c_void_p(cs.cuda_stream)), "svr_stage_copy")
+                    for ptrs in self.peer_ptr.values():   # NVLink, copy engines
+                        L.check(self.lib.svr_stage_copy(ptrs[slot], self.stage_ptr[slot], self.nbytes, C.c_void_p(cs.cuda_stream)), "svr_stage_copy")
+                    self.ready[slot].record(cs)
+            else:
+                if uploads:
+                    self.stage[slot].copy_(host_volume.view(torch.uint8).reshape(-1), non_blocking=True)
+                if self.fanout == "nvlink":
+                    self.dist.broadcast(self.stage[slot], src=self.src, group=self.group)
+                self.ready[slot].record(cs)
+        if self.fanout == "p2p":
+            self.dist.barrier(group=self.host_group)  # rank src has CALLED record: the others may wait on the event
         self.head ^= 1
         self.inflight += 1
 
@@ -329,7 +438,7 @@ class VolumeStream:
         slot = self.tail
         main = torch.cuda.current_stream(self.r.device)
         main.wait_event(self.ready[slot])
-        L.check(self.r.lib.svr_volume_upload(C.byref(self.r.volume), _ptr(self.stage[slot]), 1), "svr_volume_upload")
+        L.check(self.lib.svr_volume_upload(C.byref(self.r.volume), self.stage_ptr[slot], 1), "svr_volume_upload")
         self.consumed[slot].record(main)
         self.r.lib.setup_volume(C.byref(self.r.volume))
         self.r.frame_no = 0
