@@ -71,60 +71,115 @@ __global__ void range_kernel(cudaTextureObject_t pointTex, int3 vol, int3 grid, 
     }
 }
 
+// The brick kernel below reads the caller's cudaArray through a point-sampled view (the boundary passes only
+// a texture handle).  (Measured alternative: the same kernel fed from the linear device buffer an upload
+// copies from -- coalesced 2-byte loads, bounds checks and 64-bit addressing per texel -- takes 0.83 ms at
+// 512^3 against 0.37 ms for the texture path, whose address arithmetic and border handling are free.)
+struct TexFetch {
+    cudaTextureObject_t tex;
+    // unnormalised point fetch at the texel centre; out-of-range reads the border value 0
+    __device__ float operator()(int x, int y, int z) const { return tex3D<float>(tex, (float)x + 0.5f, (float)y + 0.5f, (float)z + 0.5f); }
+};
+
 // The same range grid for cell edges <= 16, a brick of cells per block: the brick's texels (plus the
 // one-texel apron) are fetched ONCE into shared memory -- 1.3-1.7 fetches per voxel instead of
-// (1 + 2/C)^3 -- and reduced separably (x, then y, then z).
-__global__ void __launch_bounds__(256) range_brick_kernel(cudaTextureObject_t pointTex, int3 grid, int cell, int3 brick, float2* out)
+// (1 + 2/C)^3 -- and reduced separably (x, then y, then z).  The cell edge is a template parameter: every
+// index decode is a division by a constant and the reductions unroll (the kernel is instruction-bound).
+// brick = 32 x 8 x 8 voxels (32 x 16 x 16 for 16-voxel cells)
+template <class Fetch, int CELL>
+__global__ void __launch_bounds__(256) range_brick_kernel(Fetch fetch, int3 grid, float2* out)
 {
+    constexpr int BX = 32 / CELL, BY = CELL <= 8 ? 8 / CELL : 1, BZ = BY;
+    constexpr int TX = BX * CELL + 2, TY = BY * CELL + 2, TZ = BZ * CELL + 2;
+    constexpr int TOTAL = TX * TY * TZ;
     extern __shared__ float smem[];
-    const int TX = brick.x * cell + 2, TY = brick.y * cell + 2, TZ = brick.z * cell + 2;
-    float* tex = smem;                                  // TX * TY * TZ texels
-    float2* rx = (float2*)(smem + TX * TY * TZ);        // brick.x * TY * TZ      (reduced along x)
-    float2* ry = rx + brick.x * TY * TZ;                // brick.x * brick.y * TZ (reduced along x, y)
-    const int cx0 = blockIdx.x * brick.x, cy0 = blockIdx.y * brick.y, cz0 = blockIdx.z * brick.z;
-    const int x0 = cx0 * cell - 1, y0 = cy0 * cell - 1, z0 = cz0 * cell - 1;
-    const int total = TX * TY * TZ;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        int x = i % TX, y = (i / TX) % TY, z = i / (TX * TY);
-        // unnormalised point fetch at the texel centre; out-of-range reads the border value 0
-        tex[i] = tex3D<float>(pointTex, (float)(x0 + x) + 0.5f, (float)(y0 + y) + 0.5f, (float)(z0 + z) + 0.5f);
+    float* tex = smem;                      // TX * TY * TZ texels
+    float2* rx = (float2*)(smem + TOTAL);   // BX * TY * TZ  (reduced along x)
+    float2* ry = rx + BX * TY * TZ;         // BX * BY * TZ  (reduced along x, y)
+    const int cx0 = blockIdx.x * BX, cy0 = blockIdx.y * BY, cz0 = blockIdx.z * BZ;
+    const int x0 = cx0 * CELL - 1, y0 = cy0 * CELL - 1, z0 = cz0 * CELL - 1;
+    // consecutive threads read consecutive texels of a row; four independent fetches are in flight before
+    // the first result is stored
+    for (int base = threadIdx.x; base < TOTAL; base += 4 * 256) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * 256;
+            if (i < TOTAL) {
+                const int x = i % TX, y = (i / TX) % TY, z = i / (TX * TY);
+                v[u] = fetch(x0 + x, y0 + y, z0 + z);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * 256;
+            if (i < TOTAL) tex[i] = v[u];
+        }
     }
     __syncthreads();
-    const int nx = brick.x * TY * TZ;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-        int c = i % brick.x, y = (i / brick.x) % TY, z = i / (brick.x * TY);
-        const float* row = tex + (z * TY + y) * TX + c * cell;
+    for (int i = threadIdx.x; i < BX * TY * TZ; i += 256) {
+        const int c = i % BX, y = (i / BX) % TY, z = i / (BX * TY);
+        const float* row = tex + (z * TY + y) * TX + c * CELL;
         float mn = row[0], mx = row[0];
-        for (int k = 1; k < cell + 2; ++k) {
+#pragma unroll
+        for (int k = 1; k < CELL + 2; ++k) {
             mn = fminf(mn, row[k]);
             mx = fmaxf(mx, row[k]);
         }
-        rx[(z * TY + y) * brick.x + c] = make_float2(mn, mx);
+        rx[(z * TY + y) * BX + c] = make_float2(mn, mx);
     }
     __syncthreads();
-    const int ny = brick.x * brick.y * TZ;
-    for (int i = threadIdx.x; i < ny; i += blockDim.x) {
-        int c = i % brick.x, cy = (i / brick.x) % brick.y, z = i / (brick.x * brick.y);
-        float2 r = rx[(z * TY + cy * cell) * brick.x + c];
-        for (int k = 1; k < cell + 2; ++k) {
-            float2 v = rx[(z * TY + cy * cell + k) * brick.x + c];
+    for (int i = threadIdx.x; i < BX * BY * TZ; i += 256) {
+        const int c = i % BX, cy = (i / BX) % BY, z = i / (BX * BY);
+        float2 r = rx[(z * TY + cy * CELL) * BX + c];
+#pragma unroll
+        for (int k = 1; k < CELL + 2; ++k) {
+            const float2 v = rx[(z * TY + cy * CELL + k) * BX + c];
             r.x = fminf(r.x, v.x);
             r.y = fmaxf(r.y, v.y);
         }
-        ry[(z * brick.y + cy) * brick.x + c] = r;
+        ry[(z * BY + cy) * BX + c] = r;
     }
     __syncthreads();
-    const int nz = brick.x * brick.y * brick.z;
-    for (int i = threadIdx.x; i < nz; i += blockDim.x) {
-        int c = i % brick.x, cy = (i / brick.x) % brick.y, cz = i / (brick.x * brick.y);
-        float2 r = ry[((cz * cell) * brick.y + cy) * brick.x + c];
-        for (int k = 1; k < cell + 2; ++k) {
-            float2 v = ry[((cz * cell + k) * brick.y + cy) * brick.x + c];
+    for (int i = threadIdx.x; i < BX * BY * BZ; i += 256) {
+        const int c = i % BX, cy = (i / BX) % BY, cz = i / (BX * BY);
+        float2 r = ry[((cz * CELL) * BY + cy) * BX + c];
+#pragma unroll
+        for (int k = 1; k < CELL + 2; ++k) {
+            const float2 v = ry[((cz * CELL + k) * BY + cy) * BX + c];
             r.x = fminf(r.x, v.x);
             r.y = fmaxf(r.y, v.y);
         }
-        int gx = cx0 + c, gy = cy0 + cy, gz = cz0 + cz;
-        if (gx < grid.x && gy < grid.y && gz < grid.z) out[((size_t)gz * grid.y + gy) * grid.x + gx] = r;
+        const int gx = cx0 + c, gy = cy0 + cy, gz = cz0 + cz;
+        if (gx < grid.x && gy < grid.y && gz < grid.z)
+            out[((size_t)gz * grid.y + gy) * grid.x + gx] = r;
+    }
+}
+
+template <class Fetch, int CELL>
+int launch_range_brick_cell(HostState& st, Fetch fetch)
+{
+    constexpr int BX = 32 / CELL, BY = CELL <= 8 ? 8 / CELL : 1, BZ = BY;
+    constexpr int TX = BX * CELL + 2, TY = BY * CELL + 2, TZ = BZ * CELL + 2;
+    constexpr size_t shm = sizeof(float) * ((size_t)TX * TY * TZ + 2 * (size_t)BX * TY * TZ + 2 * (size_t)BX * BY * TZ);
+    dim3 g((st.gridDims.x + BX - 1) / BX, (st.gridDims.y + BY - 1) / BY, (st.gridDims.z + BZ - 1) / BZ);
+    if (shm > 48 * 1024)
+        SVR_TRY(cudaFuncSetAttribute(range_brick_kernel<Fetch, CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    range_brick_kernel<Fetch, CELL><<<g, 256, shm, st.stream>>>(fetch, st.gridDims, st.dRange);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <class Fetch>
+int launch_range_brick(HostState& st, Fetch fetch)
+{
+    switch (st.gridCell) {
+        case 2: return launch_range_brick_cell<Fetch, 2>(st, fetch);
+        case 4: return launch_range_brick_cell<Fetch, 4>(st, fetch);
+        case 8: return launch_range_brick_cell<Fetch, 8>(st, fetch);
+        case 16: return launch_range_brick_cell<Fetch, 16>(st, fetch);
+        default: return fail_msg("range grid: brick kernel needs a cell edge of 2, 4, 8 or 16");
     }
 }
 
@@ -311,20 +366,14 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
     if (!st.rangeValid) {
         // ---- stage 1: range grid (again after svr_volume_upload: same allocations, new voxels)
         if (cell <= 16) {
-            // brick = 32 x 8 x 8 voxels (32 x 16 x 16 for 16-voxel cells)
-            const int3 brick = make_int3(32 / cell, cell <= 8 ? 8 / cell : 1, cell <= 8 ? 8 / cell : 1);
-            const int TX = brick.x * cell + 2, TY = brick.y * cell + 2, TZ = brick.z * cell + 2;
-            const size_t shm = sizeof(float) * ((size_t)TX * TY * TZ + 2 * (size_t)brick.x * TY * TZ + 2 * (size_t)brick.x * brick.y * TZ);
-            dim3 g((st.gridDims.x + brick.x - 1) / brick.x, (st.gridDims.y + brick.y - 1) / brick.y, (st.gridDims.z + brick.z - 1) / brick.z);
-            if (shm > 48 * 1024)
-                SVR_TRY(cudaFuncSetAttribute(range_brick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-            range_brick_kernel<<<g, 256, shm, st.stream>>>(st.volPointTex, st.gridDims, cell, brick, st.dRange);
+            int rc = launch_range_brick(st, TexFetch{st.volPointTex});
+            if (rc) return rc;
         } else {
             dim3 g(st.gridDims.x, st.gridDims.y, st.gridDims.z);
             range_kernel<<<g, 128, 0, st.stream>>>(st.volPointTex, st.volDims, st.gridDims, cell, st.dRange);
+            count_launch();
+            SVR_TRY(cudaGetLastError());
         }
-        count_launch();
-        SVR_TRY(cudaGetLastError());
         st.rangeValid = true;
         st.majorantValid = false;
     }

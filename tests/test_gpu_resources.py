@@ -139,6 +139,67 @@ def test_upload_into_bound_resources_equals_fresh_load(renderer):
     assert torch.equal(pt_a, pt_d) and torch.equal(rc_a, rc_d)
 
 
+@pytest.mark.parametrize("fmt", [L.VOXEL_U8, L.VOXEL_U16, L.VOXEL_F16, L.VOXEL_F32])
+@pytest.mark.parametrize("cell", [4, 8, 16])
+def test_range_grid_follows_uploads_from_host_and_device(renderer, fmt, cell):
+    """The macrocell ranges after svr_volume_upload (host or device source) are those of a fresh load of
+    the same voxels, float for float -- every u8 / u16 value, a volume whose dimensions are not multiples
+    of the cell (zero border), every brick-kernel cell size."""
+    dims = (45, 38, 29)  # x, y, z
+    rng = np.random.default_rng(11)
+    nvox = dims[0] * dims[1] * dims[2]
+    dt = S.VOXEL_DTYPES[fmt]
+
+    def volume(seed):
+        r_ = np.random.default_rng(seed)
+        if fmt == L.VOXEL_U8:
+            v = r_.integers(0, 256, nvox).astype(dt)
+            v[:256] = np.arange(256)
+        elif fmt == L.VOXEL_U16:
+            v = r_.integers(0, 65536, nvox).astype(dt)
+            v[:16384] = np.arange(0, 65536, 4) + seed % 4
+        else:
+            v = r_.random(nvox).astype(dt)
+        v = v.reshape(dims[2], dims[1], dims[0])
+        v[:, :, : dims[0] // 3] = 0  # an empty region
+        return v
+
+    def ranges():
+        renderer.frame_no = 0
+        renderer.render_pathtracer_spp(1, 1)  # brings the grid up to date
+        torch.cuda.synchronize()
+        g, c = (C.c_int32 * 3)(), C.c_int32()
+        L.check(renderer.lib.svr_grid_info(g, C.byref(c)))
+        assert c.value == cell
+        out = np.zeros((g[2], g[1], g[0], 2), np.float32)
+        L.check(renderer.lib.svr_grid_copy(None, C.c_void_p(out.ctypes.data)))
+        return out
+
+    a, b = volume(1), volume(2)
+    setup(renderer, small_config(n=16, w=32, h=32))
+    renderer.set_option(L.OPT_MACROCELL_SIZE, cell)
+    renderer.load_volume(a, fmt, dims, max_grad_mag=1000.0)
+    renderer.set_camera(S.default_camera(dims, 32, 32))
+    ra_tex = ranges()                                    # fresh load
+    renderer.upload_volume(b)                            # host source
+    rb_tex = ranges()
+    assert not np.array_equal(ra_tex, rb_tex)
+    renderer.upload_volume(torch.from_numpy(a.copy()).cuda().view(torch.uint8))   # device source
+    ra_lin = ranges()
+    renderer.upload_volume(torch.from_numpy(b.copy()).cuda().view(torch.uint8))
+    rb_lin = ranges()
+    assert np.array_equal(ra_tex.view(np.uint32), ra_lin.view(np.uint32))
+    assert np.array_equal(rb_tex.view(np.uint32), rb_lin.view(np.uint32))
+    assert ra_lin[..., 0].min() == 0.0 and ra_lin[..., 1].max() > 0.9
+    # against numpy on the same voxels: min / max over texels cC-1 .. (c+1)C with a zero border
+    norm = {L.VOXEL_U8: 255.0, L.VOXEL_U16: 65535.0}.get(fmt, 1.0)
+    pad = np.zeros((dims[2] + 2 * cell + 2, dims[1] + 2 * cell + 2, dims[0] + 2 * cell + 2), np.float64)
+    pad[1:1 + dims[2], 1:1 + dims[1], 1:1 + dims[0]] = a.astype(np.float64) / norm
+    for (gz, gy, gx) in ((0, 0, 0), (ra_lin.shape[0] - 1, ra_lin.shape[1] - 1, ra_lin.shape[2] - 1), (1, 1, 2)):
+        blk = pad[gz * cell:gz * cell + cell + 2, gy * cell:gy * cell + cell + 2, gx * cell:gx * cell + cell + 2]
+        assert ra_lin[gz, gy, gx, 0] == np.float32(blk.min()) and ra_lin[gz, gy, gx, 1] == np.float32(blk.max())
+
+
 def test_volume_stream_equals_direct_uploads(renderer):
     """render.VolumeStream (the transfer of frame i+1 overlapped with the rendering of frame i, what bench.py's
     e2e loop does) renders a sequence of volumes to the same images, bit for bit, as uploading each one directly."""
