@@ -14,7 +14,7 @@ ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := -std=c++17 -O3 -use_fast_math -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v -cudart shared
 CSRC     := sunvolumerender_b200/csrc
 OBJDIR   := build/obj
-SRCS     := $(CSRC)/svr_api.cu $(CSRC)/svr_macrocell.cu $(CSRC)/svr_raycast.cu $(CSRC)/svr_pathtrace.cu $(CSRC)/svr_volume_io.cu $(CSRC)/svr_tf_io.cu $(CSRC)/svr_env_io.cu
+SRCS     := $(CSRC)/svr_api.cu $(CSRC)/svr_macrocell.cu $(CSRC)/svr_raycast.cu $(CSRC)/svr_pathtrace.cu $(CSRC)/svr_volume_io.cu $(CSRC)/svr_tf_io.cu $(CSRC)/svr_env_io.cu $(CSRC)/svr_canvas.cu
 OBJS     := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 HDRS     := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h include/*.h)
 LIB      := sunvolumerender_b200/libsvr_b200.so
@@ -36,7 +36,7 @@ oracle:
 
 tools: tools/svr_headless
 
-tools/svr_headless: tools/svr_headless.cpp $(LIB) include/svr_render.h include/svr_types.h include/svr_volume_io.h include/svr_tf_io.h
+tools/svr_headless: tools/svr_headless.cpp $(LIB) include/svr_canvas.h include/svr_render.h include/svr_types.h include/svr_volume_io.h include/svr_tf_io.h
 	$(HOSTCXX) -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include tools/svr_headless.cpp -o $@ \
 	    -Lsunvolumerender_b200 -lsvr_b200 -L/usr/local/cuda/lib64 -lcudart -ldl \
 	    -Wl,-rpath,'$$ORIGIN/../sunvolumerender_b200' -Wl,-rpath,/usr/local/cuda/lib64

@@ -225,6 +225,67 @@ SIGNATURES_ENV = [
 ]
 
 
+# ---- include/svr_canvas.h
+class View(C.Structure):  # svr_view: the camera-related members of Canvas (gui/canvas.h:210-217)
+    _fields_ = [("viewMat", C.c_float * 16), ("eyeDist", C.c_float), ("translate", C.c_float * 2), ("fov", C.c_float),
+                ("apeture", C.c_float), ("focalLength", C.c_float), ("exposure", C.c_float), ("mouseStart", C.c_float * 2)]
+
+
+BUTTON_LEFT, BUTTON_MID = 1, 4
+KEY_LEFT, KEY_RIGHT, KEY_DOWN = 0, 1, 2
+RENDER_MODE_PATHTRACER, RENDER_MODE_RAYCASTING = 0, 1
+_F3 = C.POINTER(C.c_float * 3)
+_V = C.POINTER(View)
+
+SIGNATURES_CANVAS = [
+    ("svr_view_init", None, [_V]),
+    ("svr_view_zoom_to_extent", None, [_V, _F3]),
+    ("svr_view_reset", None, [_V, _F3]),
+    ("svr_view_rotate", None, [_V, C.c_float, C.c_float, C.c_float, C.c_float]),
+    ("svr_view_pixel_to_view", None, [C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_float * 2)]),
+    ("svr_view_mouse_press", C.c_int, [_V, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_int]),
+    ("svr_view_mouse_move", C.c_int, [_V, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_int, _F3]),
+    ("svr_view_wheel", C.c_int, [_V, C.c_int, _F3]),
+    ("svr_view_key", C.c_int, [_V, C.c_int]),
+    ("svr_view_camera", None, [_V, C.c_uint32, C.c_uint32, C.POINTER(Camera)]),
+    ("svr_canvas_create", _P, [C.c_uint32, C.c_uint32]),
+    ("svr_canvas_destroy", None, [_P]),
+    ("svr_canvas_load_volume", C.c_int, [_P, C.c_char_p]),
+    ("svr_canvas_set_volume", C.c_int, [_P, C.POINTER(Volume), _F3, C.c_float]),
+    ("svr_canvas_set_transfer_function", C.c_int, [_P, C.POINTER(TransferFunction)]),
+    ("svr_canvas_set_density_scale", C.c_int, [_P, C.c_double]),
+    ("svr_canvas_set_gradient_factor", C.c_int, [_P, C.c_double]),
+    ("svr_canvas_set_scatter_times", C.c_int, [_P, C.c_double]),
+    ("svr_canvas_set_render_mode", C.c_int, [_P, C.c_int]),
+    ("svr_canvas_set_env_background", C.c_int, [_P, C.c_float, C.c_float, C.c_float]),
+    ("svr_canvas_set_env_map", C.c_int, [_P, C.c_char_p]),
+    ("svr_canvas_set_env_offset", C.c_int, [_P, C.c_float, C.c_float]),
+    ("svr_canvas_set_env_intensity", C.c_int, [_P, C.c_float]),
+    ("svr_canvas_set_area_lights", C.c_int, [_P, C.POINTER(AreaLight), C.c_uint32]),
+    ("svr_canvas_set_fov", C.c_int, [_P, C.c_float]),
+    ("svr_canvas_set_apeture", C.c_int, [_P, C.c_float]),
+    ("svr_canvas_set_focal_length", C.c_int, [_P, C.c_float]),
+    ("svr_canvas_set_exposure", C.c_int, [_P, C.c_float]),
+    ("svr_canvas_set_clip_plane", C.c_int, [_P, C.c_int, C.c_double, C.c_double]),
+    ("svr_canvas_mouse_press", C.c_int, [_P, C.c_float, C.c_float, C.c_int]),
+    ("svr_canvas_mouse_move", C.c_int, [_P, C.c_float, C.c_float, C.c_int]),
+    ("svr_canvas_wheel", C.c_int, [_P, C.c_int]),
+    ("svr_canvas_key", C.c_int, [_P, C.c_int]),
+    ("svr_canvas_paint", C.c_int, [_P]),
+    ("svr_canvas_paint_into", C.c_int, [_P, _P]),
+    ("svr_canvas_set_immediate_repaint", None, [_P, C.c_int]),
+    ("svr_canvas_image", _P, [_P]),
+    ("svr_canvas_hdr", _P, [_P]),
+    ("svr_canvas_read_image", C.c_int, [_P, _P]),
+    ("svr_canvas_frame_no", C.c_uint32, [_P]),
+    ("svr_canvas_paint_count", C.c_uint64, [_P]),
+    ("svr_canvas_get_view", None, [_P, _V]),
+    ("svr_canvas_get_camera", None, [_P, C.POINTER(Camera)]),
+    ("svr_canvas_get_volume", None, [_P, C.POINTER(Volume)]),
+    ("svr_canvas_get_env_light", None, [_P, C.POINTER(EnvLight)]),
+]
+
+
 class SvrError(RuntimeError):
     pass
 
@@ -243,7 +304,7 @@ def load():
             "sunvolumerender_b200 has no CPU or PyTorch fallback."
         )
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
-    for name, res, args in SIGNATURES + SIGNATURES_IO + SIGNATURES_TF + SIGNATURES_ENV:
+    for name, res, args in SIGNATURES + SIGNATURES_IO + SIGNATURES_TF + SIGNATURES_ENV + SIGNATURES_CANVAS:
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args

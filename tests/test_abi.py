@@ -27,6 +27,7 @@ def test_header_and_binding_agree():
     assert _declared_functions("svr_volume_io.h") == sorted(n for n, _, _ in L.SIGNATURES_IO)
     assert _declared_functions("svr_tf_io.h") == sorted(n for n, _, _ in L.SIGNATURES_TF)
     assert _declared_functions("svr_env_io.h") == sorted(n for n, _, _ in L.SIGNATURES_ENV)
+    assert _declared_functions("svr_canvas.h") == sorted(n for n, _, _ in L.SIGNATURES_CANVAS)
 
 
 def test_reference_boundary_symbols_present():
@@ -39,7 +40,7 @@ def test_library_exports_every_declared_symbol():
     assert os.path.exists(L.LIB_PATH), "build with `make lib`"
     out = subprocess.check_output(["nm", "-D", "--defined-only", L.LIB_PATH], text=True)
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
-    missing = [n for n in _declared_functions() + _declared_functions("svr_volume_io.h") + _declared_functions("svr_tf_io.h") + _declared_functions("svr_env_io.h") if n not in exported]
+    missing = [n for n in _declared_functions() + _declared_functions("svr_volume_io.h") + _declared_functions("svr_tf_io.h") + _declared_functions("svr_env_io.h") + _declared_functions("svr_canvas.h") if n not in exported]
     assert not missing, missing
 
 

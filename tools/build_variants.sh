@@ -9,7 +9,7 @@ for v in "$@"; do
   name=${v%%:*}; flags=${v#*:}
   ( nvcc -std=c++17 -O3 -use_fast_math -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v -cudart shared \
       $flags -c sunvolumerender_b200/csrc/svr_pathtrace.cu -o build/variants/pt_$name.o 2> build/variants/pt_$name.log
-    nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart shared -o build/variants/libsvr_$name.so build/obj/svr_api.o build/obj/svr_macrocell.o build/obj/svr_raycast.o build/obj/svr_volume_io.o build/obj/svr_tf_io.o build/obj/svr_env_io.o build/variants/pt_$name.o -lz ) &
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart shared -o build/variants/libsvr_$name.so build/obj/svr_api.o build/obj/svr_macrocell.o build/obj/svr_raycast.o build/obj/svr_volume_io.o build/obj/svr_tf_io.o build/obj/svr_env_io.o build/obj/svr_canvas.o build/variants/pt_$name.o -lz ) &
 done
 wait
 for v in "$@"; do

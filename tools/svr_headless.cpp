@@ -6,6 +6,12 @@
 //
 //   svr_headless [--config C1|C2|C3|C4] [--mode pt|rc] [--spp N] [--depth D] [--batched 0|1]
 //                [--pt-mode 0|1|2] [--n N --w W --h H] [--out prefix] [--reps R] [--volume file.mhd|.mha] [--tf file.tf|app]
+//                [--interact script.txt]
+// --interact replays an interaction script through the windowless Canvas (include/svr_canvas.h: gui/canvas.cpp's
+// event handlers, setters and frame protocol) instead of timing a render loop.  One command per line:
+//   press X Y BUTTONS | move X Y BUTTONS | wheel DELTA | key left|right|down      (BUTTONS: 1 left, 4 middle)
+//   mode pt|rc | depth D | density S | gradient G | fov F | exposure E | apeture A | focal L | clip x|y|z LO HI
+//   envcolor R G B | envintensity I | envmap file.hdr | repaint 0|1 | paint N | save prefix
 //
 // --volume loads a MetaImage file the way Canvas::LoadVolume does (core/VolumeReader.cpp:13-94) instead of
 // generating the configuration's synthetic volume; camera and light are framed on its extent.
@@ -24,6 +30,10 @@
 #include <string>
 #include <vector>
 
+#include <fstream>
+#include <sstream>
+
+#include "svr_canvas.h"
 #include "svr_render.h"
 #include "svr_tf_io.h"
 #include "svr_volume_io.h"
@@ -83,6 +93,7 @@ int main(int argc, char** argv)
 {
     Config cfg = kConfigs[0];
     std::string mode = "pt", out = "svr_out", volumePath, tfPath;
+    std::string interactPath;
     int batched = 1, ptMode = 2, reps = 3, sppArg = -1, depthArg = -1;
     for (int i = 1; i + 1 < argc; i += 2) {
         std::string k = argv[i], v = argv[i + 1];
@@ -103,6 +114,7 @@ int main(int argc, char** argv)
         else if (k == "--volume") volumePath = v;
         else if (k == "--tf") tfPath = v;
         else if (k == "--reps") reps = atoi(v.c_str());
+        else if (k == "--interact") interactPath = v;
         else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
     }
     if (sppArg > 0) cfg.spp = sppArg;
@@ -182,6 +194,78 @@ int main(int argc, char** argv)
     env.defaultRadiance = {0.5f, 0.5f, 0.5f};  // gui/canvas.cpp:11-12
     env.intensity = 1.f;
     setup_env_lights(&env);
+
+    if (!interactPath.empty()) {
+        // ---- the windowless Canvas driven by a script of events and setters
+        svr_canvas* canvas = svr_canvas_create((uint32_t)W, (uint32_t)H);
+        if (!canvas) {
+            fprintf(stderr, "svr_canvas_create failed: %s\n", svr_last_error());
+            return 1;
+        }
+        const float size[3] = {2.f * vol.bbox.vmax.x, 2.f * vol.bbox.vmax.y, 2.f * vol.bbox.vmax.z};  // VolumeReader::GetVolumeSize
+        const float radius = 0.5f * sqrtf(vol.spacing.x * vol.spacing.x + vol.spacing.y * vol.spacing.y + vol.spacing.z * vol.spacing.z);
+        SVR(svr_canvas_set_volume(canvas, &vol, size, radius));
+        SVR(svr_canvas_set_transfer_function(canvas, &tf));
+        SVR(svr_canvas_set_area_lights(canvas, &light, 1));
+        std::ifstream in(interactPath);
+        if (!in) {
+            fprintf(stderr, "cannot open %s\n", interactPath.c_str());
+            return 1;
+        }
+        std::string line;
+        int lineNo = 0;
+        while (std::getline(in, line)) {
+            ++lineNo;
+            std::istringstream ls(line);
+            std::string cmd;
+            if (!(ls >> cmd) || cmd[0] == '#') continue;
+            float a = 0.f, b = 0.f, c3 = 0.f;
+            int n = 0;
+            std::string word;
+            if (cmd == "press" && ls >> a >> b >> n) SVR(svr_canvas_mouse_press(canvas, a, b, n));
+            else if (cmd == "move" && ls >> a >> b >> n) SVR(svr_canvas_mouse_move(canvas, a, b, n));
+            else if (cmd == "wheel" && ls >> n) SVR(svr_canvas_wheel(canvas, n));
+            else if (cmd == "key" && ls >> word) SVR(svr_canvas_key(canvas, word == "left" ? SVR_KEY_LEFT : word == "right" ? SVR_KEY_RIGHT : SVR_KEY_DOWN));
+            else if (cmd == "mode" && ls >> word) SVR(svr_canvas_set_render_mode(canvas, word == "pt" ? SVR_RENDER_MODE_PATHTRACER : SVR_RENDER_MODE_RAYCASTING));
+            else if (cmd == "depth" && ls >> a) SVR(svr_canvas_set_scatter_times(canvas, a));
+            else if (cmd == "density" && ls >> a) SVR(svr_canvas_set_density_scale(canvas, a));
+            else if (cmd == "gradient" && ls >> a) SVR(svr_canvas_set_gradient_factor(canvas, a));
+            else if (cmd == "fov" && ls >> a) SVR(svr_canvas_set_fov(canvas, a));
+            else if (cmd == "exposure" && ls >> a) SVR(svr_canvas_set_exposure(canvas, a));
+            else if (cmd == "apeture" && ls >> a) SVR(svr_canvas_set_apeture(canvas, a));
+            else if (cmd == "focal" && ls >> a) SVR(svr_canvas_set_focal_length(canvas, a));
+            else if (cmd == "clip" && ls >> word >> a >> b) SVR(svr_canvas_set_clip_plane(canvas, word == "x" ? 0 : word == "y" ? 1 : 2, a, b));
+            else if (cmd == "envcolor" && ls >> a >> b >> c3) SVR(svr_canvas_set_env_background(canvas, a, b, c3));
+            else if (cmd == "envintensity" && ls >> a) SVR(svr_canvas_set_env_intensity(canvas, a));
+            else if (cmd == "envmap" && ls >> word) SVR(svr_canvas_set_env_map(canvas, word.c_str()));
+            else if (cmd == "repaint" && ls >> n) svr_canvas_set_immediate_repaint(canvas, n);
+            else if (cmd == "paint" && ls >> n) {
+                for (int i = 0; i < n; ++i) SVR(svr_canvas_paint(canvas));
+            } else if (cmd == "save" && ls >> word) {
+                std::vector<unsigned char> px(npix * 4);
+                SVR(svr_canvas_read_image(canvas, px.data()));
+                FILE* f = fopen((word + ".ppm").c_str(), "wb");
+                if (f) {
+                    fprintf(f, "P6\n%d %d\n255\n", W, H);
+                    for (int y = H - 1; y >= 0; --y)
+                        for (int x = 0; x < W; ++x) fwrite(&px[4 * ((size_t)y * W + x)], 1, 3, f);
+                    fclose(f);
+                }
+            } else {
+                fprintf(stderr, "%s:%d: cannot parse '%s'\n", interactPath.c_str(), lineNo, line.c_str());
+                return 2;
+            }
+        }
+        svr_camera cc;
+        svr_canvas_get_camera(canvas, &cc);
+        printf("{\"interact\": \"%s\", \"paints\": %llu, \"frame_no\": %u, \"camera_pos\": [%.4f, %.4f, %.4f], \"launches\": %llu}\n",
+               interactPath.c_str(), (unsigned long long)svr_canvas_paint_count(canvas), svr_canvas_frame_no(canvas), cc.pos.x, cc.pos.y, cc.pos.z,
+               (unsigned long long)svr_launch_count());
+        svr_canvas_destroy(canvas);
+        svr_volume_destroy(&vol);
+        svr_tf_destroy(&tf);
+        return 0;
+    }
 
     // RenderParams::SetupHDRBuffer (render_parameters.h:17-23) and the image the PBO would be
     svr_render_params rp;
