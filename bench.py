@@ -238,6 +238,7 @@ def run_ours(a):
     ms = D.max_over_ranks(ms_local, dev)
     kernel_ms = sum(x.elapsed_time(y) for x, y in kernel_events) / len(kernel_events)
     value = npix * spp * world * a.steps / (ms * 1e-3)
+    cell_used = grid_cell(r)  # before other scenes are loaded into the renderer
 
     # ---- e2e: everything from host buffers, results back on the host
     def run_e2e():
@@ -322,6 +323,9 @@ def run_ours(a):
     else:
         e2e, img_nonzero = run_e2e()
 
+    # the metric's second half at N > 1 (collective: every rank takes part)
+    raycast_multi = raycast_lines_multi(r, rank, world, dev) if world > 1 and not a.no_raycast else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -361,7 +365,7 @@ def run_ours(a):
     if world == 1 and not a.no_ref_cuda:
         ref_cuda = reference_cuda_sample(cfg, r, 16)
 
-    raycast = raycast_lines(r) if world == 1 and not a.no_ref_cuda else None
+    raycast = (raycast_lines(r) if not a.no_ref_cuda and not a.no_raycast else None) if world == 1 else raycast_multi
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -375,7 +379,7 @@ def run_ours(a):
             "parallelism": f"spp-split x{world}, volume replicated (e2e fan-out: {(e2e or {}).get('fanout')}), NCCL sum-reduce of float4 accumulators to rank 0"
                            if world > 1 else "single GPU",
             "estimator": {0: "global majorant + XORWOW (reference twin)", 1: "global majorant + Philox", 2: "macrocell local majorants + Philox"}[a.pt_mode],
-            "macrocell": grid_cell(r),
+            "macrocell": cell_used,
             "l2": f"volume {vb.numel() >> 20} MiB > 126 MB L2 and incoherent taps; no flush between steps",
             "image_nonzero_fraction": round(img_nonzero, 4) if img_nonzero is not None else None,
         },
@@ -482,6 +486,64 @@ def raycast_lines(r):
         except (FileNotFoundError, OSError) as e:
             line["reference_cuda"] = {"unavailable": str(e)}
         out.append(line)
+    return out
+
+
+def raycast_lines_multi(r, rank, world, dev):
+    """Ray casting on N GPUs (the metric's "ray-cast Mrays/s at 1/2/4/8 B200"): C2 replicated, image ROWS split
+    across the ranks (one deterministic pass), the u8 row blocks gathered onto rank 0 with
+    NCCL.  Timed per frame with CUDA events, max over ranks, best of 10 frames; rank 0 also renders the whole
+    frame alone and the gathered image must equal it bit for bit."""
+    import torch
+    import torch.distributed as dist
+
+    from sunvolumerender_b200 import distributed as D
+    from sunvolumerender_b200 import scene as S
+    from sunvolumerender_b200.render import setup_config
+
+    out = []
+    for tf in ("thin", "default"):
+        cfg = S.Config("C2", 256, 0, 1, 1024, 1024, tf)
+        setup_config(r, cfg)
+        W, H = cfg.width, cfg.height
+        step = S.raycast_step_size()
+        rows = S.split_rows(H, world)
+        y0, y1 = rows[rank]
+        pad = max(b - a for a, b in rows)
+        block = torch.zeros(pad * W * 4, dtype=torch.uint8, device=dev)
+        gathered = [torch.zeros_like(block) for _ in range(world)] if rank == 0 else None
+        img = r.img.view(H, W, 4)
+
+        even = all(b - a == pad for a, b in rows)
+        mine = r.img[y0 * W * 4: y1 * W * 4] if even else block   # a rank's rows are contiguous in the image
+
+        def frame():
+            r.render_raycasting_f32(None, step, rows=(y0, y1), img=r.img)   # this rank's rows of the u8 image
+            if not even:
+                block[: (y1 - y0) * W * 4].copy_(img[y0:y1].reshape(-1))
+            dist.gather(mine, gathered, dst=0)
+
+        frame()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(10):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            frame()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+            best = ms if best is None else min(best, ms)
+        equal = None
+        if rank == 0:
+            full = torch.cat([g[: (b - a) * W * 4] for g, (a, b) in zip(gathered, rows)]).view(H, W, 4)
+            r.render_raycasting(step)
+            torch.cuda.synchronize()
+            equal = bool(torch.equal(full, r.ldr_image()))
+        out.append({"workload": f"C2: 256^3 u8 CT-like volume, 1024x1024, TF-{tf}, rows split x{world}, NCCL gather of u8 row blocks",
+                    "value": W * H / (best * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": best, "equals_single_gpu_image": equal})
     return out
 
 
@@ -605,6 +667,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-raycast", action="store_true")
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--ref-r32", action="store_true", help="reference built with the shipped -maxrregcount=32")
     a = ap.parse_args()
