@@ -89,7 +89,8 @@ enum svr_option {
     /* path-tracer kernel shape: 2 = sample-parallel warp (the lanes of a warp take different samples of
      * the same pixel), 1 = megakernel (one pixel per lane, samples one after the other),
      * 0 = phase-scheduled warp (generate / march / collide / event / bounce phases, the warp
-     * votes each round and runs the phase most lanes wait in) */
+     * votes each round and runs the phase most lanes wait in), 3 = sample-parallel warp with the scatter
+     * queue at every depth (see SVR_OPT_PT_QUEUE_MIN_DEPTH) */
     SVR_OPT_PT_KERNEL = 9,
     /* phase-scheduled kernel: macrocell visits per MARCH round (0 = default 4) */
     SVR_OPT_PT_ROUNDS = 10,
@@ -105,6 +106,11 @@ enum svr_option {
      * megakernel.  Images differ from the other shapes only in float summation order. */
     SVR_OPT_PT_WARP_PIXELS = 13,
     SVR_OPT_PT_WARP_MIN_SPP = 14,
+    /* SVR_OPT_PT_KERNEL = 2 with local majorants (SVR_OPT_PT_MODE = 2): from this traceDepth on the
+     * sample-parallel kernel runs with a per-warp queue of scatter events in shared memory (kernel shape 3:
+     * camera-ray rounds and scatter-event rounds that each start with all 32 lanes busy, however unequal the
+     * path lengths).  Default 8; 0 = never.  Images differ from shape 2 only in float summation order. */
+    SVR_OPT_PT_QUEUE_MIN_DEPTH = 15,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

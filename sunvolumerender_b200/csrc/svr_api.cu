@@ -32,12 +32,13 @@ HostState& state()
         p->options[SVR_OPT_PT_ENTRY_CACHE] = 1;
         p->options[SVR_OPT_PT_WARP_PIXELS] = 4;
         p->options[SVR_OPT_PT_WARP_MIN_SPP] = 32;
+        p->options[SVR_OPT_PT_QUEUE_MIN_DEPTH] = 8;
         // A host that only knows the reference's seven entry points (gui/canvas.cpp) cannot call
         // svr_set_option: the same switches are read once from the environment.
         static const struct { const char* name; int key, lo, hi; } kEnv[] = {
             {"SVR_PT_MODE", SVR_OPT_PT_MODE, 0, 2},           {"SVR_SHADOW_ESTIMATOR", SVR_OPT_SHADOW_ESTIMATOR, 0, 1},
             {"SVR_ENV_ENABLED", SVR_OPT_ENV_ENABLED, 0, 1},   {"SVR_RC_SKIP", SVR_OPT_RC_SKIP, 0, 1},
-            {"SVR_SEED", SVR_OPT_SEED, INT32_MIN, INT32_MAX}, {"SVR_PT_KERNEL", SVR_OPT_PT_KERNEL, 0, 2},
+            {"SVR_SEED", SVR_OPT_SEED, INT32_MIN, INT32_MAX}, {"SVR_PT_KERNEL", SVR_OPT_PT_KERNEL, 0, 3},
         };
         for (const auto& e : kEnv) {
             const char* v = getenv(e.name);
@@ -168,13 +169,16 @@ extern "C" int svr_set_option(int key, int value)
             if (value != 64 && value != 128 && value != 256) return fail_msg("block size must be 64, 128 or 256");
             break;
         case SVR_OPT_PT_KERNEL:
-            if (value < 0 || value > 2) return fail_msg("SVR_OPT_PT_KERNEL must be 0, 1 or 2");
+            if (value < 0 || value > 3) return fail_msg("SVR_OPT_PT_KERNEL must be 0, 1, 2 or 3");
             break;
         case SVR_OPT_PT_WARP_PIXELS:
             if (value < 1 || value > 64) return fail_msg("SVR_OPT_PT_WARP_PIXELS must be in 1..64");
             break;
         case SVR_OPT_PT_WARP_MIN_SPP:
             if (value < 1) return fail_msg("SVR_OPT_PT_WARP_MIN_SPP must be >= 1");
+            break;
+        case SVR_OPT_PT_QUEUE_MIN_DEPTH:
+            if (value < 0) return fail_msg("SVR_OPT_PT_QUEUE_MIN_DEPTH must be >= 0");
             break;
         case SVR_OPT_PT_ROUNDS:
             if (value < 0) return fail_msg("SVR_OPT_PT_ROUNDS must be >= 0");

@@ -432,7 +432,7 @@ struct PathState {
 };
 
 // what a lane does next
-enum Next { NEXT_TRACK = 0, NEXT_PATH_DONE = 1, NEXT_FLIGHT_MISSED = 2, NEXT_BOUNCE = 3 };
+enum Next { NEXT_TRACK = 0, NEXT_PATH_DONE = 1, NEXT_FLIGHT_MISSED = 2, NEXT_BOUNCE = 3, NEXT_EVENT_AT_T = 4 /* scatter queue: a collision popped from the queue */ };
 
 // pathtracer.cu:204-213: seed, camera ray; then start tracking it.  Returns false when the ray
 // cannot collide (misses the volume): an immediate "escaped" event.
@@ -601,6 +601,23 @@ SVR_DEV void path_end(PathState<MODE>& ps)
 template <int MODE>
 SVR_DEV float3 pixel_sum(const PathState<MODE>& ps) { return MODE == 0 ? ps.sum : ps.L; }
 
+// One flight: the tracking loop of the ray in ps.ray (started with ps.trk.begin).  Returns the parameter of the
+// real collision that ended it, or -FLT_MAX (the ray left the medium; a ratio-tracked shadow ray always does).
+template <int MODE, bool COUNT>
+SVR_DEV float fly(const DevScene& s, PathState<MODE>& ps, LocalCounters<COUNT>& lc)
+{
+    const int slot = ps.shadow ? SVR_CNT_SHADOW_TAPS : SVR_CNT_TRACK_TAPS;
+    float* ratio = (ps.shadow && s.shadowEstimator) ? &ps.ratioT : nullptr;
+    while (true) {
+        VisitResult v = ps.trk.template visit<COUNT>(s, ps.ray, ps.rng, lc);
+        if (v == VISIT_CONTINUE) continue;
+        if (v == VISIT_ESCAPED) break;
+        if (ps.trk.template collide<COUNT>(s, ps.ray, ps.rng, lc, slot, ratio)) return ps.trk.t;
+        if (ratio && ratio_roulette(ps.ratioT, ps.rng)) break;
+    }
+    return -FLT_MAX;
+}
+
 // One path: the reference's loop nest for one (pixel, sample), added to the pixel's accumulators.
 template <int MODE, bool COUNT>
 SVR_DEV void trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE>& ps, uint32_t idx, uint32_t idy, uint32_t offset,
@@ -620,20 +637,7 @@ SVR_DEV void trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE>&
     if (a.traceDepth == 0) next = NEXT_PATH_DONE;  // the bounce loop never runs (pathtracer.cu:216): the sample is black
     while (next != NEXT_PATH_DONE) {
         float t = -FLT_MAX;
-        if (next == NEXT_TRACK) {
-            const int slot = ps.shadow ? SVR_CNT_SHADOW_TAPS : SVR_CNT_TRACK_TAPS;
-            float* ratio = (ps.shadow && s.shadowEstimator) ? &ps.ratioT : nullptr;
-            while (true) {
-                VisitResult v = ps.trk.template visit<COUNT>(s, ps.ray, ps.rng, lc);
-                if (v == VISIT_CONTINUE) continue;
-                if (v == VISIT_ESCAPED) break;
-                if (ps.trk.template collide<COUNT>(s, ps.ray, ps.rng, lc, slot, ratio)) {
-                    t = ps.trk.t;
-                    break;
-                }
-                if (ratio && ratio_roulette(ps.ratioT, ps.rng)) break;
-            }
-        }
+        if (next == NEXT_TRACK) t = fly<MODE, COUNT>(s, ps, lc);
         if (next == NEXT_BOUNCE || ps.shadow)
             next = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, t), a.traceDepth, lc);
         else
@@ -694,6 +698,151 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             } else
             for (uint32_t n = lane; n < a.nSamples; n += 32u) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
             float3 sum = pixel_sum<MODE>(ps);
+            __syncwarp();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+                sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+                sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+            }
+            if (lane == 0) write_pixel(s, a, offset, sum);
+        }
+    }
+    lc.flush(cnt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel shape 3: sample-parallel warp with a scatter queue (deep paths).  In a high-albedo medium most
+// samples of a pixel leave after no or one scatter event and a few bounce traceDepth times; with the loop
+// nest of shape 2 the warp waits for its longest path (ncu on C4: 6 of 32 lanes active).  Here a warp
+// alternates between two kinds of rounds:
+//   A  32 camera rays of the pixel (coherent: same origin, neighbouring directions).  A sample whose camera
+//      ray leaves the medium is finished on the spot; one that collides is pushed on the warp's queue in
+//      shared memory as (ray, collision parameter, throughput, bounce count, random-stream position);
+//   B  when 32 queued collisions are waiting (or no camera ray is left): 32 lanes pop one each and run ONE
+//      scatter event -- shade, sample the light, fly the shadow ray, add the direct light, sample the BSDF,
+//      fly the bounce ray -- and push the collision that flight ends in, if any.
+// Both kinds run the same loop (trace_sample's), entered at different points and left at the first collision
+// that is not the lane's own, so every device function is instantiated once.
+// Every round starts with all lanes busy, whatever the depth of the paths they serve.  A path is still a
+// pure function of (seed, pixel, sample): the counter of its Philox stream travels with the queue entry.
+// The image equals shape 2 up to float summation order (the lanes add into per-lane partial sums).
+// ---------------------------------------------------------------------------------------------
+constexpr int SVR_QUEUE_CAP = 64;    // entries per warp: a round pushes at most 32 onto fewer than 32
+constexpr int SVR_QUEUE_WORDS = 14;  // orig 3, dir 3, t, T 3, k, c0, r1, have
+
+template <bool COUNT>
+SVR_DEV void queue_push(float* q, int idx, const PathState<2>& ps, float t)
+{
+    q[0 * SVR_QUEUE_CAP + idx] = ps.ray.orig.x;
+    q[1 * SVR_QUEUE_CAP + idx] = ps.ray.orig.y;
+    q[2 * SVR_QUEUE_CAP + idx] = ps.ray.orig.z;
+    q[3 * SVR_QUEUE_CAP + idx] = ps.ray.dir.x;
+    q[4 * SVR_QUEUE_CAP + idx] = ps.ray.dir.y;
+    q[5 * SVR_QUEUE_CAP + idx] = ps.ray.dir.z;
+    q[6 * SVR_QUEUE_CAP + idx] = t;
+    q[7 * SVR_QUEUE_CAP + idx] = ps.T.x;
+    q[8 * SVR_QUEUE_CAP + idx] = ps.T.y;
+    q[9 * SVR_QUEUE_CAP + idx] = ps.T.z;
+    q[10 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.k);
+    q[11 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.rng.c0);
+    q[12 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.rng.r1);
+    q[13 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.rng.have);
+}
+
+SVR_DEV float queue_pop(const float* q, int idx, PathState<2>& ps)
+{
+    ps.ray.orig = f3(q[0 * SVR_QUEUE_CAP + idx], q[1 * SVR_QUEUE_CAP + idx], q[2 * SVR_QUEUE_CAP + idx]);
+    ps.ray.dir = f3(q[3 * SVR_QUEUE_CAP + idx], q[4 * SVR_QUEUE_CAP + idx], q[5 * SVR_QUEUE_CAP + idx]);
+    ps.T = f3(q[7 * SVR_QUEUE_CAP + idx], q[8 * SVR_QUEUE_CAP + idx], q[9 * SVR_QUEUE_CAP + idx]);
+    ps.k = __float_as_uint(q[10 * SVR_QUEUE_CAP + idx]);
+    ps.rng.c0 = __float_as_uint(q[11 * SVR_QUEUE_CAP + idx]);
+    ps.rng.r1 = __float_as_uint(q[12 * SVR_QUEUE_CAP + idx]);
+    ps.rng.have = __float_as_uint(q[13 * SVR_QUEUE_CAP + idx]);
+    ps.shadow = false;
+    return q[6 * SVR_QUEUE_CAP + idx];
+}
+
+// One more block per SM than the other shapes (64 registers, some spills): this kernel serves incoherent deep
+// paths in volumes that miss the caches, where more warps in flight pay (C4: 130 -> 125 ms per 128 spp).
+template <bool COUNT>
+__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS + 1) pathtrace_queue_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+{
+    constexpr int MODE = 2;
+    __shared__ float queues[SVR_PT_MAX_THREADS / 32][SVR_QUEUE_WORDS * SVR_QUEUE_CAP];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 5) + warp;
+    float* q = queues[warp];
+    LocalCounters<COUNT> lc;
+    if (idy < a.y1) {
+        PathState<MODE> ps;
+        for (uint32_t i = 0; i < (uint32_t)a.warpPixels; ++i) {
+            const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
+            if (idx >= s.cam.imageW) break;
+            const uint32_t offset = idy * s.cam.imageW + idx;
+            const PixelInfo pi = classify_pixel(s, idx, idy, true, a.entryCache != 0);
+            pixel_begin<MODE>(ps);
+            ps.camLights = pi.lights;
+            if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
+                // every sample of this pixel is the constant sky (see trace_sample): the same additions, nothing else
+                const float3 sky = (a.traceDepth != 0 && s.envEnabled) ? f3(s.env.defaultRadiance) * s.env.intensity : f3(0.f);
+                for (uint32_t n = lane; n < a.nSamples; n += 32u) {
+                    lc.add(SVR_CNT_PATHS, 1);
+                    ps.L += sky;
+                }
+            } else if (a.traceDepth == 0) {
+                for (uint32_t n = lane; n < a.nSamples; n += 32u) lc.add(SVR_CNT_PATHS, 1);  // black (pathtracer.cu:216)
+            } else {
+                uint32_t nextN = 0;  // camera rays issued so far (warp-uniform)
+                int queued = 0;      // entries on the queue (warp-uniform)
+                while (nextN < a.nSamples || queued > 0) {
+                    // what this lane does in the round: a popped collision (round B) or a fresh camera ray (round A)
+                    bool active, own = false;  // own: the flight-end event at hand is the popped entry's own collision
+                    Next next = NEXT_PATH_DONE;
+                    float t = -FLT_MAX;
+                    if (queued >= 32 || nextN >= a.nSamples) {
+                        const int take = queued < 32 ? queued : 32;
+                        queued -= take;
+                        active = (int)lane < take;
+                        if (active) {
+                            ps.rng.c1 = offset * 0x9E3779B1u + s.seedKey;  // Philox::init's pixel word
+                            t = queue_pop(q, queued + (int)lane, ps);
+                            next = NEXT_EVENT_AT_T;
+                            own = true;
+                        }
+                    } else {
+                        const uint32_t n = nextN + lane;
+                        nextN += 32u;
+                        active = n < a.nSamples;
+                        if (active) {
+                            lc.add(SVR_CNT_PATHS, 1);
+                            next = path_begin<MODE>(s, ps, idx, idy, offset, a.firstSample + n, pi.tSkip) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+                        }
+                    }
+                    __syncwarp();  // every pop of the round precedes every push
+                    // trace_sample's loop, left at the first collision that is not the lane's own: that one is queued
+                    bool push = false;
+                    while (active) {
+                        if (next == NEXT_TRACK) t = fly<MODE, COUNT>(s, ps, lc);
+                        else if (next != NEXT_EVENT_AT_T) t = -FLT_MAX;
+                        if (next == NEXT_BOUNCE || ps.shadow) {
+                            next = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, t), a.traceDepth, lc);
+                        } else {
+                            if (t >= 0.f && !own) {
+                                push = true;
+                                break;
+                            }
+                            own = false;
+                            next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
+                        }
+                        if (next == NEXT_PATH_DONE) break;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, push);
+                    if (push) queue_push<COUNT>(q, queued + __popc(m & ((1u << lane) - 1u)), ps, t);
+                    queued += __popc(m);
+                }
+            }
+            float3 sum = ps.L;
             __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -844,7 +993,10 @@ __global__ void resolve_kernel(const float4* __restrict__ sum, float* __restrict
 template <int MODE>
 void launch_mode(int shape, dim3 grid, int block, cudaStream_t stream, const DevScene& sc, const PtLaunch& a, Counters* cnt)
 {
-    if (shape == 2) {
+    if (shape == 3) {  // launch_pathtrace() only picks it for MODE 2
+        if (cnt) pathtrace_queue_kernel<true><<<grid, block, 0, stream>>>(sc, a, cnt);
+        else pathtrace_queue_kernel<false><<<grid, block, 0, stream>>>(sc, a, cnt);
+    } else if (shape == 2) {
         if (cnt) pathtrace_warp_kernel<MODE, true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_warp_kernel<MODE, false><<<grid, block, 0, stream>>>(sc, a, cnt);
     } else if (shape == 1) {
@@ -884,10 +1036,15 @@ int launch_pathtrace(PtLaunch a)
     const int block = st.options[SVR_OPT_PT_BLOCK];
     int shape = st.options[SVR_OPT_PT_KERNEL];
     // the sample-parallel shape needs a warp's worth of samples per pixel; below that one lane per pixel
-    if (shape == 2 && a.nSamples < (uint32_t)st.options[SVR_OPT_PT_WARP_MIN_SPP]) shape = 1;
+    // deep paths: the sample-parallel shape gets its scatter queue
+    const int queueDepth = st.options[SVR_OPT_PT_QUEUE_MIN_DEPTH];
+    if (shape == 2 && queueDepth > 0 && a.traceDepth >= (uint32_t)queueDepth) shape = 3;
+    // the scatter queue serves local-majorant Philox paths; the other estimators run the plain sample-parallel shape
+    if (shape == 3 && mode != 2) shape = 2;
+    if (shape >= 2 && a.nSamples < (uint32_t)st.options[SVR_OPT_PT_WARP_MIN_SPP]) shape = 1;
     a.warpPixels = st.options[SVR_OPT_PT_WARP_PIXELS];
     uint32_t tileW = 16u, tileH = (uint32_t)block / 16u;
-    if (shape == 2) {
+    if (shape >= 2) {
         tileW = (uint32_t)a.warpPixels;
         tileH = (uint32_t)block / 32u;
     }

@@ -20,6 +20,7 @@ def setup(r, cfg):
     r.set_option(L.OPT_PT_KERNEL, 2)
     r.set_option(L.OPT_PT_WARP_PIXELS, 4)
     r.set_option(L.OPT_PT_WARP_MIN_SPP, 32)
+    r.set_option(L.OPT_PT_QUEUE_MIN_DEPTH, 8)
     r.set_option(L.OPT_SHADOW_ESTIMATOR, 0)
     r.set_option(L.OPT_RC_SKIP, 1)
     r.set_option(L.OPT_LEAP, 1)

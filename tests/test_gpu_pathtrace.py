@@ -157,7 +157,7 @@ def _statistical_parity(renderer, cfg, depth, K, per, configure, mean_tol=0.01, 
     return mine, ref_all
 
 
-@pytest.mark.parametrize("mode,estimator,shape", [(2, 0, 2), (2, 1, 2), (1, 0, 2), (1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0)])
+@pytest.mark.parametrize("mode,estimator,shape", [(2, 0, 2), (2, 1, 2), (1, 0, 2), (1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0), (2, 0, 3), (2, 1, 3)])
 def test_product_modes_are_statistically_the_reference(renderer, mode, estimator, shape):
     """Philox / local-majorant / ratio-tracking modes and all three kernel shapes draw different random
     numbers from the same estimator as the reference's kernel_pathtracer."""
@@ -217,6 +217,60 @@ def test_sample_parallel_shape_equals_megakernel_up_to_summation_order(renderer)
         assert torch.equal(imgs[(2, 1, 64, 0)], imgs[(2, 4, 128, 1)])
         assert torch.equal(imgs[(2, 7, 64, 1)], imgs[(2, 4, 128, 1)])
     renderer.set_option(L.OPT_PT_BLOCK, 128)
+
+
+@pytest.mark.parametrize("gen,fmt,tf,depth,estimator", [(L.GEN_CT, L.VOXEL_U16, "default", 1, 0), (L.GEN_CT, L.VOXEL_U16, "default", 6, 1),
+                                                     (L.GEN_CLOUD, L.VOXEL_F16, "cloud", 32, 0), (L.GEN_SPHERE, L.VOXEL_U8, "thin", 8, 0)])
+def test_scatter_queue_shape_equals_sample_parallel_up_to_summation_order(renderer, gen, fmt, tf, depth, estimator):
+    """Kernel shape 3 (camera rounds + a per-warp queue of scatter events in shared memory) serves every sample with
+    the same random stream and the same sequence of draws as shape 2: identical paths, a different order of additions."""
+    cfg = small_config(n=80, w=150, h=101, gen=gen, fmt=fmt, tf=tf, depth=depth, env=True)
+    setup(renderer, cfg)
+    renderer.set_option(L.OPT_SHADOW_ESTIMATOR, estimator)
+    renderer.set_option(L.OPT_PT_QUEUE_MIN_DEPTH, 0)  # shape 2 means shape 2 here, whatever the depth
+    for spp in (96, 40):
+        imgs = {}
+        for shape, wp, blk in ((2, 4, 128), (3, 4, 128), (3, 3, 64)):
+            renderer.set_option(L.OPT_PT_KERNEL, shape)
+            renderer.set_option(L.OPT_PT_WARP_PIXELS, wp)
+            renderer.set_option(L.OPT_PT_BLOCK, blk)
+            renderer.frame_no = 0
+            renderer.render_pathtracer_spp(spp, depth)
+            torch.cuda.synchronize()
+            imgs[(shape, wp, blk)] = renderer.hdr_image().clone()
+        base = imgs[(2, 4, 128)]
+        assert float(base.max()) > 0
+        assert torch.allclose(imgs[(3, 4, 128)], base, rtol=5e-5, atol=2e-6), float((imgs[(3, 4, 128)] - base).abs().max())
+        assert torch.equal(imgs[(3, 3, 64)], imgs[(3, 4, 128)])  # launch geometry does not enter the result
+    # counted work is the same too: the same paths
+    counts = {}
+    for shape in (2, 3):
+        renderer.set_option(L.OPT_PT_KERNEL, shape)
+        renderer.set_option(L.OPT_COUNTERS, 1)
+        renderer.reset_counters()
+        renderer.frame_no = 0
+        renderer.render_pathtracer_spp(64, depth)
+        torch.cuda.synchronize()
+        counts[shape] = renderer.counters()
+        renderer.set_option(L.OPT_COUNTERS, 0)
+    # (the two kernels are compiled separately: a last-bit difference in a ray parameter can move a handful of
+    # cell visits; collisions, scatter events and paths are the same)
+    for k in counts[2]:
+        if k == "cells":
+            assert abs(counts[2][k] - counts[3][k]) <= 1e-4 * counts[2][k]
+        else:
+            assert counts[2][k] == counts[3][k], k
+    assert counts[2]["scatters"] > 0
+    # the default: shape 2 turns into shape 3 from traceDepth 8 on
+    renderer.set_option(L.OPT_PT_KERNEL, 2)
+    renderer.set_option(L.OPT_PT_BLOCK, 128)
+    renderer.set_option(L.OPT_PT_WARP_PIXELS, 4)
+    renderer.set_option(L.OPT_PT_QUEUE_MIN_DEPTH, 8)
+    renderer.frame_no = 0
+    renderer.render_pathtracer_spp(40, depth)
+    torch.cuda.synchronize()
+    auto = renderer.hdr_image().clone()
+    assert torch.equal(auto, imgs[(3, 4, 128)] if depth >= 8 else imgs[(2, 4, 128)])
 
 
 def test_deterministic_and_seeded(renderer):
