@@ -156,6 +156,15 @@ int svr_render_raycasting_rows(svr_u8vec4* img, svr_vec4* outOrNull, const svr_v
                                const svr_transfer_function* tf, const svr_camera* camera, float stepSize,
                                uint32_t y0, uint32_t y1);
 
+/* The balanced split: the image is cut into bands of *bandRows rows (the kernel's block height) and this call
+ * renders bands phase, phase + stride, phase + 2 stride, ... -- rank r of N passes (r, N).  Contiguous row blocks
+ * give the ranks that see the body several times the work of the ranks that see its margins; interleaved bands
+ * do not.  Rows outside the call's bands are left untouched (zero the image first and sum-reduce the u8 images:
+ * disjoint bands make the sum a gather). */
+int svr_render_raycasting_bands(svr_u8vec4* img, svr_vec4* outOrNull, const svr_volume* volume,
+                                const svr_transfer_function* tf, const svr_camera* camera, float stepSize,
+                                uint32_t phase, uint32_t stride, uint32_t* bandRows);
+
 /* ---- resource builders (the input contract of the path) ---- */
 enum svr_voxel_format { SVR_VOXEL_U8 = 0, SVR_VOXEL_U16 = 1, SVR_VOXEL_F16 = 2, SVR_VOXEL_F32 = 3 };
 

@@ -134,6 +134,8 @@ SIGNATURES = [
     ("svr_render_raycasting_rows", C.c_int, [_P, _P, C.POINTER(Volume), C.POINTER(TransferFunction), C.POINTER(Camera), C.c_float, C.c_uint32, C.c_uint32]),
     ("svr_volume_create", C.c_int, [C.POINTER(Volume), _P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float]),
     ("svr_volume_destroy", C.c_int, [C.POINTER(Volume)]),
+    ("svr_render_raycasting_bands", C.c_int, [_P, _P, C.POINTER(Volume), C.POINTER(TransferFunction), C.POINTER(Camera), C.c_float, C.c_uint32, C.c_uint32,
+                                            C.POINTER(C.c_uint32)]),
     ("svr_volume_upload", C.c_int, [C.POINTER(Volume), _P, C.c_int]),
     ("svr_stage_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     ("svr_stage_free", C.c_int, [_P]),

@@ -20,12 +20,14 @@ namespace {
 
 template <bool SKIP, bool COUNT>
 __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ DevScene s, float stepSize, uint32_t* __restrict__ img,
-                                                      float4* __restrict__ outf, uint32_t y0, uint32_t y1, Counters* cnt)
+                                                      float4* __restrict__ outf, uint32_t y0, uint32_t y1, uint32_t bandPhase,
+                                                      uint32_t bandStride, Counters* cnt)
 {
-    // warp = 8x4 pixel tile; block = 16 pixels wide, 2 warps across
+    // warp = 8x4 pixel tile; block = 16 pixels wide, 2 warps across.  Row bands of the block's height are dealt out
+    // round robin: this launch renders bands bandPhase, bandPhase + bandStride, ... (1 GPU: phase 0, stride 1)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idx = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t idy = y0 + blockIdx.y * (blockDim.x >> 4) + (warp >> 1) * 4u + (lane >> 3);
+    const uint32_t idy = y0 + (blockIdx.y * bandStride + bandPhase) * (blockDim.x >> 4) + (warp >> 1) * 4u + (lane >> 3);
     const bool inside = idx < s.cam.imageW && idy < y1;
     LocalCounters<COUNT> lc;
 
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ De
 }
 
 int launch_raycast(uint32_t* img, float4* outf, const svr_volume* volume, const svr_transfer_function* tf,
-                   const svr_camera* camera, float stepSize, uint32_t y0, uint32_t y1)
+                   const svr_camera* camera, float stepSize, uint32_t y0, uint32_t y1, uint32_t bandPhase = 0, uint32_t bandStride = 1)
 {
     HostState& st = state();
     if (!volume || !tf || !camera) return fail_msg("render_raycasting: null scene argument");
@@ -134,13 +136,16 @@ int launch_raycast(uint32_t* img, float4* outf, const svr_volume* volume, const 
     if (count && !cnt) return fail_msg("render_raycasting: counter allocation failed");
     const int block = st.options[SVR_OPT_RC_BLOCK];
     const uint32_t tileH = (uint32_t)block / 16u;  // block tile = 16 pixels x block/16 rows
-    dim3 grid((camera->imageW + 15u) / 16u, ((y1 - y0) + tileH - 1u) / tileH);
+    const uint32_t bands = ((y1 - y0) + tileH - 1u) / tileH;
+    if (bandStride == 0 || bandPhase >= bandStride) return fail_msg("render_raycasting: band phase must be below the band stride");
+    if (bandPhase >= bands) return 0;
+    dim3 grid((camera->imageW + 15u) / 16u, (bands - bandPhase + bandStride - 1u) / bandStride);
     if (skip) {
-        if (count) raycast_kernel<true, true><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, cnt);
-        else raycast_kernel<true, false><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, cnt);
+        if (count) raycast_kernel<true, true><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt);
+        else raycast_kernel<true, false><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt);
     } else {
-        if (count) raycast_kernel<false, true><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, cnt);
-        else raycast_kernel<false, false><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, cnt);
+        if (count) raycast_kernel<false, true><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt);
+        else raycast_kernel<false, false><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt);
     }
     count_launch();
     SVR_TRY(cudaGetLastError());
@@ -175,4 +180,12 @@ extern "C" int svr_render_raycasting_rows(svr_u8vec4* img, svr_vec4* outOrNull, 
                                           uint32_t y0, uint32_t y1)
 {
     return launch_raycast((uint32_t*)img, (float4*)outOrNull, volume, tf, camera, stepSize, y0, y1);
+}
+
+extern "C" int svr_render_raycasting_bands(svr_u8vec4* img, svr_vec4* outOrNull, const svr_volume* volume,
+                                           const svr_transfer_function* tf, const svr_camera* camera, float stepSize,
+                                           uint32_t phase, uint32_t stride, uint32_t* bandRows)
+{
+    if (bandRows) *bandRows = (uint32_t)state().options[SVR_OPT_RC_BLOCK] / 16u;
+    return launch_raycast((uint32_t*)img, (float4*)outOrNull, volume, tf, camera, stepSize, 0, camera ? camera->imageH : 0, phase, stride);
 }

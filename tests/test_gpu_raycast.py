@@ -161,3 +161,28 @@ def test_empty_volume_and_ragged_image_size(renderer):
     out = raycast_f32(renderer)
     assert float(out.abs().max()) == 0.0
     assert int(renderer.ldr_image().max()) == 0
+
+
+def test_interleaved_bands_tile_the_image(renderer):
+    """svr_render_raycasting_bands: the bands of phases 0..stride-1 are disjoint and together are the frame."""
+    cfg = small_config(gen=L.GEN_CT, fmt=L.VOXEL_U16, w=150, h=101)
+    setup(renderer, cfg)
+    renderer.render_raycasting(STEP)
+    torch.cuda.synchronize()
+    full = renderer.ldr_image().clone()
+    assert int(full[..., 3].max()) > 100
+    for stride, block in ((3, 64), (8, 64), (2, 256), (1, 128)):
+        renderer.set_option(L.OPT_RC_BLOCK, block)
+        total = torch.zeros_like(full, dtype=torch.int32)
+        for phase in range(stride):
+            renderer.img.zero_()
+            rows = renderer.render_raycasting_bands(phase, stride, STEP)
+            torch.cuda.synchronize()
+            assert rows == block // 16
+            part = renderer.ldr_image()
+            band = (torch.arange(cfg.height, device="cuda") // rows) % stride
+            assert int(part[band != phase].abs().sum()) == 0           # nothing outside this phase's bands
+            total += part.int()
+        assert torch.equal(total, full.int())
+    renderer.set_option(L.OPT_RC_BLOCK, 64)
+    assert renderer.lib.svr_render_raycasting_bands(None, None, None, None, None, STEP, 0, 1, None) != 0
