@@ -342,6 +342,7 @@ extern "C" int svr_canvas_load_volume(svr_canvas* c, const char* path)
 
 extern "C" int svr_canvas_set_volume(svr_canvas* c, const svr_volume* vol, const float volume_size[3], float element_radius)
 {
+    if (!c) return fail_msg("svr_canvas_set_volume: null canvas");
     if (!c || !vol || !vol->tex || !volume_size) return fail_msg("svr_canvas_set_volume: bad argument");
     const float gradientFactor = c->volume.gradientFactor;
     drop_volume(c);
@@ -352,6 +353,7 @@ extern "C" int svr_canvas_set_volume(svr_canvas* c, const svr_volume* vol, const
 
 extern "C" int svr_canvas_set_transfer_function(svr_canvas* c, const svr_transfer_function* tf)
 {
+    if (!c) return fail_msg("svr_canvas_set_transfer_function: null canvas");
     if (!c || !tf) return fail_msg("svr_canvas_set_transfer_function: bad argument");
     c->tf = *tf;
     setup_transferfunction(&c->tf);
@@ -360,6 +362,7 @@ extern "C" int svr_canvas_set_transfer_function(svr_canvas* c, const svr_transfe
 
 extern "C" int svr_canvas_set_density_scale(svr_canvas* c, double s)
 {
+    if (!c) return fail_msg("svr_canvas_set_density_scale: null canvas");
     c->volume.densityScale = (float)s;
     setup_volume(&c->volume);
     return restart(c);
@@ -367,6 +370,7 @@ extern "C" int svr_canvas_set_density_scale(svr_canvas* c, double s)
 
 extern "C" int svr_canvas_set_gradient_factor(svr_canvas* c, double g)
 {
+    if (!c) return fail_msg("svr_canvas_set_gradient_factor: null canvas");
     c->volume.gradientFactor = (float)g;
     setup_volume(&c->volume);
     return restart(c);
@@ -374,12 +378,14 @@ extern "C" int svr_canvas_set_gradient_factor(svr_canvas* c, double g)
 
 extern "C" int svr_canvas_set_scatter_times(svr_canvas* c, double depth)
 {
+    if (!c) return fail_msg("svr_canvas_set_scatter_times: null canvas");
     c->renderParams.traceDepth = (uint32_t)depth;
     return restart(c);
 }
 
 extern "C" int svr_canvas_set_render_mode(svr_canvas* c, int mode)
 {
+    if (!c) return fail_msg("svr_canvas_set_render_mode: null canvas");
     if (mode != SVR_RENDER_MODE_PATHTRACER && mode != SVR_RENDER_MODE_RAYCASTING) return fail_msg("svr_canvas_set_render_mode: bad mode");
     c->renderMode = mode;  // the timer that repaints in path-tracer mode (canvas.h:80-93) is the host's paint loop
     return restart(c);
@@ -387,6 +393,7 @@ extern "C" int svr_canvas_set_render_mode(svr_canvas* c, int mode)
 
 extern "C" int svr_canvas_set_env_background(svr_canvas* c, float r, float g, float b)
 {
+    if (!c) return fail_msg("svr_canvas_set_env_background: null canvas");
     // cudaEnvironmentLight::Set(radiance) also resets intensity to 1 and the offset (cuda_environment_light.h:25-31)
     drop_env_tex(c);
     c->env.tex = 0;
@@ -399,6 +406,7 @@ extern "C" int svr_canvas_set_env_background(svr_canvas* c, float r, float g, fl
 
 extern "C" int svr_canvas_set_env_map(svr_canvas* c, const char* hdr_path)
 {
+    if (!c) return fail_msg("svr_canvas_set_env_map: null canvas");
     svr_env_light e;
     int rc = svr_env_load_hdr(hdr_path, &e);  // Lights::SetEnvironmentLight(filename): Set(tex), intensity 1, offset 0
     if (rc) return rc;
@@ -413,6 +421,7 @@ extern "C" int svr_canvas_set_env_map(svr_canvas* c, const char* hdr_path)
 
 extern "C" int svr_canvas_set_env_offset(svr_canvas* c, float u, float v)
 {
+    if (!c) return fail_msg("svr_canvas_set_env_offset: null canvas");
     c->env.offset = {u, v};
     setup_env_lights(&c->env);
     return restart(c);
@@ -420,6 +429,7 @@ extern "C" int svr_canvas_set_env_offset(svr_canvas* c, float u, float v)
 
 extern "C" int svr_canvas_set_env_intensity(svr_canvas* c, float intensity)
 {
+    if (!c) return fail_msg("svr_canvas_set_env_intensity: null canvas");
     c->env.intensity = intensity;
     setup_env_lights(&c->env);
     return restart(c);
@@ -427,6 +437,7 @@ extern "C" int svr_canvas_set_env_intensity(svr_canvas* c, float intensity)
 
 extern "C" int svr_canvas_set_area_lights(svr_canvas* c, const svr_area_light* lights, uint32_t n)
 {
+    if (!c) return fail_msg("svr_canvas_set_area_lights: null canvas");
     c->lights.assign(lights, lights + (lights ? n : 0));
     svr_area_light none;
     memset(&none, 0, sizeof(none));
@@ -436,6 +447,7 @@ extern "C" int svr_canvas_set_area_lights(svr_canvas* c, const svr_area_light* l
 
 extern "C" int svr_canvas_set_fov(svr_canvas* c, float fov)
 {
+    if (!c) return fail_msg("svr_canvas_set_fov: null canvas");
     c->view.fov = fov;
     update_camera(c);
     return restart(c);
@@ -443,6 +455,7 @@ extern "C" int svr_canvas_set_fov(svr_canvas* c, float fov)
 
 extern "C" int svr_canvas_set_apeture(svr_canvas* c, float apeture)
 {
+    if (!c) return fail_msg("svr_canvas_set_apeture: null canvas");
     c->view.apeture = apeture;
     update_camera(c);
     return restart(c);
@@ -450,6 +463,7 @@ extern "C" int svr_canvas_set_apeture(svr_canvas* c, float apeture)
 
 extern "C" int svr_canvas_set_focal_length(svr_canvas* c, float focal_length)
 {
+    if (!c) return fail_msg("svr_canvas_set_focal_length: null canvas");
     c->view.focalLength = focal_length;
     update_camera(c);
     return restart(c);
@@ -457,6 +471,7 @@ extern "C" int svr_canvas_set_focal_length(svr_canvas* c, float focal_length)
 
 extern "C" int svr_canvas_set_exposure(svr_canvas* c, float exposure)
 {
+    if (!c) return fail_msg("svr_canvas_set_exposure: null canvas");
     c->view.exposure = exposure;
     update_camera(c);
     return restart(c);
@@ -464,6 +479,7 @@ extern "C" int svr_canvas_set_exposure(svr_canvas* c, float exposure)
 
 extern "C" int svr_canvas_set_clip_plane(svr_canvas* c, int axis, double lo, double hi)
 {
+    if (!c) return fail_msg("svr_canvas_set_clip_plane: null canvas");
     const svr_vec2 p = {(float)lo, (float)hi};
     if (axis == 0) c->volume.x_clip = p;
     else if (axis == 1) c->volume.y_clip = p;
@@ -475,12 +491,14 @@ extern "C" int svr_canvas_set_clip_plane(svr_canvas* c, int axis, double lo, dou
 
 extern "C" int svr_canvas_mouse_press(svr_canvas* c, float px, float py, int buttons)
 {
+    if (!c) return fail_msg("svr_canvas_mouse_press: null canvas");
     svr_view_mouse_press(&c->view, c->width, c->height, px, py, buttons);
     return 0;
 }
 
 extern "C" int svr_canvas_mouse_move(svr_canvas* c, float px, float py, int buttons)
 {
+    if (!c) return fail_msg("svr_canvas_mouse_move: null canvas");
     // one repaint per handled button (UpdateCamera(); updateGL()), then ReStartRender() (canvas.cpp:135-169)
     const int changed = svr_view_mouse_move(&c->view, c->width, c->height, px, py, buttons, c->volumeSize);
     if (changed) {
@@ -498,6 +516,7 @@ extern "C" int svr_canvas_mouse_move(svr_canvas* c, float px, float py, int butt
 
 extern "C" int svr_canvas_wheel(svr_canvas* c, int delta)
 {
+    if (!c) return fail_msg("svr_canvas_wheel: null canvas");
     svr_view_wheel(&c->view, delta, c->volumeSize);
     update_camera(c);
     return restart(c);
@@ -505,6 +524,7 @@ extern "C" int svr_canvas_wheel(svr_canvas* c, int delta)
 
 extern "C" int svr_canvas_key(svr_canvas* c, int key)
 {
+    if (!c) return fail_msg("svr_canvas_key: null canvas");
     if (!svr_view_key(&c->view, key)) return 0;
     update_camera(c);
     if (c->immediate) {
