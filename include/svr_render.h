@@ -156,8 +156,9 @@ int svr_render_raycasting_rows(svr_u8vec4* img, svr_vec4* outOrNull, const svr_v
                                const svr_transfer_function* tf, const svr_camera* camera, float stepSize,
                                uint32_t y0, uint32_t y1);
 
-/* The balanced split: the image is cut into bands of *bandRows rows (the kernel's block height) and this call
- * renders bands phase, phase + stride, phase + 2 stride, ... -- rank r of N passes (r, N).  Contiguous row blocks
+/* The balanced split: the image is cut into bands of *bandRows rows (the kernel's block height), numbered from
+ * the middle of the image outwards (0 = the middle band, 1 = the one below it, 2 = the one above, ...), and this
+ * call renders bands phase, phase + stride, phase + 2 stride, ... -- rank r of N passes (r, N).  Contiguous row blocks
  * give the ranks that see the body several times the work of the ranks that see its margins; interleaved bands
  * do not.  Rows outside the call's bands are left untouched (zero the image first and sum-reduce the u8 images:
  * disjoint bands make the sum a gather). */

@@ -180,8 +180,12 @@ def test_interleaved_bands_tile_the_image(renderer):
             torch.cuda.synchronize()
             assert rows == block // 16
             part = renderer.ldr_image()
-            band = (torch.arange(cfg.height, device="cuda") // rows) % stride
-            assert int(part[band != phase].abs().sum()) == 0           # nothing outside this phase's bands
+            # bands are counted from the middle of the image outwards: k = 0 is the middle band, 1 the one below, ...
+            n_bands = (cfg.height + rows - 1) // rows
+            mid = n_bands // 2
+            k_of_band = torch.tensor([2 * (b - mid) if b >= mid else 2 * (mid - b) - 1 for b in range(n_bands)], device="cuda")
+            k = k_of_band[torch.arange(cfg.height, device="cuda") // rows]
+            assert int(part[k % stride != phase].abs().sum()) == 0     # nothing outside this phase's bands
             total += part.int()
         assert torch.equal(total, full.int())
     renderer.set_option(L.OPT_RC_BLOCK, 64)
