@@ -17,8 +17,9 @@ reduced over the ranks (N > 1: one NCCL sum-reduce of the per-GPU buffers onto r
             N > 1: one PCIe upload on rank 0 + an NCCL broadcast over NVLink), re-uploads the
             transfer-function table, re-publishes camera and lights, renders, and reads the tone-mapped
             image and the float accumulator back into pinned host memory.  Frames are streamed: the
-            upload of step i+1 runs on a copy stream beside the rendering of step i (render.VolumeStream);
-            the same loop without that overlap is reported as e2e.ms_per_step_without_overlap.
+            upload of step i+1 runs on a copy stream beside the rendering of step i (render.VolumeStream)
+            and the read-back of step i beside the binding and rendering of step i+1; the same loop
+            without any overlap is reported as e2e.ms_per_step_without_overlap.
   roofline  HBM: algorithmic bytes per launch (COUNTED taps x 8 voxels x bytes/voxel + TF lookups x 32 B
             + framebuffer bytes) / the path-tracing kernel's mean launch duration
             measured with CUDA events inside the timed region, against MEASURED_PEAKS.json.
@@ -268,7 +269,17 @@ def run_ours(a):
         vs = VolumeStream(r, vb.numel(), group=bgroup, fanout=a.e2e_fanout)
         fanout = vs.fanout
 
-        def e2e_step(prefetch_next, serial=False):
+        # Results stream out the same way: rank 0 resolves frame i, a read-back stream copies image + accumulator to
+        # pinned host buffers (double-buffered) while frame i+1 is being bound and rendered, and the caller looks
+        # at frame i-1.  The setup_* calls of the next frame must not wait for that copy: SVR_OPT_SETUP_SYNC = 0.
+        rb_stream = torch.cuda.Stream(device=dev)
+        host_imgs = [host_img, torch.empty_like(host_img).pin_memory()]
+        host_hdrs = [host_hdr, torch.empty_like(host_hdr).pin_memory()]
+        resolved = [torch.cuda.Event(), torch.cuda.Event()]
+        read_back = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def e2e_step(i, prefetch_next, serial=False):
+            main = torch.cuda.current_stream()
             if serial:
                 vs.prefetch(host_vox)                  # no overlap: transfer, then render
             vs.bind()                                  # staged voxels -> cudaArray; macrocell ranges rebuilt at the next render
@@ -282,23 +293,39 @@ def run_ours(a):
             if world > 1:
                 dist.reduce(sum_buf, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
+                slot = i & 1
+                main.wait_event(read_back[slot ^ 1])   # resolve overwrites r.img / r.hdr: the previous frame's copy has left
                 r.resolve(sum_buf)
-                host_img.copy_(r.img, non_blocking=True)
-                host_hdr.copy_(r.hdr, non_blocking=True)
-                torch.cuda.current_stream().synchronize()  # the caller looks at the image
+                if serial:
+                    host_imgs[slot].copy_(r.img, non_blocking=True)
+                    host_hdrs[slot].copy_(r.hdr, non_blocking=True)
+                    main.synchronize()                 # the caller looks at this frame
+                else:
+                    resolved[slot].record(main)
+                    with torch.cuda.stream(rb_stream):
+                        rb_stream.wait_event(resolved[slot])
+                        host_imgs[slot].copy_(r.img, non_blocking=True)
+                        host_hdrs[slot].copy_(r.hdr, non_blocking=True)
+                        read_back[slot].record(rb_stream)
+                    if i > 0:
+                        read_back[slot ^ 1].synchronize()  # the caller looks at the previous frame
 
         def e2e_run(steps, serial):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r.set_option(L.OPT_SETUP_SYNC, 1 if serial else 0)
             barrier()
             t0 = time.time()
             ev0.record()
             if not serial:
                 vs.prefetch(host_vox)
             for i in range(steps):
-                e2e_step(i + 1 < steps, serial)
+                e2e_step(i, i + 1 < steps, serial)
+            if rank == 0 and not serial:
+                read_back[(steps - 1) & 1].synchronize()   # the last frame has reached the host
             ev1.record()
             barrier()
             t1 = time.time()
+            r.set_option(L.OPT_SETUP_SYNC, 1)
             return D.max_over_ranks(ev0.elapsed_time(ev1), dev), (t0, t1)
 
         e2e_run(max(1, min(a.warmup, 2)), False)
@@ -311,10 +338,13 @@ def run_ours(a):
         small = tf_table.nbytes + 112 + 16 + 76 + 44 * len(lights) + 32  # table + scene PODs, every rank
         h2d = int(vb.numel() * (world if fanout == "pcie" else 1) + small * world)
         d2h = int(host_img.numel() + host_hdr.numel() * 4)
-        img_nonzero = float((host_img.view(H, W, 4)[..., :3] > 0).float().mean()) if rank == 0 else 0.0
+        last = host_imgs[(a.steps - 1) & 1]
+        img_nonzero = float((last.view(H, W, 4)[..., :3] > 0).float().mean()) if rank == 0 else 0.0
+        if rank == 0:  # what reached the host is the frame on the device
+            assert torch.equal(last, r.img.cpu()) and torch.equal(host_hdrs[(a.steps - 1) & 1], r.hdr.cpu()), "e2e read-back differs from the device image"
         vs.close()
         return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
-                "pipeline": "frame i+1's H2D overlaps frame i's render (VolumeStream); every step uploads and reads back",
+                "pipeline": "frame i+1's H2D and frame i-1's D2H overlap frame i's render (VolumeStream, read-back stream); every step uploads and reads back",
                 "ms_per_step_without_overlap": e2e_serial_ms, "fanout": fanout}, img_nonzero
 
     if a.no_e2e or (vb.numel() > (2 << 30) and not a.force_e2e):

@@ -111,6 +111,11 @@ enum svr_option {
      * camera-ray rounds and scatter-event rounds that each start with all 32 lanes busy, however unequal the
      * path lengths).  Default 8; 0 = never.  Images differ from shape 2 only in float summation order. */
     SVR_OPT_PT_QUEUE_MIN_DEPTH = 15,
+    /* 1 (default) = setup_volume / _transferfunction / _camera / _env_lights return after cudaDeviceSynchronize,
+     * as the reference's do (pathtracer.cu:34-55).  0 = they only store the PODs (this library passes the scene
+     * as kernel parameters, there is no device copy to wait for): a streaming host whose copy streams must keep
+     * running across the setup calls of the next frame turns the synchronisation off. */
+    SVR_OPT_SETUP_SYNC = 16,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

@@ -33,6 +33,7 @@ HostState& state()
         p->options[SVR_OPT_PT_WARP_PIXELS] = 4;
         p->options[SVR_OPT_PT_WARP_MIN_SPP] = 32;
         p->options[SVR_OPT_PT_QUEUE_MIN_DEPTH] = 8;
+        p->options[SVR_OPT_SETUP_SYNC] = 1;
         // A host that only knows the reference's seven entry points (gui/canvas.cpp) cannot call
         // svr_set_option: the same switches are read once from the environment.
         static const struct { const char* name; int key, lo, hi; } kEnv[] = {
@@ -81,7 +82,7 @@ extern "C" void setup_volume(const svr_volume* vol)
     HostState& st = state();
     st.scene.vol = *vol;
     st.majorantValid = false;  // densityScale / array may have changed
-    SVR_FATAL(cudaDeviceSynchronize());
+    if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
 }
 
 extern "C" void setup_transferfunction(const svr_transfer_function* tf)
@@ -89,19 +90,21 @@ extern "C" void setup_transferfunction(const svr_transfer_function* tf)
     HostState& st = state();
     st.scene.tf = *tf;
     st.majorantValid = false;  // every TF edit invalidates the local majorants
-    SVR_FATAL(cudaDeviceSynchronize());
+    if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
 }
 
 extern "C" void setup_camera(const svr_camera* cam)
 {
-    state().scene.cam = *cam;
-    SVR_FATAL(cudaDeviceSynchronize());
+    HostState& st = state();
+    st.scene.cam = *cam;
+    if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
 }
 
 extern "C" void setup_env_lights(const svr_env_light* light)
 {
-    state().scene.env = *light;
-    SVR_FATAL(cudaDeviceSynchronize());
+    HostState& st = state();
+    st.scene.env = *light;
+    if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
 }
 
 extern "C" void setup_area_lights(svr_area_light* lights, uint32_t n)

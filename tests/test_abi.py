@@ -50,6 +50,8 @@ def test_library_loads_and_binds():
     assert lib.svr_get_option(L.OPT_PT_MODE) == 2
     assert lib.svr_get_option(L.OPT_MACROCELL_SIZE) == 0  # automatic
     assert lib.svr_get_option(L.OPT_PT_KERNEL) == 2
+    assert lib.svr_get_option(L.OPT_SETUP_SYNC) == 1          # setup_* synchronise like the reference's unless told otherwise
+    assert lib.svr_get_option(L.OPT_PT_QUEUE_MIN_DEPTH) == 8
     # option validation is host logic
     assert lib.svr_set_option(L.OPT_PT_MODE, 7) != 0
     assert b"SVR_OPT_PT_MODE" in lib.svr_last_error()
