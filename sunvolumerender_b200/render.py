@@ -324,8 +324,12 @@ class VolumeStream:
         self.stage_ptr = [None, None]
         self.peer_ptr = {}
         if self.fanout == "p2p":
-            self.host_group = host_group if host_group is not None else dist.new_group(backend="gloo")
-            if not self._setup_p2p():
+            try:
+                # host-side barrier and handle exchange; gloo needs a resolvable local address on every rank
+                self.host_group = host_group if host_group is not None else dist.new_group(backend="gloo")
+            except Exception:
+                self.host_group = None
+            if self.host_group is None or not self._setup_p2p():
                 self.fanout = "nvlink"
         if self.fanout != "p2p":
             self.stage = [torch.empty(self.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
