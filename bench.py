@@ -523,7 +523,7 @@ def raycast_lines(r):
 
 def other_workload_lines(r, a):
     """Context beside the headline: C4 (BASELINE.json configs[3]: 1024^3 f16 high-albedo cloud, traceDepth 32, macrocell
-    majorants, 1920x1080), device-resident, 64 of its 512 spp per launch, best of 3; and the reference's kernels on
+    majorants, 1920x1080), device-resident, 128 of its 512 spp per launch, best of 3; and the reference's kernels on
     the same scene (8 frames)."""
     import torch
 
@@ -535,7 +535,7 @@ def other_workload_lines(r, a):
         setup_config(r, cfg)
     except Exception as e:  # e.g. not enough device memory beside the other buffers
         return [{"workload": "C4", "unavailable": str(e)}]
-    spp = 64
+    spp = 128
     npix = cfg.width * cfg.height
     buf = torch.zeros(npix * 4, dtype=torch.float32, device="cuda")
     best = None
