@@ -15,8 +15,10 @@ extern "C" {
 
 /* Decodes a Radiance .hdr file (#?RADIANCE / #?RGBE, FORMAT=32-bit_rle_rgbe, "-Y h +X w", flat or
  * new-style run-length scanlines) to linear floats, channel = mantissa byte * 2^(exponent - 136) as
- * stbi_loadf does.  Call with rgb_out == NULL to get the size; then with room for 3 * w * h floats.
- * Host only: needs no GPU. */
+ * stbi_loadf does.  Call with rgb_out == NULL to get the size; then with room for 3 * w * h floats AND *w, *h
+ * still holding that size (in-out: a file whose size changed in between is an error, not an overrun).
+ * Pictures above 32768 per side or 2^27 pixels, and files too short for the picture their header declares, are
+ * rejected before anything is allocated.  Host only: needs no GPU. */
 int svr_hdr_read(const char* path, float* rgb_out, uint32_t* w, uint32_t* h);
 
 /* Lights::SetEnvironmentLight(filename) (core/lights/lights.cpp:31-75): reads the file, expands RGB to

@@ -116,6 +116,10 @@ enum svr_option {
      * as kernel parameters, there is no device copy to wait for): a streaming host whose copy streams must keep
      * running across the setup calls of the next frame turns the synchronisation off. */
     SVR_OPT_SETUP_SYNC = 16,
+    /* 1 (default) = a pixel whose camera rays provably pass every area-light disk skips get_nearest_light_sample
+     * (pathtracer.cu:214-215); 0 = every camera ray tests every disk, as the reference does.  Images are
+     * bit-identical either way (the cull is conservative). */
+    SVR_OPT_PT_LIGHT_CULL = 17,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

@@ -29,6 +29,10 @@ enum svr_met_type {
     SVR_MET_UINT = 4, SVR_MET_INT = 5, SVR_MET_FLOAT = 6, SVR_MET_DOUBLE = 7
 };
 
+/* Largest accepted DimSize per axis: the 3-D texture limit of every CUDA device (the voxels end in a 3-D cudaArray,
+ * core/VolumeReader.cpp:144-150).  Headers beyond it are rejected before anything is allocated. */
+#define SVR_MAX_VOLUME_DIM 16384u
+
 typedef struct svr_metaimage_header {
     uint32_t ndims;          /* NDims (2 or 3; a 2-D image is one slice) */
     uint32_t dim[3];         /* DimSize */

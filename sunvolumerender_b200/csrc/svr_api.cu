@@ -34,6 +34,7 @@ HostState& state()
         p->options[SVR_OPT_PT_WARP_MIN_SPP] = 32;
         p->options[SVR_OPT_PT_QUEUE_MIN_DEPTH] = 8;
         p->options[SVR_OPT_SETUP_SYNC] = 1;
+        p->options[SVR_OPT_PT_LIGHT_CULL] = 1;
         // A host that only knows the reference's seven entry points (gui/canvas.cpp) cannot call
         // svr_set_option: the same switches are read once from the environment.
         static const struct { const char* name; int key, lo, hi; } kEnv[] = {
@@ -77,11 +78,28 @@ using namespace svr;
 // later launch passes as its kernel parameter block; like the reference they return only after
 // the device is idle (cudaDeviceSynchronize), except setup_area_lights (pathtracer.cu:57-61).
 // ------------------------------------------------------------------------------------------------
+// Does `b` describe the same device resources and geometry as `a`?  Everything a slider tick of the canvas leaves
+// alone (densityScale, gradientFactor and the clip planes are what gui/canvas.h:49-175 edits between frames).
+static bool same_volume_resource(const svr_volume& a, const svr_volume& b)
+{
+    return a.tex == b.tex && memcmp(&a.bbox, &b.bbox, sizeof(a.bbox)) == 0 && memcmp(&a.spacing, &b.spacing, sizeof(a.spacing)) == 0 &&
+           a.invMaxMagnitude == b.invMaxMagnitude;
+}
+
 extern "C" void setup_volume(const svr_volume* vol)
 {
     HostState& st = state();
+    // The macrocell cache is keyed on the cudaArray handle.  A host that follows the reference's flow
+    // (VolumeReader::ClearDevice: cudaFreeArray + cudaDestroyTextureObject, then cudaMalloc3DArray for the next
+    // volume, core/VolumeReader.cpp:108-122, 138-172) never passes through svr_volume_destroy, and the driver is free
+    // to hand the new array and texture object the handle values of the freed ones.  So the handle alone proves
+    // nothing: any change of texture handle, box, spacing or gradient normalisation drops the cache (ranges,
+    // dims and the point-sampled view bound to the old array); and when the struct is unchanged in all of those a
+    // sampled fingerprint of the voxels is compared against the one taken when the ranges were built.
+    if (st.gridArray && !same_volume_resource(st.scene.vol, *vol)) release_grid(st);
     st.scene.vol = *vol;
     st.majorantValid = false;  // densityScale / array may have changed
+    st.fingerprintDue = true;  // checked at the next grid use (needs the stream; setup_* must stay cheap)
     if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
 }
 
@@ -138,6 +156,8 @@ extern "C" int svr_set_device(int device)
     cudaFree(st.dTfTable);
     cudaFree(st.dCounters);
     cudaFree(st.dStats);
+    cudaFree(st.dFingerprint);
+    st.dFingerprint = nullptr;
     st.dStats = nullptr;
     st.autoCell = 0;
     st.dTfSparse = nullptr;
@@ -309,22 +329,32 @@ extern "C" int svr_volume_create(svr_volume* out, const void* data, int data_on_
         return fail("cudaCreateTextureObject(volume)", e);
     }
 
+    // from here on every error path releases the array and the texture object
+    auto drop = [&](int rc) {
+        cudaDestroyTextureObject(tex);
+        cudaFreeArray(arr);
+        return rc;
+    };
     if (!(maxGradMag > 0.f)) {
         if (!data_on_device) {
             // stage once on the device for the reduction
             void* tmp = nullptr;
             size_t bytes = (size_t)nx * ny * nz * bpe;
-            SVR_TRY(cudaMalloc(&tmp, bytes));
-            cudaMemcpyAsync(tmp, data, bytes, cudaMemcpyHostToDevice, st.stream);
-            int rc = svr_max_gradient_magnitude(tmp, format, nx, ny, nz, sx, sy, sz, &maxGradMag);
+            e = cudaMalloc(&tmp, bytes);
+            if (e != cudaSuccess) return drop(fail("cudaMalloc(gradient staging)", e));
+            e = cudaMemcpyAsync(tmp, data, bytes, cudaMemcpyHostToDevice, st.stream);
+            int rc = e != cudaSuccess ? fail("cudaMemcpyAsync(gradient staging)", e)
+                                      : svr_max_gradient_magnitude(tmp, format, nx, ny, nz, sx, sy, sz, &maxGradMag);
             cudaFree(tmp);
-            if (rc) return rc;
+            if (rc) return drop(rc);
         } else {
             int rc = svr_max_gradient_magnitude(data, format, nx, ny, nz, sx, sy, sz, &maxGradMag);
-            if (rc) return rc;
+            if (rc) return drop(rc);
         }
         if (!(maxGradMag > 0.f)) maxGradMag = 1.f;
     }
+    e = cudaStreamSynchronize(st.stream);
+    if (e != cudaSuccess) return drop(fail("cudaStreamSynchronize(svr_volume_create)", e));
 
     memset(out, 0, sizeof(*out));
     float3 size = f3(nx * sx, ny * sy, nz * sz);
@@ -339,7 +369,6 @@ extern "C" int svr_volume_create(svr_volume* out, const void* data, int data_on_
     out->spacing = {sx, sy, sz};
     out->invSpacing = {1.f / sx, 1.f / sy, 1.f / sz};
     out->x_clip = out->y_clip = out->z_clip = {-1.f, 1.f};  // gui/canvas.cpp:31
-    SVR_TRY(cudaStreamSynchronize(st.stream));
     return 0;
 }
 

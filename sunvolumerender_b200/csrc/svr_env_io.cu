@@ -94,9 +94,14 @@ int decode(FILE* f, uint32_t w, uint32_t h, float* out)
 
 using namespace svr;
 
-extern "C" int svr_hdr_read(const char* path, float* rgb_out, uint32_t* w, uint32_t* h)
+// Largest accepted picture: 32768 per side and 2^27 pixels (2 GiB as float4), checked before anything is allocated.
+static const uint32_t kMaxSide = 32768u;
+static const uint64_t kMaxPixels = 1ull << 27;
+
+// One parse of the file: header, size checks, then the pixels into *rgbVec (resized here) or into the caller's
+// buffer, which was sized for wantW x wantH.
+static int read_hdr(const char* path, std::vector<float>* rgbVec, float* rgbExt, uint32_t wantW, uint32_t wantH, uint32_t* w, uint32_t* h)
 {
-    if (!path || !w || !h) return fail_msg("svr_hdr_read: bad argument");
     FILE* f = fopen(path, "rb");
     if (!f) return fail_msg((std::string("svr_hdr_read: unable to load environment map: ") + path).c_str());
     int rc = 0;
@@ -116,30 +121,65 @@ extern "C" int svr_hdr_read(const char* path, float* rgb_out, uint32_t* w, uint3
         unsigned hh = 0, ww = 0;
         if (!read_line(f, &line) || sscanf(line.c_str(), "-Y %u +X %u", &hh, &ww) != 2 || !hh || !ww)
             rc = fail_msg("svr_hdr_read: unsupported data layout (only -Y h +X w)");
+        else if (ww > kMaxSide || hh > kMaxSide || (uint64_t)ww * hh > kMaxPixels)
+            rc = fail_msg("svr_hdr_read: picture too large (at most 32768 per side and 2^27 pixels)");
         else {
+            // the pixel data must be able to hold the picture: a run-length scanline is at least 4 + 4 * 2 * ceil(w / 127)
+            // bytes, a flat one 4 * w
+            const long pos = ftell(f);
+            fseek(f, 0, SEEK_END);
+            const long end = ftell(f);
+            fseek(f, pos, SEEK_SET);
+            const uint64_t left = end > pos ? (uint64_t)(end - pos) : 0;
+            const uint64_t minLine = (ww < 8 || ww >= 32768) ? 4ull * ww : 4ull + 8ull * ((ww + 126u) / 127u);
+            if (left < minLine * hh) rc = fail_msg("svr_hdr_read: truncated pixel data (the file cannot hold the picture its header declares)");
+        }
+        if (!rc) {
             *w = ww;
             *h = hh;
-            if (rgb_out) rc = decode(f, ww, hh, rgb_out);
+            if (rgbVec) {
+                rgbVec->resize((size_t)ww * hh * 3);
+                rc = decode(f, ww, hh, rgbVec->data());
+            } else if (rgbExt) {
+                if (ww != wantW || hh != wantH) rc = fail_msg("svr_hdr_read: the picture's size differs from the size the buffer was made for");
+                else rc = decode(f, ww, hh, rgbExt);
+            }
         }
     }
     fclose(f);
     return rc;
 }
 
+// With rgb_out: *w and *h are in-out -- on entry the size the buffer was made for (from the sizing call), so a file
+// that changed in between is an error, not an overrun.
+extern "C" int svr_hdr_read(const char* path, float* rgb_out, uint32_t* w, uint32_t* h)
+{
+    if (!path || !w || !h) return fail_msg("svr_hdr_read: bad argument");
+    try {
+        const uint32_t wantW = *w, wantH = *h;
+        return read_hdr(path, nullptr, rgb_out, wantW, wantH, w, h);
+    } catch (...) {
+        return fail_msg("svr_hdr_read: out of host memory");
+    }
+}
+
 extern "C" int svr_env_load_hdr(const char* path, svr_env_light* out)
 {
-    if (!out) return fail_msg("svr_env_load_hdr: bad argument");
-    uint32_t w = 0, h = 0;
-    int rc = svr_hdr_read(path, nullptr, &w, &h);
-    if (rc) return rc;
-    std::vector<float> rgb((size_t)w * h * 3), rgba((size_t)w * h * 4);
-    rc = svr_hdr_read(path, rgb.data(), &w, &h);
-    if (rc) return rc;
-    for (size_t i = 0; i < (size_t)w * h; ++i) {  // lights.cpp:47-53
-        rgba[4 * i + 0] = rgb[3 * i + 0];
-        rgba[4 * i + 1] = rgb[3 * i + 1];
-        rgba[4 * i + 2] = rgb[3 * i + 2];
-        rgba[4 * i + 3] = 0.f;
+    if (!out || !path) return fail_msg("svr_env_load_hdr: bad argument");
+    try {
+        uint32_t w = 0, h = 0;
+        std::vector<float> rgb;
+        int rc = read_hdr(path, &rgb, nullptr, 0, 0, &w, &h);  // ONE parse: the buffer is sized from the header it decodes
+        if (rc) return rc;
+        std::vector<float> rgba((size_t)w * h * 4);
+        for (size_t i = 0; i < (size_t)w * h; ++i) {  // lights.cpp:47-53
+            rgba[4 * i + 0] = rgb[3 * i + 0];
+            rgba[4 * i + 1] = rgb[3 * i + 1];
+            rgba[4 * i + 2] = rgb[3 * i + 2];
+            rgba[4 * i + 3] = 0.f;
+        }
+        return svr_env_create(out, rgba.data(), w, h);
+    } catch (...) {
+        return fail_msg("svr_env_load_hdr: out of host memory");
     }
-    return svr_env_create(out, rgba.data(), w, h);
 }

@@ -274,6 +274,54 @@ __global__ void dist_axis_kernel(const uint8_t* __restrict__ src, uint8_t* __res
     }
 }
 
+// Sampled hash of the voxels: 8192 point fetches at hashed positions (plus nothing else: a full checksum would cost
+// what rebuilding the ranges costs).  Detects that the array behind an unchanged handle holds another volume.
+__global__ void fingerprint_kernel(cudaTextureObject_t pointTex, int3 vol, unsigned long long* out)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t h = tid * 0x9E3779B1u + 0x7F4A7C15u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    const uint32_t x = h % (uint32_t)vol.x;
+    h = h * 0x297A2D39u + 1u;
+    h ^= h >> 15;
+    const uint32_t y = h % (uint32_t)vol.y;
+    h = h * 0x85EBCA6Bu + 1u;
+    h ^= h >> 13;
+    const uint32_t z = h % (uint32_t)vol.z;
+    const float v = tex3D<float>(pointTex, (float)x + 0.5f, (float)y + 0.5f, (float)z + 0.5f);
+    unsigned long long c = ((unsigned long long)__float_as_uint(v) + 1ull) * ((unsigned long long)tid * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, c);
+}
+
+int launch_fingerprint(HostState& st, int slot)
+{
+    if (!st.dFingerprint) SVR_TRY(cudaMalloc(&st.dFingerprint, 2 * sizeof(unsigned long long)));
+    SVR_TRY(cudaMemsetAsync(st.dFingerprint + slot, 0, sizeof(unsigned long long), st.stream));
+    fingerprint_kernel<<<64, 128, 0, st.stream>>>(st.volPointTex, st.volDims, st.dFingerprint + slot);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+int create_point_view(HostState& st, const cudaResourceDesc& vrd, const cudaChannelFormatDesc& ch)
+{
+    if (st.volPointTex) cudaDestroyTextureObject(st.volPointTex);
+    st.volPointTex = 0;
+    cudaGetLastError();  // destroying a view whose array the host has freed may report an error: the view is gone either way
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = (ch.f == cudaChannelFormatKindFloat) ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 0;
+    SVR_TRY(cudaCreateTextureObject(&st.volPointTex, &vrd, &td, nullptr));
+    return 0;
+}
+
 }  // namespace
 
 void release_grid(HostState& st)
@@ -290,6 +338,7 @@ void release_grid(HostState& st)
     st.dDist[0] = st.dDist[1] = nullptr;
     st.dOcc = nullptr;
     st.gridArray = nullptr;
+    st.autoArray = nullptr;  // the automatic cell size is re-derived for whatever volume comes next
     st.rangeValid = false;
     st.majorantValid = false;
 }
@@ -332,22 +381,37 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
     cudaArray_t varr = vrd.res.array.array, tarr = trd.res.array.array;
 
     if (majorantsRebuilt) *majorantsRebuilt = false;
+    cudaChannelFormatDesc ch;
+    cudaExtent ext;
+    unsigned int flags = 0;
+    SVR_TRY(cudaArrayGetInfo(&ch, &ext, &flags, varr));
+    if (ext.depth == 0) return fail_msg("ensure_grid: volume array is not 3-D");
+    if (varr == st.gridArray && st.dRange && st.fingerprintDue) {
+        // setup_volume was called since the voxels were last looked at, with a struct that names the same resources
+        // (svr_api.cu: setup_volume).  The array behind the handle may still be another one (freed and reallocated by
+        // the host): compare its dims, take a fresh point-sampled view of it, and compare a sampled hash of its voxels
+        // with the one taken when the ranges were built.
+        if ((int)ext.width != st.volDims.x || (int)ext.height != st.volDims.y || (int)ext.depth != st.volDims.z) {
+            release_grid(st);
+        } else {
+            int rc = create_point_view(st, vrd, ch);
+            if (rc) return rc;
+            if (st.rangeValid) {
+                rc = launch_fingerprint(st, 1);
+                if (rc) return rc;
+                unsigned long long h[2] = {0, 1};
+                SVR_TRY(cudaMemcpyAsync(h, st.dFingerprint, sizeof(h), cudaMemcpyDeviceToHost, st.stream));
+                SVR_TRY(cudaStreamSynchronize(st.stream));
+                if (h[0] != h[1]) st.rangeValid = false;
+            }
+        }
+    }
+    st.fingerprintDue = false;
     if (varr != st.gridArray || cell != st.gridCell || !st.dRange) {
         // ---- allocate for this (array, cell size)
-        cudaChannelFormatDesc ch;
-        cudaExtent ext;
-        unsigned int flags = 0;
-        SVR_TRY(cudaArrayGetInfo(&ch, &ext, &flags, varr));
-        if (ext.depth == 0) return fail_msg("ensure_grid: volume array is not 3-D");
         release_grid(st);
-
-        cudaTextureDesc td;
-        memset(&td, 0, sizeof(td));
-        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
-        td.filterMode = cudaFilterModePoint;
-        td.readMode = (ch.f == cudaChannelFormatKindFloat) ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
-        td.normalizedCoords = 0;
-        SVR_TRY(cudaCreateTextureObject(&st.volPointTex, &vrd, &td, nullptr));
+        int rcv = create_point_view(st, vrd, ch);
+        if (rcv) return rcv;
 
         st.volDims = make_int3((int)ext.width, (int)ext.height, (int)ext.depth);
         st.gridDims = make_int3((st.volDims.x + cell - 1) / cell, (st.volDims.y + cell - 1) / cell,
@@ -376,6 +440,8 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
         }
         st.rangeValid = true;
         st.majorantValid = false;
+        int rc = launch_fingerprint(st, 0);  // of the voxels these ranges describe (stays on the device until it is needed)
+        if (rc) return rc;
     }
 
     const int leap = st.options[SVR_OPT_LEAP] != 0;

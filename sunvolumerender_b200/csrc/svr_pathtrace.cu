@@ -59,6 +59,7 @@ struct PtLaunch {
     int32_t marchBurst;    // phase-scheduled kernel: macrocell visits per MARCH round
     int32_t entryCache;    // 1 = per-pixel camera-ray entry cache (mode 2)
     int32_t warpPixels;    // sample-parallel kernel: pixels one warp renders one after the other
+    int32_t lightCull;     // 1 = classify_pixel may rule out camera-ray light hits (SVR_OPT_PT_LIGHT_CULL)
 };
 
 template <int MODE>
@@ -260,7 +261,7 @@ struct PixelInfo {
     bool lights, empty;
 };
 
-SVR_DEV PixelInfo classify_pixel(const DevScene& s, uint32_t idx, uint32_t idy, bool haveGrid, bool walk)
+SVR_DEV PixelInfo classify_pixel(const DevScene& s, uint32_t idx, uint32_t idy, bool haveGrid, bool walk, bool lightCull)
 {
     PixelInfo pi;
     pi.tSkip = 0.f;
@@ -282,7 +283,7 @@ SVR_DEV PixelInfo classify_pixel(const DevScene& s, uint32_t idx, uint32_t idy, 
     const float alpha = sqrtf(hx * hx + hy * hy) * 1.05f;
 
     // ---- lights: a ray hits a disk only if it passes within `radius` of the centre, in front of the origin
-    bool lights = false;
+    bool lights = !lightCull && s.numLights != 0;
     for (uint32_t i = 0; i < s.numLights; ++i) {
         const float3 v = f3(s.lights[i].disk.center) - ray.orig;
         const float dist = sqrtf(dot(v, v)), along = dot(v, ray.dir);
@@ -656,7 +657,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     LocalCounters<COUNT> lc;
     if (inside) {
         const uint32_t offset = idy * s.cam.imageW + idx;
-        const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
+        const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0, a.lightCull != 0);
         PathState<MODE> ps;
         pixel_begin<MODE>(ps);
         for (uint32_t n = 0; n < a.nSamples; ++n) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
-            const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
+            const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0, a.lightCull != 0);
             pixel_begin<MODE>(ps);
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
                 // every sample of this pixel is the constant sky (see trace_sample): the same additions, nothing else
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
 // The image equals shape 2 up to float summation order (the lanes add into per-lane partial sums).
 // ---------------------------------------------------------------------------------------------
 constexpr int SVR_QUEUE_CAP = 64;    // entries per warp: a round pushes at most 32 onto fewer than 32
-constexpr int SVR_QUEUE_WORDS = 14;  // orig 3, dir 3, t, T 3, k, c0, r1, have
+constexpr int SVR_QUEUE_WORDS = 14;  // orig 3, dir 3, t, T 3, k | have << 31, c0, c1, r1
 
 template <bool COUNT>
 SVR_DEV void queue_push(float* q, int idx, const PathState<2>& ps, float t)
@@ -744,10 +745,10 @@ SVR_DEV void queue_push(float* q, int idx, const PathState<2>& ps, float t)
     q[7 * SVR_QUEUE_CAP + idx] = ps.T.x;
     q[8 * SVR_QUEUE_CAP + idx] = ps.T.y;
     q[9 * SVR_QUEUE_CAP + idx] = ps.T.z;
-    q[10 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.k);
+    q[10 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.k | (ps.rng.have << 31));  // k <= traceDepth < 2^31
     q[11 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.rng.c0);
-    q[12 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.rng.r1);
-    q[13 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.rng.have);
+    q[12 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.rng.c1);
+    q[13 * SVR_QUEUE_CAP + idx] = __uint_as_float(ps.rng.r1);
 }
 
 SVR_DEV float queue_pop(const float* q, int idx, PathState<2>& ps)
@@ -755,10 +756,12 @@ SVR_DEV float queue_pop(const float* q, int idx, PathState<2>& ps)
     ps.ray.orig = f3(q[0 * SVR_QUEUE_CAP + idx], q[1 * SVR_QUEUE_CAP + idx], q[2 * SVR_QUEUE_CAP + idx]);
     ps.ray.dir = f3(q[3 * SVR_QUEUE_CAP + idx], q[4 * SVR_QUEUE_CAP + idx], q[5 * SVR_QUEUE_CAP + idx]);
     ps.T = f3(q[7 * SVR_QUEUE_CAP + idx], q[8 * SVR_QUEUE_CAP + idx], q[9 * SVR_QUEUE_CAP + idx]);
-    ps.k = __float_as_uint(q[10 * SVR_QUEUE_CAP + idx]);
+    const uint32_t kh = __float_as_uint(q[10 * SVR_QUEUE_CAP + idx]);
+    ps.k = kh & 0x7fffffffu;
+    ps.rng.have = kh >> 31;
     ps.rng.c0 = __float_as_uint(q[11 * SVR_QUEUE_CAP + idx]);
-    ps.rng.r1 = __float_as_uint(q[12 * SVR_QUEUE_CAP + idx]);
-    ps.rng.have = __float_as_uint(q[13 * SVR_QUEUE_CAP + idx]);
+    ps.rng.c1 = __float_as_uint(q[12 * SVR_QUEUE_CAP + idx]);
+    ps.rng.r1 = __float_as_uint(q[13 * SVR_QUEUE_CAP + idx]);
     ps.shadow = false;
     return q[6 * SVR_QUEUE_CAP + idx];
 }
@@ -780,7 +783,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS + 1) pat
             const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
-            const PixelInfo pi = classify_pixel(s, idx, idy, true, a.entryCache != 0);
+            const PixelInfo pi = classify_pixel(s, idx, idy, true, a.entryCache != 0, a.lightCull != 0);
             pixel_begin<MODE>(ps);
             ps.camLights = pi.lights;
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
@@ -805,7 +808,6 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS + 1) pat
                         queued -= take;
                         active = (int)lane < take;
                         if (active) {
-                            ps.rng.c1 = offset * 0x9E3779B1u + s.seedKey;  // Philox::init's pixel word
                             t = queue_pop(q, queued + (int)lane, ps);
                             next = NEXT_EVENT_AT_T;
                             own = true;
@@ -840,6 +842,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS + 1) pat
                     const unsigned m = __ballot_sync(0xffffffffu, push);
                     if (push) queue_push<COUNT>(q, queued + __popc(m & ((1u << lane) - 1u)), ps, t);
                     queued += __popc(m);
+                    __syncwarp();  // this round's pushes precede the next round's pops (other lanes read them)
                 }
             }
             float3 sum = ps.L;
@@ -880,7 +883,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     pi.tSkip = 0.f;
     pi.lights = true;
     pi.empty = false;
-    if (inside) pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0);
+    if (inside) pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0, a.lightCull != 0);
     ps.camLights = pi.lights;
     const float tSkip = pi.tSkip;
 
@@ -1028,6 +1031,7 @@ int launch_pathtrace(PtLaunch a)
     if (a.y0 >= a.y1 || a.nSamples == 0) return 0;
     a.marchBurst = st.options[SVR_OPT_PT_ROUNDS] > 0 ? st.options[SVR_OPT_PT_ROUNDS] : 4;
     a.entryCache = st.options[SVR_OPT_PT_ENTRY_CACHE] && a.nSamples >= 2;
+    a.lightCull = st.options[SVR_OPT_PT_LIGHT_CULL];
     Counters* cnt = nullptr;
     if (st.options[SVR_OPT_COUNTERS]) {
         cnt = device_counters();

@@ -60,8 +60,8 @@ struct XorwowCompat {
 };
 
 struct Philox {
-    uint32_t c0;   // low counter word: sample index in the high 18 bits, draw-block number in the low 14
-    uint32_t c1;   // high counter word: pixel and seed
+    uint32_t c0;   // low counter word: low 18 bits of the sample index in the high 18 bits, draw-block number in the low 14
+    uint32_t c1;   // high counter word: pixel, seed and the sample index's bits 18..31
     uint32_t r1;   // second word of the current block
     uint32_t have; // 1 = r1 not yet consumed
 
@@ -74,9 +74,12 @@ struct Philox {
     // lives in the COUNTER and the key is a compile-time constant, so the ten round keys are immediates
     // instead of ten registers.  A path that draws more than 2^14 blocks runs on into the counter range
     // of the next sample index -- still deterministic, and far beyond what a path consumes.
+    // Sample indices are 32 bits wide (frameNo of a progressive render, first_sample + rank * spp of a split): the low
+    // 18 bits sit in c0, bits 18..31 are folded into c1 -- zero for the first 262144 samples, so those streams are what
+    // they always were, and later samples get streams of their own instead of replaying sample mod 2^18.
     SVR_DEV void init(uint32_t seedKey, uint32_t pixel, uint32_t sample_)
     {
-        c1 = pixel * 0x9E3779B1u + seedKey;  // bijective in pixel for a fixed seed
+        c1 = (pixel * 0x9E3779B1u + seedKey) ^ ((sample_ >> (32 - BLOCK_BITS)) * 0x85EBCA6Bu);  // bijective in pixel for a fixed seed and epoch
         c0 = sample_ << BLOCK_BITS;
         have = 0;
         r1 = 0;

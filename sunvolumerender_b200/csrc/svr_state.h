@@ -36,6 +36,8 @@ struct HostState {
     int tfEntries = 0;
     cudaTextureObject_t volPointTex = 0;  // point-sampled view of gridArray
     bool rangeValid = false;              // false until the range grid reflects the array's current voxels
+    bool fingerprintDue = false;          // setup_volume was called since the voxels were last looked at
+    unsigned long long* dFingerprint = nullptr;  // [0] sampled hash of the voxels the ranges were built from, [1] scratch
     bool majorantValid = false;           // false after setup_volume/setup_transferfunction
     float majorantDensityScale = 0.f;
     cudaArray_t majorantTfArray = nullptr;

@@ -185,9 +185,22 @@ struct DevBuf {
 
 using namespace svr;
 
+static int read_header(const char* path, svr_metaimage_header* out);
+
 extern "C" int svr_metaimage_read_header(const char* path, svr_metaimage_header* out)
 {
     if (!path || !out) return fail_msg("svr_metaimage_read_header: bad argument");
+    try {
+        return read_header(path, out);
+    } catch (const std::bad_alloc&) {
+        return fail_msg("svr_metaimage_read_header: out of host memory");
+    } catch (...) {
+        return fail_msg("svr_metaimage_read_header: unexpected exception");
+    }
+}
+
+static int read_header(const char* path, svr_metaimage_header* out)
+{
     std::ifstream f(path, std::ios::binary);
     if (!f) return fail_msg((std::string("svr_metaimage_read_header: cannot open ") + path).c_str());
     memset(out, 0, sizeof(*out));
@@ -241,8 +254,12 @@ extern "C" int svr_metaimage_read_header(const char* path, svr_metaimage_header*
         // ObjectType, TransformMatrix, Offset, CenterOfRotation, AnatomicalOrientation, ...: not needed
     }
     if (!haveDim || !haveDataFile || out->element_type < 0) return fail_msg("svr_metaimage_read_header: DimSize, ElementType and ElementDataFile are required");
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) {
         if (out->dim[i] == 0 || !(out->spacing[i] > 0.f)) return fail_msg("svr_metaimage_read_header: zero dimension or non-positive spacing");
+        // the voxels end in a 3-D cudaArray (VolumeReader.cpp:144-150): 16384 texels per axis at most on every CUDA device,
+        // which also keeps every size below (2^14)^3 * 8 = 2^45 bytes -- no size_t arithmetic can wrap
+        if (out->dim[i] > SVR_MAX_VOLUME_DIM) return fail_msg("svr_metaimage_read_header: DimSize exceeds the 3-D texture limit (16384 per axis)");
+    }
     if (lower(dataFile) == "local") {
         out->data_offset = (uint64_t)f.tellg();
         out->data_file[0] = 0;
@@ -268,6 +285,8 @@ extern "C" int svr_volume_from_raw(const void* host_data, int met_type, int msb,
     const size_t es = met_size(met_type);
     if (!host_data || !out || !es || !nx || !ny || !nz || !(sx > 0.f) || !(sy > 0.f) || !(sz > 0.f))
         return fail_msg("svr_volume_from_raw: bad argument");
+    if (nx > SVR_MAX_VOLUME_DIM || ny > SVR_MAX_VOLUME_DIM || nz > SVR_MAX_VOLUME_DIM)
+        return fail_msg("svr_volume_from_raw: dimension exceeds the 3-D texture limit (16384 per axis)");
     HostState& st = state();
     const size_t n = (size_t)nx * ny * nz;
     DevBuf raw, data, aux, hist;
@@ -335,8 +354,22 @@ extern "C" int svr_volume_from_raw(const void* host_data, int met_type, int msb,
     return 0;
 }
 
+static int load_metaimage(const char* path, svr_volume* out, svr_volume_stats* stats, uint32_t* histogram, uint32_t histogram_capacity);
+
+// An exception must not cross the C boundary (a host whose memory is exhausted gets an error code, not std::terminate).
 extern "C" int svr_volume_load_metaimage(const char* path, svr_volume* out, svr_volume_stats* stats, uint32_t* histogram,
                                          uint32_t histogram_capacity)
+{
+    try {
+        return load_metaimage(path, out, stats, histogram, histogram_capacity);
+    } catch (const std::bad_alloc&) {
+        return fail_msg("svr_volume_load_metaimage: out of host memory");
+    } catch (...) {
+        return fail_msg("svr_volume_load_metaimage: unexpected exception");
+    }
+}
+
+static int load_metaimage(const char* path, svr_volume* out, svr_volume_stats* stats, uint32_t* histogram, uint32_t histogram_capacity)
 {
     svr_metaimage_header hd;
     int rc = svr_metaimage_read_header(path, &hd);
@@ -353,9 +386,13 @@ extern "C" int svr_volume_load_metaimage(const char* path, svr_volume* out, svr_
         else if (hd.header_size == -1 && !hd.compressed) start = fileSize >= bytes ? fileSize - bytes : 0;
     }
     std::vector<unsigned char> buf;
+    if (start > fileSize) return fail_msg("svr_volume_load_metaimage: HeaderSize lies beyond the end of the data file");
     if (hd.compressed) {
-        uint64_t csize = hd.compressed_size ? hd.compressed_size : (fileSize > start ? fileSize - start : 0);
-        if (start + csize > fileSize) return fail_msg("svr_volume_load_metaimage: compressed data is truncated");
+        uint64_t csize = hd.compressed_size ? hd.compressed_size : fileSize - start;
+        if (csize > fileSize - start) return fail_msg("svr_volume_load_metaimage: compressed data is truncated");
+        // zlib's deflate cannot shrink data by more than about 1032 : 1: a header that promises more than the
+        // compressed bytes can hold is rejected before anything of that size is allocated
+        if (bytes / 1100 > csize + 64) return fail_msg("svr_volume_load_metaimage: DimSize x ElementType cannot come out of the compressed data");
         std::vector<unsigned char> cbuf(csize);
         f.seekg((std::streamoff)start);
         f.read((char*)cbuf.data(), (std::streamsize)csize);
@@ -364,7 +401,7 @@ extern "C" int svr_volume_load_metaimage(const char* path, svr_volume* out, svr_
         int z = uncompress(buf.data(), &dlen, cbuf.data(), (uLong)csize);
         if (z != Z_OK || dlen != bytes) return fail_msg("svr_volume_load_metaimage: zlib inflate failed or size mismatch");
     } else {
-        if (start + bytes > fileSize) return fail_msg("svr_volume_load_metaimage: data file is shorter than DimSize x ElementType");
+        if (bytes > fileSize - start) return fail_msg("svr_volume_load_metaimage: data file is shorter than DimSize x ElementType");
         buf.resize(bytes);
         f.seekg((std::streamoff)start);
         f.read((char*)buf.data(), (std::streamsize)bytes);

@@ -25,6 +25,7 @@ def setup(r, cfg):
     r.set_option(L.OPT_RC_SKIP, 1)
     r.set_option(L.OPT_LEAP, 1)
     r.set_option(L.OPT_PT_ENTRY_CACHE, 1)
+    r.set_option(L.OPT_PT_LIGHT_CULL, 1)
     r.set_option(L.OPT_MACROCELL_SIZE, 8)
     r.set_option(L.OPT_COUNTERS, 0)
     r.set_option(L.OPT_SEED, 0x5EED)

@@ -462,6 +462,55 @@ def test_config_c3_full_size_properties(renderer):
     _statistical_parity(renderer, cfg, 1, 8, 32, lambda: None)
 
 
+def test_config_c3_as_benched_with_environment_light_full_size(renderer):
+    """C3 exactly as bench.py renders it -- area light + constant environment light -- at full size against the
+    environment-light twin of the reference (its own sources with the line commented out at pathtracer.cu:233
+    re-enabled, oracle/Makefile): path for path in the twin mode, statistically in the product mode."""
+    cfg = S.CONFIGS["C3"]
+    setup(renderer, cfg)
+    assert cfg.env and renderer.get_option(L.OPT_ENV_ENABLED) == 1
+    renderer.set_option(L.OPT_PT_MODE, 0)
+    ref = reference(renderer, cfg, env=True)
+    mine = _frames(renderer, 2, 1)
+    ref.render_pathtracer(2, 1)
+    theirs = ref.hdr_image().cpu().numpy()
+    assert theirs.min() >= 0 and theirs[0, 0, 0] == pytest.approx(0.5)   # the corner sees the constant sky
+    d = np.abs(mine - theirs).max(axis=2)
+    assert (d <= 1e-4).mean() >= 0.9999, (d.max(), (d <= 1e-4).mean())
+    assert abs(mine.mean() - theirs.mean()) <= 1e-4 * theirs.mean()
+    del ref
+    renderer.set_option(L.OPT_PT_MODE, 2)
+    _statistical_parity(renderer, cfg, 1, 8, 32, lambda: None, env=True)
+
+
+def test_config_c1_path_trace_16spp_full_size(renderer):
+    """C1 (BASELINE.json configs[0]): 128^3 u8 sphere, 512x512, the 16-spp path trace with one area light, at full
+    size: the twin mode path for path against the reference's kernel, the product mode statistically."""
+    cfg = S.CONFIGS["C1"]
+    setup(renderer, cfg)
+    renderer.set_option(L.OPT_PT_MODE, 0)
+    ref = reference(renderer, cfg)
+    mine = _frames(renderer, cfg.spp, cfg.trace_depth)
+    ref.render_pathtracer(cfg.spp, cfg.trace_depth)
+    theirs = ref.hdr_image().cpu().numpy()
+    assert theirs.max() > 0
+    d = np.abs(mine - theirs).max(axis=2)
+    assert (d <= 1e-4).mean() >= 0.9999, (d.max(), (d <= 1e-4).mean())
+    assert abs(mine.mean() - theirs.mean()) <= 1e-4 * theirs.mean()
+    assert np.abs(renderer.ldr_image().cpu().numpy().astype(int) - ref.ldr_image().cpu().numpy().astype(int)).max() <= 1
+    # one 16-sample batch == 16 frames (sample-parallel shape forced: 16 < the default minimum batch)
+    renderer.set_option(L.OPT_PT_WARP_MIN_SPP, 1)
+    renderer.frame_no = 0
+    renderer.render_pathtracer_spp(cfg.spp, cfg.trace_depth)
+    torch.cuda.synchronize()
+    batched = renderer.hdr_image().cpu().numpy()
+    assert (np.abs(batched - theirs).max(axis=2) <= 1e-4).mean() >= 0.9999
+    del ref
+    renderer.set_option(L.OPT_PT_MODE, 2)
+    renderer.set_option(L.OPT_PT_WARP_MIN_SPP, 32)
+    _statistical_parity(renderer, cfg, cfg.trace_depth, 8, 16, lambda: None)
+
+
 def test_config_c4_full_size_statistics(renderer):
     """C4: 1024^3 f16 high-albedo cloud, multiple scattering (traceDepth 32), 1920x1080 -- the regime
     where paths are long, the volume (2 GiB) misses L2 and the macrocell majorants matter most."""

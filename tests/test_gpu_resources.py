@@ -305,3 +305,62 @@ def test_application_default_transfer_function_renders_like_the_reference(render
     torch.cuda.synchronize()
     d = np.abs(renderer.hdr_image().cpu().numpy() - ref2.hdr_image().cpu().numpy()).max(axis=2)
     assert (d <= 1e-4).mean() >= 0.999
+
+
+def _cudart():
+    import glob
+    import os
+
+    cands = glob.glob(os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64", "libcudart.so*"))
+    rt = C.CDLL(sorted(cands)[-1])
+    rt.cudaGetTextureObjectResourceDesc.argtypes = [C.c_void_p, C.c_uint64]
+    rt.cudaDestroyTextureObject.argtypes = [C.c_uint64]
+    rt.cudaFreeArray.argtypes = [C.c_void_p]
+    return rt
+
+
+def test_host_that_frees_and_reallocates_the_array_itself_gets_fresh_macrocells(renderer):
+    """A host following the reference's own flow (VolumeReader::ClearDevice: cudaDestroyTextureObject + cudaFreeArray,
+    then cudaMalloc3DArray for the next volume; core/VolumeReader.cpp:108-122, 138-172) never calls svr_volume_destroy,
+    and the new array may get the freed one's handle.  The macrocell cache must not survive that: same dims, same box,
+    same gradient normalisation, other voxels -> the image is the one a cold library renders."""
+    rt = _cudart()
+    cfg = small_config(n=64, w=96, h=96, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=2)
+    setup(renderer, cfg)
+    r = renderer
+    n = cfg.n
+
+    def render():
+        r.set_option(L.OPT_PT_MODE, 2)
+        r.frame_no = 0
+        r.render_pathtracer_spp(33, 2)
+        torch.cuda.synchronize()
+        return r.hdr_image().clone(), raycast_f32(r).clone()
+
+    vox_a = r.generate_volume(L.GEN_CT, L.VOXEL_U16, n, 1234)
+    # volume B: the body moved and thinned, air where A had tissue and the other way round
+    host_b = np.roll(vox_a.cpu().numpy().view(np.uint16).reshape(n, n, n), (9, -7, 5), axis=(0, 1, 2)).copy()
+    host_b[:, : n // 3] = 0
+    reused = 0
+    for attempt in range(3):
+        r.load_volume(vox_a, cfg.fmt, (n,) * 3, max_grad_mag=1000.0)
+        img_a, rc_a = render()   # builds ranges / majorants for A
+        old = (int(r.volume.tex), None)
+        # the host tears the resources down behind the library's back, as VolumeReader::ClearDevice does
+        desc = (C.c_uint64 * 8)()
+        assert rt.cudaGetTextureObjectResourceDesc(desc, r.volume.tex) == 0
+        arr = desc[1]
+        torch.cuda.synchronize()
+        assert rt.cudaDestroyTextureObject(r.volume.tex) == 0
+        assert rt.cudaFreeArray(C.c_void_p(arr)) == 0
+        r.volume = None  # nothing for Renderer.free_volume to destroy
+        r.load_volume(host_b, cfg.fmt, (n,) * 3, max_grad_mag=1000.0)   # cudaMalloc3DArray + setup_volume
+        assert rt.cudaGetTextureObjectResourceDesc(desc, r.volume.tex) == 0
+        reused += int(desc[1] == arr and int(r.volume.tex) == old[0])
+        img_b, rc_b = render()
+        # ground truth: the same volume with the cache dropped explicitly
+        L.check(r.lib.svr_volume_invalidate_cache())
+        img_b_cold, rc_b_cold = render()
+        assert torch.equal(img_b, img_b_cold) and torch.equal(rc_b, rc_b_cold), f"stale macrocells (attempt {attempt}, handles reused: {reused})"
+        assert not torch.equal(img_b, img_a)
+    print("array + texture handles reused in", reused, "of 3 attempts")

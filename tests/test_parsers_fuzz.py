@@ -68,3 +68,53 @@ def test_hdr_reader_survives_garbage(tmp_path):
             buf = (C.c_float * (3 * w.value * h.value))()
             lib.svr_hdr_read(str(p).encode(), buf, C.byref(w), C.byref(h))  # truncated pixel data: an error, not a crash
     assert os.path.exists(p)
+
+
+def test_headers_that_promise_absurd_sizes_are_errors_not_aborts(tmp_path):
+    """DimSize 200000^3 with CompressedData, dims whose product wraps size_t, and a .hdr of 3e6 x 3e6 used to
+    end in std::bad_alloc -> std::terminate across the C boundary.  Each is an error code now, before any allocation."""
+    lib = L.load()
+    cases = {
+        "huge_compressed": b"ObjectType = Image\nNDims = 3\nDimSize = 200000 200000 200000\nElementType = MET_UCHAR\nCompressedData = True\nElementDataFile = LOCAL\n" + b"x" * 64,
+        "wraps_size_t": b"NDims = 3\nDimSize = 4194304 2097152 2097152\nElementType = MET_USHORT\nElementDataFile = LOCAL\n" + b"x" * 64,
+        "max_dims_tiny_zlib": b"NDims = 3\nDimSize = 16384 16384 16384\nElementType = MET_DOUBLE\nCompressedData = True\nElementDataFile = LOCAL\n" + b"x" * 64,
+        "max_dims_raw": b"NDims = 3\nDimSize = 16384 16384 16384\nElementType = MET_DOUBLE\nElementDataFile = LOCAL\n" + b"x" * 64,
+        "negative_dim": b"NDims = 3\nDimSize = -4 8 8\nElementType = MET_UCHAR\nElementDataFile = LOCAL\n" + b"x" * 600,
+        "header_size_beyond_file": b"NDims = 3\nDimSize = 2 2 2\nElementType = MET_UCHAR\nHeaderSize = 99999999\nElementDataFile = d.raw\n",
+    }
+    (tmp_path / "d.raw").write_bytes(b"12345678")
+    vol, stats = L.Volume(), L.VolumeStats()
+    for name, blob in cases.items():
+        p = tmp_path / (name + ".mha")
+        p.write_bytes(blob)
+        rc = lib.svr_volume_load_metaimage(str(p).encode(), C.byref(vol), C.byref(stats), None, 0)
+        assert rc != 0, name
+        assert lib.svr_last_error(), name
+    for dims in (b"-Y 3000000 +X 3000000", b"-Y 32768 +X 32768", b"-Y 20000 +X 20000", b"-Y 4096 +X 4096"):
+        p = tmp_path / "big.hdr"
+        p.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n" + dims + b"\n" + b"\x02\x02\x10\x00" * 8)
+        w, h = C.c_uint32(0), C.c_uint32(0)
+        assert lib.svr_hdr_read(str(p).encode(), None, C.byref(w), C.byref(h)) != 0
+        env = L.EnvLight()
+        assert lib.svr_env_load_hdr(str(p).encode(), C.byref(env)) != 0   # fails before it touches the GPU
+
+
+def test_hdr_buffer_sized_for_another_picture_is_an_error(tmp_path):
+    """svr_hdr_read's second call decodes into a caller buffer: *w, *h are in-out, so a file that changed between the
+    sizing call and the decoding call cannot overrun the buffer."""
+    lib = L.load()
+    p = tmp_path / "a.hdr"
+
+    def flat(w, h):
+        return b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w) + bytes([10, 20, 30, 128]) * (w * h)
+
+    p.write_bytes(flat(4, 4))
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    assert lib.svr_hdr_read(str(p).encode(), None, C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (4, 4)
+    buf = (C.c_float * (3 * 16))()
+    p.write_bytes(flat(6, 6))   # the file grows behind the caller's back
+    assert lib.svr_hdr_read(str(p).encode(), buf, C.byref(w), C.byref(h)) != 0
+    p.write_bytes(flat(4, 4))
+    w, h = C.c_uint32(4), C.c_uint32(4)
+    assert lib.svr_hdr_read(str(p).encode(), buf, C.byref(w), C.byref(h)) == 0
+    assert buf[0] == 10 * 2.0 ** (128 - 136)
