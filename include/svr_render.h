@@ -90,7 +90,7 @@ enum svr_option {
      * the same pixel), 1 = megakernel (one pixel per lane, samples one after the other),
      * 0 = phase-scheduled warp (generate / march / collide / event / bounce phases, the warp
      * votes each round and runs the phase most lanes wait in), 3 = sample-parallel warp with the scatter
-     * queue at every depth (see SVR_OPT_PT_QUEUE_MIN_DEPTH) */
+     * queue at every depth (see SVR_OPT_PT_QUEUE_MIN_DEPTH), 4 = majorant-profile kernel (see SVR_OPT_PT_PROFILE) */
     SVR_OPT_PT_KERNEL = 9,
     /* phase-scheduled kernel: macrocell visits per MARCH round (0 = default 4) */
     SVR_OPT_PT_ROUNDS = 10,
@@ -120,6 +120,14 @@ enum svr_option {
      * (pathtracer.cu:214-215); 0 = every camera ray tests every disk, as the reference does.  Images are
      * bit-identical either way (the cull is conservative). */
     SVR_OPT_PT_LIGHT_CULL = 17,
+    /* 1 = with local majorants and a pinhole camera the sample-parallel shapes track camera rays against a per-pixel
+     * majorant PROFILE the warp builds once per pixel (kernel shape 4: no lane walks a camera ray, every tentative
+     * collision of a camera ray runs with the lanes packed; scatter queue as shape 3).  Same estimator, other random
+     * walks: images agree with shapes 1-3 statistically.  0 (default) = shapes 2 / 3 as selected: the profile kernel
+     * executes fewer cell visits but measured slower on every BASELINE configuration. */
+    SVR_OPT_PT_PROFILE = 18,
+    /* shape 4: idle lanes take the pixel's next camera samples together once this many lanes wait (1..32, 0 = default 8) */
+    SVR_OPT_PT_REFILL = 19,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

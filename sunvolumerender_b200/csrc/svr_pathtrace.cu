@@ -41,6 +41,13 @@
 #ifndef SVR_PT_MAX_THREADS
 #define SVR_PT_MAX_THREADS 128
 #endif
+// the majorant-profile kernel (shape 4) and the scatter-queue kernel (shape 3) have budgets of their own
+#ifndef SVR_PT_PROFILE_BLOCKS
+#define SVR_PT_PROFILE_BLOCKS 7
+#endif
+#ifndef SVR_PT_QUEUE_BLOCKS
+#define SVR_PT_QUEUE_BLOCKS (SVR_PT_MIN_BLOCKS + 1)
+#endif
 
 namespace svr {
 Counters* device_counters();
@@ -60,6 +67,7 @@ struct PtLaunch {
     int32_t entryCache;    // 1 = per-pixel camera-ray entry cache (mode 2)
     int32_t warpPixels;    // sample-parallel kernel: pixels one warp renders one after the other
     int32_t lightCull;     // 1 = classify_pixel may rule out camera-ray light hits (SVR_OPT_PT_LIGHT_CULL)
+    int32_t clipped;       // some clip plane is active: the volume's box is smaller than its texture
 };
 
 template <int MODE>
@@ -769,7 +777,7 @@ SVR_DEV float queue_pop(const float* q, int idx, PathState<2>& ps)
 // One more block per SM than the other shapes (64 registers, some spills): this kernel serves incoherent deep
 // paths in volumes that miss the caches, where more warps in flight pay (C4: 130 -> 125 ms per 128 spp).
 template <bool COUNT>
-__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS + 1) pathtrace_queue_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_QUEUE_BLOCKS) pathtrace_queue_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
     constexpr int MODE = 2;
     __shared__ float queues[SVR_PT_MAX_THREADS / 32][SVR_QUEUE_WORDS * SVR_QUEUE_CAP];
@@ -852,6 +860,439 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS + 1) pat
                 sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
                 sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
                 sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+            }
+            if (lane == 0) write_pixel(s, a, offset, sum);
+        }
+    }
+    lc.flush(cnt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel shape 4: sample-parallel warp, camera rays tracked against a per-pixel MAJORANT PROFILE, scatter queue.
+//
+// In shapes 2 and 3 every lane walks the macrocells of its own camera ray although the 32 lanes of a warp shoot
+// (nearly) the same ray: on C3 that is 14.7 dependent cell visits per scattered sample, repeated by every lane, and the
+// tentative collisions on the way execute with a third of the lanes (ncu, profiles/r01).  Here the walk is done ONCE per
+// pixel, by the warp together, and no lane ever walks a camera ray:
+//   1. profile.  The pixel's centre ray is cut into slabs by the macrocell planes of its fastest axis; lane k looks up
+//      the cells slab k crosses and keeps their largest majorant M_k (32 slabs per round, one per lane).  A jittered
+//      ray of the pixel has the same origin and, at equal ray parameter t, lies within dev = t * alpha of the centre ray
+//      (alpha: half the pixel's angular diagonal).  Every macrocell majorant already bounds the medium up to half a
+//      voxel outside its cell (svr_macrocell.cu stage 1); whatever dev exceeds that is covered by widening the looked-up
+//      cell box sideways by r = dev - 0.45 voxel and by giving each slab plane a transition interval of +-r in which the
+//      larger of the two neighbouring slab majorants applies.  So M(t), piecewise constant in t, is a valid majorant
+//      for EVERY camera ray of the pixel.  A shuffle scan turns it into cumulative optical depth C(t), kept in shared
+//      memory (2 intervals per slab, at most 128 slabs; longer rays use slabs several cells thick).
+//   2. camera rounds.  A lane holds one sample: it adds an exponential draw to its optical-depth target, inverts C
+//      (galloping search from where it stands; t follows in closed form), fetches the medium at its OWN ray's point and
+//      accepts with probability sigma / M(t) -- delta tracking against M(t).  One iteration is one tentative collision
+//      for every lane: the same instructions for all, whatever each ray has met so far.  A lane whose sample collides
+//      pushes it on the scatter queue (shape 3's), a lane whose sample leaves the medium adds light / sky; both take the
+//      pixel's next sample and go on, so lanes do not wait for each other's samples.
+//   3. scatter rounds: shape 3's round B, unchanged (shade, light sample, shadow flight, BSDF, bounce flight).
+// Any valid majorant gives the same free-path distribution, so the estimator is the reference's; the random walk of a
+// sample is still a pure function of (seed, pixel, sample), but it is not the walk shapes 1-3 make (other tentative
+// collisions): images agree statistically, not bit for bit.  Needs a pinhole camera (one origin per pixel).
+// ---------------------------------------------------------------------------------------------
+constexpr int SVR_PROF_SLABS = 128;
+
+struct PixelProfile {  // warp-uniform
+    float t0, dT, rho;  // parameter of the first slab plane, parameter length of a slab, half-width of a transition interval
+    float tA;           // where the profile begins (intervals are cut off there)
+    float total;        // optical depth of the whole profile
+    int n;              // slabs
+    int iStart;         // first interval that can hold a collision
+};
+
+SVR_DEV float axis_of(float3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+// Builds the profile of the pixel whose centre ray is `ray` (all lanes call it with the same arguments).
+// C[0 .. 2n]: cumulative optical depth at the start of interval i; interval 2k = transition around plane k
+// ([t_k - rho, t_k + rho], majorant max(M[k-1], M[k])), interval 2k+1 = slab k proper ([t_k + rho, t_k+1 - rho], M[k]).
+template <bool COUNT>
+SVR_DEV void build_profile(const DevScene& s, const Ray& ray, float alpha, float* C, float* M, PixelProfile& pp, uint32_t lane,
+                           LocalCounters<COUNT>& lc)
+{
+    pp.total = 0.f;
+    pp.n = 0;
+    pp.iStart = 0;
+    pp.t0 = pp.dT = pp.rho = pp.tA = 0.f;
+    const DevGrid& g = s.grid;
+    const float3 g0 = ray.orig * g.toCell - g.cellOff, dg = ray.dir * g.toCell;
+    const int* occ = g.occ;
+    const float3 lo = f3((float)__ldg(occ + 0), (float)__ldg(occ + 1), (float)__ldg(occ + 2));
+    const float3 hi = f3((float)(__ldg(occ + 3) + 1), (float)(__ldg(occ + 4) + 1), (float)(__ldg(occ + 5) + 1));
+    if (!(lo.x < hi.x)) return;  // no occupied cell at all
+    // sideways spread of the pixel's rays at the far end of the occupied box, in cells per axis, beyond the 0.45 voxel
+    // every majorant already covers
+    const float3 cellWorld = f3((float)g.cell) * f3(s.vol.spacing);
+    const float3 bc = f3(s.vol.bbox.vmin) + 0.5f * (lo + hi) * cellWorld - ray.orig;
+    const float3 bh = 0.5f * (hi - lo) * cellWorld;
+    const float devWorld = (sqrtf(dot(bc, bc)) + sqrtf(dot(bh, bh))) * alpha;
+    const float slack = 0.45f / (float)g.cell;
+    const float3 r = f3(fmaxf(devWorld * fabsf(g.toCell.x) - slack, 0.f), fmaxf(devWorld * fabsf(g.toCell.y) - slack, 0.f),
+                        fmaxf(devWorld * fabsf(g.toCell.z) - slack, 0.f));
+    // parameter interval in which some ray of the pixel can be inside the occupied box
+    float tA, tB;
+    {
+        const float3 inv = f3(dg.x != 0.f ? 1.f / dg.x : FLT_MAX, dg.y != 0.f ? 1.f / dg.y : FLT_MAX, dg.z != 0.f ? 1.f / dg.z : FLT_MAX);
+        const float3 a0 = (lo - r - f3(1.f) - g0) * inv, a1 = (hi + r + f3(1.f) - g0) * inv;
+        tA = fmaxf(fmaxf(fminf(a0.x, a1.x), fminf(a0.y, a1.y)), fminf(a0.z, a1.z));
+        tB = fminf(fminf(fmaxf(a0.x, a1.x), fmaxf(a0.y, a1.y)), fmaxf(a0.z, a1.z));
+    }
+    tA = fmaxf(tA, 0.f);
+    if (!(tA < tB)) return;
+    if (!(fabsf(ray.dir.x) + fabsf(ray.dir.y) + fabsf(ray.dir.z) < 4.f)) return;  // NaN direction: nothing to index the grid with
+    // slabs along the fastest axis, in the forward coordinate u = sign * g_axis (increasing with t)
+    const float ax = fabsf(dg.x), ay = fabsf(dg.y), az = fabsf(dg.z);
+    const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+    const float dga = axis_of(dg, axis), g0a = axis_of(g0, axis), ra = axis_of(r, axis);
+    const float sgn = dga > 0.f ? 1.f : -1.f, invA = 1.f / fabsf(dga);
+    const float uA = sgn * fmaf(tA, dga, g0a), uB = sgn * fmaf(tB, dga, g0a);
+    const float u0 = floorf(uA);
+    const float span = fmaxf(uB - u0, 0.f);
+    // cells per slab: at most SVR_PROF_SLABS slabs, and a slab at least as thick as two transition half-widths
+    const float S = fmaxf(floorf(span / (float)(SVR_PROF_SLABS - 1)) + 1.f, ceilf(2.f * ra));
+    const int n = (int)floorf(span / S) + 2;  // the last slab lies wholly beyond tB
+    const float t0 = (u0 - sgn * g0a) * invA;
+    const float dT = S * invA, rho = ra * invA;
+    float carryC = 0.f, carryM = 0.f;
+    int firstK = n;
+    for (int base = 0; base < n; base += 32) {
+        const int k = base + (int)lane;
+        float Mk = 0.f;
+        if (k < n) {
+            for (float c = 0.f; c < S; c += 1.f) {
+                const float layer = u0 + (float)k * S + c;  // forward index of this layer of cells
+                // the centre ray's stretch through this layer, plus the transition zones on both sides (a ray of the pixel can be
+                // in this layer while the centre ray is still up to rho before / beyond it)
+                const float t1 = (layer - sgn * g0a) * invA - rho, t2 = (layer + 1.f - sgn * g0a) * invA + rho;
+                const float3 e = f3(fmaf(t1, dg.x, g0.x), fmaf(t1, dg.y, g0.y), fmaf(t1, dg.z, g0.z));
+                const float3 x = f3(fmaf(t2, dg.x, g0.x), fmaf(t2, dg.y, g0.y), fmaf(t2, dg.z, g0.z));
+                const float ia = sgn > 0.f ? layer : -layer - 1.f;
+                float3 bl = f3(floorf(fminf(e.x, x.x) - r.x), floorf(fminf(e.y, x.y) - r.y), floorf(fminf(e.z, x.z) - r.z));
+                float3 bu = f3(floorf(fmaxf(e.x, x.x) + r.x), floorf(fmaxf(e.y, x.y) + r.y), floorf(fmaxf(e.z, x.z) + r.z));
+                if (axis == 0) bl.x = bu.x = ia;
+                else if (axis == 1) bl.y = bu.y = ia;
+                else bl.z = bu.z = ia;
+                // cells outside the grid are empty (one-cell empty border at -1 and g): clamping onto the border keeps that
+                const int x0 = (int)fminf(fmaxf(bl.x, -1.f), (float)g.gx), x1 = (int)fminf(fmaxf(bu.x, -1.f), (float)g.gx);
+                const int y0 = (int)fminf(fmaxf(bl.y, -1.f), (float)g.gy), y1 = (int)fminf(fmaxf(bu.y, -1.f), (float)g.gy);
+                const int z0 = (int)fminf(fmaxf(bl.z, -1.f), (float)g.gz), z1 = (int)fminf(fmaxf(bu.z, -1.f), (float)g.gz);
+                for (int cz = z0; cz <= z1; ++cz)
+                    for (int cy = y0; cy <= y1; ++cy)
+                        for (int cx = x0; cx <= x1; ++cx) {
+                            Mk = fmaxf(Mk, g.at(cx, cy, cz));
+                            lc.add(SVR_CNT_CELLS, 1);
+                        }
+            }
+        }
+        float Mprev = __shfl_up_sync(0xffffffffu, Mk, 1);
+        if (lane == 0) Mprev = carryM;
+        // interval lengths, cut off at tA: nothing collides before the pixel's rays can be inside the occupied box (nor behind
+        // the eye: tA >= 0)
+        const float tk = fmaf((float)k, dT, t0);
+        const float len0 = fmaxf(tk + rho - fmaxf(tk - rho, tA), 0.f), len1 = fmaxf(tk + dT - rho - fmaxf(tk + rho, tA), 0.f);
+        const float d0 = k < n ? fmaxf(Mprev, Mk) * len0 : 0.f;
+        const float d1 = k < n ? Mk * len1 : 0.f;
+        const float pair = d0 + d1;
+        float incl = pair;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        if (k < n) {
+            const float c0 = carryC + (incl - pair);
+            C[2 * k] = c0;
+            C[2 * k + 1] = c0 + d0;
+            M[k] = Mk;
+        }
+        const unsigned some = __ballot_sync(0xffffffffu, pair > 0.f);
+        if (some && firstK == n) firstK = base + __ffs(some) - 1;
+        carryC += __shfl_sync(0xffffffffu, incl, 31);
+        carryM = __shfl_sync(0xffffffffu, Mk, 31);
+    }
+    if (lane == 0) C[2 * n] = carryC;
+    __syncwarp();
+    pp.t0 = t0;
+    pp.dT = dT;
+    pp.rho = rho;
+    pp.tA = tA;
+    pp.n = n;
+    pp.total = carryC;
+    pp.iStart = firstK < n ? 2 * firstK : 0;
+}
+
+SVR_DEV void queue_push_raw(float* q, int idx, float3 orig, float3 dir, float t, float3 T, uint32_t k, uint32_t c0, uint32_t c1)
+{
+    q[0 * SVR_QUEUE_CAP + idx] = orig.x;
+    q[1 * SVR_QUEUE_CAP + idx] = orig.y;
+    q[2 * SVR_QUEUE_CAP + idx] = orig.z;
+    q[3 * SVR_QUEUE_CAP + idx] = dir.x;
+    q[4 * SVR_QUEUE_CAP + idx] = dir.y;
+    q[5 * SVR_QUEUE_CAP + idx] = dir.z;
+    q[6 * SVR_QUEUE_CAP + idx] = t;
+    q[7 * SVR_QUEUE_CAP + idx] = T.x;
+    q[8 * SVR_QUEUE_CAP + idx] = T.y;
+    q[9 * SVR_QUEUE_CAP + idx] = T.z;
+    q[10 * SVR_QUEUE_CAP + idx] = __uint_as_float(k);  // no buffered random word travels with the entry
+    q[11 * SVR_QUEUE_CAP + idx] = __uint_as_float(c0);
+    q[12 * SVR_QUEUE_CAP + idx] = __uint_as_float(c1);
+    q[13 * SVR_QUEUE_CAP + idx] = 0.f;
+}
+
+// Per-warp shared memory of shape 4: the profile, an inverse table over it, the pixel's camera basis.
+//   C[0 .. 2n]   cumulative optical depth at the start of interval i            (2 * SLABS + 1 floats)
+//   M[0 .. n-1]  slab majorants                                                 (SLABS floats)
+//   inv[0..BINS] for optical depth b * total / BINS: the interval that holds it (BINS + 1 uint16)
+//   cam[0..8]    D0, du, dv: direction through sub-pixel (jx, jy) = normalize(D0 + jx du + jy dv)
+constexpr int SVR_PROF_BINS = 128;
+//   stash        the camera samples the lanes hold, parked while a scatter round uses the registers (7 x 32 words)
+constexpr int SVR_PROF_C = 0, SVR_PROF_M = 2 * SVR_PROF_SLABS + 4, SVR_PROF_CAM = SVR_PROF_M + SVR_PROF_SLABS,
+              SVR_PROF_INV = SVR_PROF_CAM + 16, SVR_PROF_STASH = SVR_PROF_INV + (SVR_PROF_BINS + 2) / 2 + 1,
+              SVR_PROF_FLOATS = SVR_PROF_STASH + 7 * 32;
+
+enum LaneStatus { LANE_IDLE = 0, LANE_FLY = 1, LANE_HIT = 2, LANE_ESC = 3 };
+
+template <bool COUNT>
+__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_PROFILE_BLOCKS) pathtrace_profile_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+{
+    constexpr int MODE = 2;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ float queues[SVR_PT_MAX_THREADS / 32][SVR_QUEUE_WORDS * SVR_QUEUE_CAP];
+    __shared__ float profiles[SVR_PT_MAX_THREADS / 32][SVR_PROF_FLOATS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 5) + warp;
+    float* q = queues[warp];
+    float* C = profiles[warp] + SVR_PROF_C;
+    float* M = profiles[warp] + SVR_PROF_M;
+    float* camv = profiles[warp] + SVR_PROF_CAM;
+    unsigned short* inv = (unsigned short*)(profiles[warp] + SVR_PROF_INV);
+    float* stash = profiles[warp] + SVR_PROF_STASH + lane;
+    LocalCounters<COUNT> lc;
+    if (idy < a.y1) {
+        PathState<MODE> ps;
+        const svr_camera& cam = s.cam;
+        // half the pixel's angular diagonal (see classify_pixel)
+        const float hx = cam.aspectRatio * cam.tanFovxOverTwo / ((float)cam.imageW - 1.f), hy = cam.tanFovxOverTwo / ((float)cam.imageH - 1.f);
+        const float alpha = sqrtf(hx * hx + hy * hy) * 1.05f;
+        for (uint32_t i = 0; i < (uint32_t)a.warpPixels; ++i) {
+            const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
+            if (idx >= cam.imageW) break;
+            const uint32_t offset = idy * cam.imageW + idx;
+            const PixelInfo pi = classify_pixel(s, idx, idy, false, false, a.lightCull != 0);  // lights only
+            pixel_begin<MODE>(ps);
+            ps.camLights = pi.lights;
+            PixelProfile pp;
+            pp.total = 0.f;
+            if (a.traceDepth != 0) {
+                __syncwarp();  // the previous pixel's profile is no longer read
+                build_profile<COUNT>(s, camera_ray_center(cam, idx, idy), alpha, C, M, pp, lane, lc);
+            }
+            if (a.traceDepth == 0) {
+                for (uint32_t n = lane; n < a.nSamples; n += 32u) lc.add(SVR_CNT_PATHS, 1);  // black (pathtracer.cu:216)
+            } else if (!(pp.total > 0.f) && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
+                // no camera ray of the pixel can collide and none can hit a light: every sample is the constant sky
+                const float3 sky = s.envEnabled ? f3(s.env.defaultRadiance) * s.env.intensity : f3(0.f);
+                for (uint32_t n = lane; n < a.nSamples; n += 32u) {
+                    lc.add(SVR_CNT_PATHS, 1);
+                    ps.L += sky;
+                }
+            } else {
+                const int nI = 2 * pp.n;
+                const float invDTau = pp.total > 0.f ? (float)SVR_PROF_BINS / pp.total : 0.f;
+                {
+                    // inverse table: inv[b] = largest interval index i with C[i] <= b * total / BINS (then the interval of any
+                    // optical depth in bin b lies in inv[b] .. inv[b + 1]); and the camera basis of the pixel
+                    for (int bin = (int)lane; bin <= SVR_PROF_BINS; bin += 32) {
+                        const float tau = (float)bin * (pp.total * (1.f / (float)SVR_PROF_BINS));
+                        int lo = 0, hi = nI > 0 ? nI - 1 : 0;
+                        while (lo < hi) {
+                            const int mid = (lo + hi + 1) >> 1;
+                            if (C[mid] <= tau) lo = mid;
+                            else hi = mid - 1;
+                        }
+                        inv[bin] = (unsigned short)(bin == SVR_PROF_BINS ? (nI > 0 ? nI - 1 : 0) : lo);
+                    }
+                    if (lane < 9) {
+                        // cuda_camera.h:66-83 with a closed aperture: dir = normalize(nx u + ny v - f w), nx = (2 (x + jx) / (W - 1) - 1) aspect tan f
+                        const float kx = cam.aspectRatio * cam.tanFovxOverTwo * cam.focalLength, ky = cam.tanFovxOverTwo * cam.focalLength;
+                        const float sx = 2.f / ((float)cam.imageW - 1.f), sy = 2.f / ((float)cam.imageH - 1.f);
+                        const float nx0 = ((float)idx * sx - 1.f) * kx, ny0 = ((float)idy * sy - 1.f) * ky;
+                        const int c3 = (int)lane % 3;
+                        const float u = c3 == 0 ? cam.u.x : (c3 == 1 ? cam.u.y : cam.u.z), v = c3 == 0 ? cam.v.x : (c3 == 1 ? cam.v.y : cam.v.z),
+                                    w = c3 == 0 ? cam.w.x : (c3 == 1 ? cam.w.y : cam.w.z);
+                        camv[lane] = lane < 3 ? nx0 * u + ny0 * v - cam.focalLength * w : (lane < 6 ? sx * kx * u : sy * ky * v);
+                    }
+                    if (lane == 9) {
+                        camv[9] = pp.t0;
+                        camv[10] = pp.dT;
+                        camv[11] = pp.rho;
+                        camv[12] = pp.tA;
+                    }
+                    __syncwarp();
+                }
+                const float3 camPos = f3(cam.pos);
+                uint32_t nextN = 0;  // camera samples handed out so far (warp-uniform)
+                int queued = 0;      // entries on the scatter queue (warp-uniform)
+                // the camera sample this lane holds
+                int status = LANE_IDLE;
+                float3 dir = f3(0.f);
+                float target = 0.f;  // LANE_FLY: optical depth of the next tentative collision; LANE_HIT: parameter of the collision
+                uint32_t c0 = 0, c1 = 0;
+                while (true) {
+                    // ---- scatter round (shape 3's round B) whenever 32 collisions wait: one scatter event each
+                    const unsigned notFlying = __ballot_sync(FULL, status != LANE_FLY);
+                    const unsigned pending = __ballot_sync(FULL, status == LANE_HIT || status == LANE_ESC);
+                    const bool camDone = nextN >= a.nSamples && notFlying == FULL && pending == 0u;
+                    if (queued >= 32 || (camDone && queued > 0)) {
+                        const int take = queued < 32 ? queued : 32;
+                        queued -= take;
+                        bool active = (int)lane < take, own = false;
+                        Next next = NEXT_PATH_DONE;
+                        float t = -FLT_MAX;
+                        // the camera sample this lane holds is parked in shared memory: the scatter round needs the registers
+                        stash[0 * 32] = __int_as_float(status);
+                        stash[1 * 32] = dir.x;
+                        stash[2 * 32] = dir.y;
+                        stash[3 * 32] = dir.z;
+                        stash[4 * 32] = target;
+                        stash[5 * 32] = __uint_as_float(c0);
+                        stash[6 * 32] = __uint_as_float(c1);
+                        __syncwarp();  // the pushes of the camera rounds precede the pops
+                        if (active) {
+                            t = queue_pop(q, queued + (int)lane, ps);
+                            next = NEXT_EVENT_AT_T;
+                            own = true;
+                        }
+                        __syncwarp();  // every pop of the round precedes every push
+                        bool push = false;
+                        while (active) {
+                            if (next == NEXT_TRACK) t = fly<MODE, COUNT>(s, ps, lc);
+                            else if (next != NEXT_EVENT_AT_T) t = -FLT_MAX;
+                            if (next == NEXT_BOUNCE || ps.shadow) {
+                                next = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, t), a.traceDepth, lc);
+                            } else {
+                                if (t >= 0.f && !own) {
+                                    push = true;
+                                    break;
+                                }
+                                own = false;
+                                next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
+                            }
+                            if (next == NEXT_PATH_DONE) break;
+                        }
+                        const unsigned m = __ballot_sync(FULL, push);
+                        if (push) queue_push<COUNT>(q, queued + __popc(m & ((1u << lane) - 1u)), ps, t);
+                        queued += __popc(m);
+                        status = __float_as_int(stash[0 * 32]);
+                        dir = f3(stash[1 * 32], stash[2 * 32], stash[3 * 32]);
+                        target = stash[4 * 32];
+                        c0 = __float_as_uint(stash[5 * 32]);
+                        c1 = __float_as_uint(stash[6 * 32]);
+                        continue;
+                    }
+                    if (camDone) break;
+                    // ---- finish section: lanes whose sample collided push it, lanes whose sample left the medium add light or
+                    // sky, and all of them take the pixel's next samples -- together, once enough lanes have come to rest
+                    if (__popc(notFlying) >= a.marchBurst || notFlying == FULL) {
+                        const unsigned hit = __ballot_sync(FULL, status == LANE_HIT);
+                        if (status == LANE_HIT)
+                            queue_push_raw(q, queued + __popc(hit & ((1u << lane) - 1u)), camPos, dir, target, f3(1.f), 0u, c0, c1);
+                        queued += __popc(hit);
+                        if (status == LANE_ESC) {
+                            // the ray left the medium: pathtracer.cu:214-234 with t < 0
+                            LightHit ls;
+                            Ray rj;
+                            rj.orig = camPos;
+                            rj.dir = dir;
+                            if (ps.camLights && nearest_light(s, rj, &ls)) {
+                                const float cosTerm = dot(ls.normal, -dir);
+                                ps.L += ls.radiance * (cosTerm <= 0.f ? 0.f : 1.f);
+                            } else if (s.envEnabled) {
+                                ps.L += env_radiance(s.env, dir);
+                            }
+                        }
+                        if (status != LANE_FLY) status = LANE_IDLE;
+                        if (nextN < a.nSamples) {
+                            const uint32_t n = nextN + (uint32_t)__popc(notFlying & ((1u << lane) - 1u));
+                            if (status == LANE_IDLE && n < a.nSamples) {
+                                lc.add(SVR_CNT_PATHS, 1);
+                                Philox rng;
+                                rng.init(s.seedKey, offset, a.firstSample + n);
+                                uint32_t w0, w1;
+                                rng.generate(w0, w1);  // block 0: pixel jitter (16 bits each) and the first free flight
+                                c0 = rng.c0;
+                                c1 = rng.c1;
+                                const float jx = (float)(w0 >> 16) * (1.f / 65536.f), jy = (float)(w0 & 0xffffu) * (1.f / 65536.f);
+                                dir = normalize(f3(fmaf(jx, camv[3], fmaf(jy, camv[6], camv[0])), fmaf(jx, camv[4], fmaf(jy, camv[7], camv[1])),
+                                                   fmaf(jx, camv[5], fmaf(jy, camv[8], camv[2]))));
+                                target = -logf(1.f - (float)(w1 >> 8) * 5.9604645e-8f);
+                                status = LANE_FLY;
+                            }
+                            const uint32_t handed = (uint32_t)__popc(notFlying);
+                            nextN = nextN + handed < a.nSamples ? nextN + handed : a.nSamples;
+                        }
+                        if (queued >= 32) continue;  // (at most 63 entries: a scatter round comes before the next push)
+                    }
+                    // ---- camera round: every lane that holds a sample makes ONE tentative collision
+                    if (status == LANE_FLY) {
+                        if (!(target < pp.total)) {
+                            status = LANE_ESC;
+                        } else {
+                            // the interval that holds `target`: largest i with C[i] <= target, between the table's bounds
+                            const int bin = min((int)(target * invDTau), SVR_PROF_BINS - 1);
+                            int lo = inv[bin], hi = inv[bin + 1];
+                            while (lo < hi) {
+                                const int mid = (lo + hi + 1) >> 1;
+                                if (C[mid] <= target) lo = mid;
+                                else hi = mid - 1;
+                            }
+                            const int k = lo >> 1;
+                            const bool slab = (lo & 1) != 0;
+                            const float Mk = M[k];
+                            const float Mi = slab ? Mk : fmaxf(Mk, k > 0 ? M[k - 1] : 0.f);
+                            const float tStart = fmaxf(fmaf((float)k, camv[10], camv[9]) + (slab ? camv[11] : -camv[11]), camv[12]);
+                            const float t = tStart + (target - C[lo]) / Mi;
+                            const float3 pos = camPos + t * dir;
+                            float sigma = tf_at(s.tf, intensity_at(s.vol, pos)).w;
+                            lc.add(SVR_CNT_TRACK_TAPS, 1);
+                            lc.add(SVR_CNT_TF_LOOKUPS, 1);
+                            if (COUNT && sigma > Mi) lc.add(SVR_CNT_SKIPPED, 1);  // a profile that is not a majorant (tests assert 0)
+                            if (a.clipped) {
+                                // collisions count inside this ray's own clipped box only (woodcock_tracking.h:24-26, 43); without clip
+                                // planes the box is the volume, outside of which the texture reads 0 (border addressing)
+                                Ray rj;
+                                rj.orig = camPos;
+                                rj.dir = dir;
+                                float tNear, tFar;
+                                const bool in = intersect_volume(s.vol, rj, &tNear, &tFar);
+                                if (!(in && t >= (tNear < 0.f ? 1e-6f : tNear) && t <= tFar)) sigma = 0.f;
+                            }
+                            Philox rng;
+                            rng.c0 = c0;
+                            rng.c1 = c1;
+                            uint32_t w0, w1;
+                            rng.generate(w0, w1);  // the accept draw and the next free flight
+                            c0 = rng.c0;
+                            if ((float)(w0 >> 8) * 5.9604645e-8f * Mi < sigma) {
+                                status = LANE_HIT;
+                                target = t;
+                            } else {
+                                target += -logf(1.f - (float)(w1 >> 8) * 5.9604645e-8f);
+                            }
+                        }
+                    }
+                }
+            }
+            float3 sum = ps.L;
+            __syncwarp();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum.x += __shfl_xor_sync(FULL, sum.x, o);
+                sum.y += __shfl_xor_sync(FULL, sum.y, o);
+                sum.z += __shfl_xor_sync(FULL, sum.z, o);
             }
             if (lane == 0) write_pixel(s, a, offset, sum);
         }
@@ -996,7 +1437,10 @@ __global__ void resolve_kernel(const float4* __restrict__ sum, float* __restrict
 template <int MODE>
 void launch_mode(int shape, dim3 grid, int block, cudaStream_t stream, const DevScene& sc, const PtLaunch& a, Counters* cnt)
 {
-    if (shape == 3) {  // launch_pathtrace() only picks it for MODE 2
+    if (shape == 4) {  // launch_pathtrace() only picks it for MODE 2 with a pinhole camera
+        if (cnt) pathtrace_profile_kernel<true><<<grid, block, 0, stream>>>(sc, a, cnt);
+        else pathtrace_profile_kernel<false><<<grid, block, 0, stream>>>(sc, a, cnt);
+    } else if (shape == 3) {  // launch_pathtrace() only picks it for MODE 2
         if (cnt) pathtrace_queue_kernel<true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_queue_kernel<false><<<grid, block, 0, stream>>>(sc, a, cnt);
     } else if (shape == 2) {
@@ -1032,6 +1476,8 @@ int launch_pathtrace(PtLaunch a)
     a.marchBurst = st.options[SVR_OPT_PT_ROUNDS] > 0 ? st.options[SVR_OPT_PT_ROUNDS] : 4;
     a.entryCache = st.options[SVR_OPT_PT_ENTRY_CACHE] && a.nSamples >= 2;
     a.lightCull = st.options[SVR_OPT_PT_LIGHT_CULL];
+    a.clipped = !(sc.vol.x_clip.x == -1.f && sc.vol.x_clip.y == 1.f && sc.vol.y_clip.x == -1.f && sc.vol.y_clip.y == 1.f && sc.vol.z_clip.x == -1.f &&
+                  sc.vol.z_clip.y == 1.f);
     Counters* cnt = nullptr;
     if (st.options[SVR_OPT_COUNTERS]) {
         cnt = device_counters();
@@ -1045,7 +1491,13 @@ int launch_pathtrace(PtLaunch a)
     if (shape == 2 && queueDepth > 0 && a.traceDepth >= (uint32_t)queueDepth) shape = 3;
     // the scatter queue serves local-majorant Philox paths; the other estimators run the plain sample-parallel shape
     if (shape == 3 && mode != 2) shape = 2;
+    // camera rays against the pixel's majorant profile (shape 4) whenever the sample-parallel shape would run with
+    // local majorants and the camera is a pinhole (one origin per pixel); it has shape 3's scatter queue built in
+    if ((shape == 2 || shape == 3) && mode == 2 && st.options[SVR_OPT_PT_PROFILE] && sc.cam.apeture == 0.f) shape = 4;
+    if (shape == 4 && (mode != 2 || sc.cam.apeture != 0.f)) shape = 2;
     if (shape >= 2 && a.nSamples < (uint32_t)st.options[SVR_OPT_PT_WARP_MIN_SPP]) shape = 1;
+    // shape 4: idle lanes take new camera samples together, once this many wait (SVR_OPT_PT_REFILL)
+    if (shape == 4) a.marchBurst = st.options[SVR_OPT_PT_REFILL] > 0 ? st.options[SVR_OPT_PT_REFILL] : 8;
     a.warpPixels = st.options[SVR_OPT_PT_WARP_PIXELS];
     uint32_t tileW = 16u, tileH = (uint32_t)block / 16u;
     if (shape >= 2) {

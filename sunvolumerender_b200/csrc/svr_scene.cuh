@@ -164,6 +164,19 @@ SVR_DEV Ray camera_ray_jittered(const svr_camera& c, uint32_t x, uint32_t y, Rng
     return r;
 }
 
+// cuda_camera.h:66-83 for a closed aperture (the lens sample is the origin itself): the direction through the pixel at
+// sub-pixel position (jx, jy)
+SVR_DEV float3 camera_dir_pinhole(const svr_camera& c, uint32_t x, uint32_t y, float jx, float jy)
+{
+    float nx = 2.f * (((float)x + jx) / ((float)c.imageW - 1.f)) - 1.f;
+    float ny = 2.f * (((float)y + jy) / ((float)c.imageH - 1.f)) - 1.f;
+    nx = nx * c.aspectRatio * c.tanFovxOverTwo;
+    ny = ny * c.tanFovxOverTwo;
+    nx = nx * c.focalLength;
+    ny = ny * c.focalLength;
+    return normalize(nx * f3(c.u) + ny * f3(c.v) - c.focalLength * f3(c.w));
+}
+
 // ---- lights (core/geometry/cuda_disk.h, core/lights/) ------------------------------------------
 SVR_DEV float disk_area(const svr_disk& d) { return SVR_PI_F * d.radius * d.radius; }  // cuda_disk.h:53-56
 

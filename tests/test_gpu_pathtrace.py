@@ -112,7 +112,7 @@ def _product_batches(r, batches, per_batch, depth):
     return np.stack(out)
 
 
-def _statistical_parity(renderer, cfg, depth, K, per, configure, mean_tol=0.01, env=False):
+def _statistical_parity(renderer, cfg, depth, K, per, configure, mean_tol=0.01, env=False, rmse_tol=1.15):
     """Both sides render disjoint batches of `per` spp (reference 4K of them, product K).  Checks:
     (1) firefly-robust RMSE at equal spp (K*per) within 1.15x the reference-vs-reference noise floor --
     radiance is clamped at the 99.5th percentile of the lit reference pixels and medians over the four
@@ -133,7 +133,7 @@ def _statistical_parity(renderer, cfg, depth, K, per, configure, mean_tol=0.01, 
     mine = mb.mean(axis=0)
     assert np.isfinite(mine).all()
     err = float(np.median([crmse(mine, h) for h in halves]))
-    assert err <= 1.15 * floor, (err, floor)
+    assert err <= rmse_tol * floor, (err, floor)
 
     tm = np.stack([_tile_means(b) for b in mb])           # (K, th, tw, 3)
     tr = np.stack([_tile_means(b) for b in rb])           # (4K, th, tw, 3)
@@ -157,9 +157,9 @@ def _statistical_parity(renderer, cfg, depth, K, per, configure, mean_tol=0.01, 
     return mine, ref_all
 
 
-@pytest.mark.parametrize("mode,estimator,shape", [(2, 0, 2), (2, 1, 2), (1, 0, 2), (1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0), (2, 0, 3), (2, 1, 3)])
+@pytest.mark.parametrize("mode,estimator,shape", [(2, 0, 4), (2, 1, 4), (2, 0, 2), (2, 1, 2), (1, 0, 2), (1, 0, 1), (2, 0, 1), (2, 1, 1), (2, 0, 0), (1, 1, 0), (2, 0, 3), (2, 1, 3)])
 def test_product_modes_are_statistically_the_reference(renderer, mode, estimator, shape):
-    """Philox / local-majorant / ratio-tracking modes and all three kernel shapes draw different random
+    """Philox / local-majorant / ratio-tracking modes and all kernel shapes draw different random
     numbers from the same estimator as the reference's kernel_pathtracer."""
     depth = 4
     cfg = small_config(gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=depth)
@@ -169,6 +169,7 @@ def test_product_modes_are_statistically_the_reference(renderer, mode, estimator
         renderer.set_option(L.OPT_PT_MODE, mode)
         renderer.set_option(L.OPT_SHADOW_ESTIMATOR, estimator)
         renderer.set_option(L.OPT_PT_KERNEL, shape)
+        renderer.set_option(L.OPT_PT_PROFILE, 1 if shape == 4 else 0)
 
     _statistical_parity(renderer, cfg, depth, 8, 64, configure)
 
@@ -197,6 +198,7 @@ def test_sample_parallel_shape_equals_megakernel_up_to_summation_order(renderer)
     pure function of (seed, pixel, sample), only the order of the float additions differs."""
     cfg = small_config(n=96, w=150, h=101, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=3)
     setup(renderer, cfg)
+    renderer.set_option(L.OPT_PT_PROFILE, 0)  # shape 2 proper: shape 4 makes other random walks (tested below)
     for mode, spp in ((2, 64), (2, 40), (0, 33), (1, 7)):
         renderer.set_option(L.OPT_PT_MODE, mode)
         renderer.set_option(L.OPT_PT_WARP_MIN_SPP, 1)
@@ -227,6 +229,7 @@ def test_scatter_queue_shape_equals_sample_parallel_up_to_summation_order(render
     cfg = small_config(n=80, w=150, h=101, gen=gen, fmt=fmt, tf=tf, depth=depth, env=True)
     setup(renderer, cfg)
     renderer.set_option(L.OPT_SHADOW_ESTIMATOR, estimator)
+    renderer.set_option(L.OPT_PT_PROFILE, 0)          # shapes 2 and 3 proper
     renderer.set_option(L.OPT_PT_QUEUE_MIN_DEPTH, 0)  # shape 2 means shape 2 here, whatever the depth
     for spp in (96, 40):
         imgs = {}

@@ -14,5 +14,5 @@ done
 wait
 for v in "$@"; do
   name=${v%%:*}
-  echo -n "$name: "; grep -A2 "pathtrace_warp_kernelILi2ELb0" build/variants/pt_$name.log | grep -E "Used|spill" | tr '\n' ' '; echo
+  echo -n "$name: "; grep -A2 "pathtrace_profile_kernelILb0" build/variants/pt_$name.log | grep -E "Used|spill" | tr '\n' ' '; echo
 done
