@@ -7,8 +7,10 @@ One "step" = one pass of the path tracer over the whole frame: `spp` samples for
 workload (default C3, the configuration the metric is quoted on: 512^3 u16 volume, 1920x1080, Woodcock
 tracking, single scattering, area + environment light, 256 spp), accumulated into a float4 sum buffer,
 reduced over the ranks (N > 1: one NCCL sum-reduce of the per-GPU buffers onto rank 0) and resolved
-(divide + tone map) into the u8 image.  Weak scaling: every rank renders `spp` samples of its own
-(sample indices [rank*spp, (rank+1)*spp)), so the job is N*spp samples per pixel.
+(divide + tone map) into the u8 image.  Weak scaling: every rank renders `spp` samples of its own; like a progressive
+render the sample range advances with every step (step g, rank r: sample indices [(g*N + r)*spp, (g*N + r + 1)*spp)),
+so no step replays the taps of the one before.  N > 1 also reports the STRONG split (the workload's spp divided over
+the ranks, reduce + resolve inside the timed region) and, with enough GPUs and memory, C5.
 
   value     whole-job samples/s with the scene resident in HBM, CUDA events over exactly K steps,
             max over ranks.
@@ -20,17 +22,21 @@ reduced over the ranks (N > 1: one NCCL sum-reduce of the per-GPU buffers onto r
             upload of step i+1 runs on a copy stream beside the rendering of step i (render.VolumeStream)
             and the read-back of step i beside the binding and rendering of step i+1; the same loop
             without any overlap is reported as e2e.ms_per_step_without_overlap.
-  roofline  HBM: algorithmic bytes per launch (COUNTED taps x 8 voxels x bytes/voxel + TF lookups x 32 B
+  roofline  nominal HBM figure: algorithmic bytes per launch (COUNTED taps x 8 voxels x bytes/voxel + TF lookups x 32 B
             + framebuffer bytes) / the path-tracing kernel's mean launch duration
-            measured with CUDA events inside the timed region, against MEASURED_PEAKS.json.
+            measured with CUDA events inside the timed region, against MEASURED_PEAKS.json; `gather`: the kernel's
+            taps/s against the tex3D ceilings measured here on the benched volume (coherent and random taps, the
+            metric's "% of gather roofline"); `issue`: issue-slot utilisation and lanes per instruction of the
+            same kernel from the committed ncu capture -- the bound that actually limits it.
   cpu_baseline  the CPU oracle (port of the reference's device code, OpenMP over rows) on a bounded
             sample of the same workload -- test infrastructure used as a yardstick, never the product.
 
 --impl reference: the reference has no CPU render path; its implementation of
 this path IS its CUDA kernels.  The arm runs them unmodified (oracle/_ref, compiled from
 /root/reference by oracle/Makefile) on one B200 through the reference's own entry points and frame
-protocol (render_pathtracer once per sample, three launches each).  `--ref-device cpu` times the
-CPU port instead.
+protocol (render_pathtracer once per sample, three launches each).  Its scene (cudaArray, texture objects,
+synthetic voxels) is built by oracle/ref_scene.cu with plain CUDA runtime calls: the arm's process never loads
+libsvr_b200.so.  `--ref-device cpu` times the CPU port instead.
 """
 import argparse
 import ctypes as C
@@ -156,6 +162,150 @@ def grid_cell(r):
     return int(cell.value)
 
 
+
+def gather_ceilings(r, achieved_gtaps=None):
+    """The metric's "% of gather roofline": the texture unit's tap rate on the BENCHED volume, measured here with
+    dependence-free tex3D loops (svr_microbench_taps) -- coherent (neighbouring lanes walk neighbouring rays: the best the
+    unit does) and random (hashed coordinates over the whole volume: every tap a miss) -- and the path tracer's counted
+    taps per second as a fraction of each.  Best of 3 launches."""
+    import torch
+
+    from sunvolumerender_b200 import _lib as L
+
+    out = {}
+    sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+    for name, rnd, threads, per in (("coherent", 0, 1 << 20, 512), ("random", 1, 1 << 20, 128)):
+        taps_out = C.c_uint64(0)
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(r.lib.svr_microbench_taps(C.byref(r.volume), rnd, threads, per, C.c_void_p(sink.data_ptr()), C.byref(taps_out)))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        g = taps_out.value / (best * 1e-3) / 1e9
+        out[f"{name}_gtaps_per_s"] = round(g, 2)
+    out["peak_source"] = "measured here: 2^20 threads x 512 coherent / 128 random tex3D taps on the benched volume, best of 3"
+    return out
+
+
+def issue_counters(workload, spp, kernel):
+    """Issue-slot utilisation and lanes per instruction of the dominant kernel, from the committed ncu --set full capture of
+    this very launch (profiles/r02/issue.json, written by tools/ncu_issue.py from the .ncu-rep): the bound that limits it."""
+    for rnd in ("r02", "r01"):
+        path = os.path.join(ROOT, "profiles", rnd, "issue.json")
+        try:
+            with open(path) as f:
+                for e in json.load(f):
+                    if e.get("workload") == workload and e.get("spp") == spp and e.get("kernel") == kernel:
+                        return dict(e, source=f"profiles/{rnd}/issue.json")
+        except Exception:
+            continue
+    return None
+
+
+def timed_steps(fn, steps, warmup, barrier, dev):
+    """`steps` calls of fn() after `warmup`, CUDA events, max over ranks -> ms per step."""
+    import torch
+
+    from sunvolumerender_b200 import distributed as D
+
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return D.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+
+
+def strong_scaling_line(r, a, cfg, sum_buf, rank, world, dev, barrier):
+    """north_star's multi-GPU split: the workload's spp DIVIDED over the GPUs (C3: 256 / N per GPU), one NCCL sum-reduce
+    of the float4 accumulators onto rank 0, resolve there -- everything inside the timed region.  The speed-up over one
+    GPU is computed by whoever reads the N = 1 line; the parts are reported so that the limiter can be named."""
+    import torch
+    import torch.distributed as dist
+
+    from sunvolumerender_b200 import scene as S
+
+    spp = a.spp or cfg.spp
+    parts = S.split_samples(spp, world)
+    first, count = parts[rank]
+    npix = cfg.width * cfg.height
+    g = [0]
+
+    def step(render=True, reduce=True):
+        base = g[0] * spp
+        g[0] += 1
+        if render and count:
+            r.accumulate(sum_buf, cfg.trace_depth, base + first, count, clear=True)
+        elif render:
+            sum_buf.zero_()
+        if reduce:
+            dist.reduce(sum_buf, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                r.resolve(sum_buf)
+
+    ms = timed_steps(step, a.steps, max(a.warmup, 3), barrier, dev)
+    ms_render = timed_steps(lambda: step(True, False), max(3, a.steps // 2), 1, barrier, dev)
+    ms_reduce = timed_steps(lambda: step(False, True), max(3, a.steps // 2), 1, barrier, dev)
+    return {"workload": f"{cfg.name}: {spp} spp split over {world} GPUs ({count} per GPU on this rank), NCCL sum-reduce of {npix * 16 / 1e6:.1f} MB float4 "
+                        f"accumulators + resolve on rank 0 inside the timed region",
+            "scaling": "strong", "value": npix * spp / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "spp_total": spp,
+            "ms_render_only": ms_render, "ms_reduce_and_resolve_only": ms_reduce,
+            "limiter": "render time shrinks with N, the reduce of the full-frame accumulator and the resolve do not"}
+
+
+def c5_line(r, a, rank, world, dev, barrier):
+    """BASELINE.json configs[4]: 2048^3 u16 (16 GiB, replicated on every GPU), 3840x2160, 1024 spp split across the GPUs of the
+    box with one NCCL reduce of the accumulation buffers.  Run when the box has 8 GPUs (or --c5) and the memory for it."""
+    import torch
+    import torch.distributed as dist
+
+    from sunvolumerender_b200 import scene as S
+    from sunvolumerender_b200.render import setup_config
+
+    if world < 8 and not a.c5:
+        return None
+    cfg = S.CONFIGS["C5"]
+    free, _ = torch.cuda.mem_get_info(dev)
+    ok = torch.tensor([1 if free > 44 * 2 ** 30 else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        return {"workload": "C5", "unavailable": "needs ~40 GiB of free device memory per GPU (16 GiB of voxels + the generator's buffer)"}
+    vb = setup_config(r, cfg)
+    del vb
+    torch.cuda.empty_cache()
+    W, H, spp = cfg.width, cfg.height, cfg.spp
+    first, count = S.split_samples(spp, world)[rank]
+    buf = torch.zeros(W * H * 4, dtype=torch.float32, device=dev)
+    g = [0]
+
+    def step():
+        base = g[0] * spp
+        g[0] += 1
+        r.accumulate(buf, cfg.trace_depth, base + first, count, clear=True)
+        dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            r.resolve(buf)
+
+    ms = timed_steps(step, 3, 2, barrier, dev)
+    nz = float((r.ldr_image()[..., :3] > 0).float().mean()) if rank == 0 else None
+    line = {"workload": f"C5: 2048^3 u16 (16 GiB replicated), {W}x{H}, {spp} spp split over {world} GPUs ({count} per GPU), NCCL sum-reduce of "
+                        f"{W * H * 16 / 1e6:.0f} MB accumulators + resolve inside the timed region, device-resident, 3 steps",
+            "scaling": "strong", "value": W * H * spp / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "macrocell": grid_cell(r),
+            "image_nonzero_fraction": nz}
+    del buf
+    setup_config(r, S.CONFIGS["C1"])  # drop the 16 GiB array
+    torch.cuda.empty_cache()
+    return line
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -188,9 +338,16 @@ def run_ours(a):
     if a.cell:
         r.set_option(L.OPT_MACROCELL_SIZE, a.cell)
     sum_buf = torch.zeros(npix * 4, dtype=torch.float32, device=dev)
-    first = rank * spp
+    gstep = [0]  # steps rendered so far: like a progressive render, every step takes the next sample range
+
+    def next_first(n_spp=None):
+        n_spp = spp if n_spp is None else n_spp
+        first = (gstep[0] * world + rank) * n_spp
+        gstep[0] += 1
+        return first
 
     def render_step(time_kernel=None):
+        first = next_first()
         if time_kernel is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -203,10 +360,11 @@ def run_ours(a):
         if rank == 0:
             r.resolve(sum_buf)
 
-    # ---- counted taps of one launch (same seeds as the timed launches => same counts)
+    # ---- counted taps of one launch (the sample range of this rank's first step; the counts of later ranges differ by
+    # Monte Carlo noise, a few 1e-4 relative)
     r.set_option(L.OPT_COUNTERS, 1)
     r.reset_counters()
-    r.accumulate(sum_buf, depth, first, spp, clear=True)
+    r.accumulate(sum_buf, depth, rank * spp, spp, clear=True)
     torch.cuda.synchronize()
     cnt = r.counters()
     r.set_option(L.OPT_COUNTERS, 0)
@@ -240,6 +398,8 @@ def run_ours(a):
     kernel_ms = sum(x.elapsed_time(y) for x, y in kernel_events) / len(kernel_events)
     value = npix * spp * world * a.steps / (ms * 1e-3)
     cell_used = grid_cell(r)  # before other scenes are loaded into the renderer
+    base_volume, base_camera, base_lights = r.volume, r.camera, list(r.lights)  # the PODs of the benched scene (copies are taken by the oracle)
+    gather = gather_ceilings(r) if rank == 0 else None
 
     # ---- e2e: everything from host buffers, results back on the host
     def run_e2e():
@@ -287,7 +447,7 @@ def run_ours(a):
             r.set_camera(cam)
             r.set_area_lights(lights)
             r.set_env_light(env, enabled=cfg.env)
-            r.accumulate(sum_buf, depth, first, spp, clear=True)
+            r.accumulate(sum_buf, depth, next_first(), spp, clear=True)
             if prefetch_next and not serial:
                 vs.prefetch(host_vox)                  # H2D (+ fan-out) of the NEXT frame, beside this frame's render kernel
             if world > 1:
@@ -353,6 +513,11 @@ def run_ours(a):
     else:
         e2e, img_nonzero = run_e2e()
 
+    # ---- N > 1: the STRONG split north_star states (the workload's spp divided over the GPUs, one NCCL sum-reduce of
+    # the float4 accumulators, resolve on rank 0 -- all inside the timed region), and C5 where it fits
+    strong = strong_scaling_line(r, a, cfg, sum_buf, rank, world, dev, barrier) if world > 1 else None
+    c5 = c5_line(r, a, rank, world, dev, barrier) if world > 1 and not a.no_c5 else None
+
     # the metric's second half at N > 1 (collective: every rank takes part)
     raycast_multi = raycast_lines_multi(r, rank, world, dev) if world > 1 and not a.no_raycast else None
 
@@ -370,25 +535,39 @@ def run_ours(a):
     roofline_kernel = f"pathtrace_{'warp' if warp_shape else 'mega'}_kernel<{a.pt_mode},0>"
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r01", "traffic.json")) as f:
-            tj = json.load(f)
-        if tj.get("workload") == a.workload and tj.get("spp") == spp and tj.get("pt_mode") == a.pt_mode and tj.get("kernel") == roofline_kernel:
-            traffic = tj["dram_bytes_per_launch"]
+        for rnd in ("r02", "r01"):
+            path = os.path.join(ROOT, "profiles", rnd, "traffic.json")
+            if not os.path.exists(path):
+                continue
+            with open(path) as f:
+                tj = json.load(f)
+            if tj.get("workload") == a.workload and tj.get("spp") == spp and tj.get("pt_mode") == a.pt_mode and tj.get("kernel") == roofline_kernel:
+                traffic = tj["dram_bytes_per_launch"]
+                break
     except Exception:
         pass
+    gtaps = taps / (kernel_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": roofline_kernel,
         "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
         "traffic": traffic, "peak_source": peak_src,
+        "note": "NOMINAL: SURVEY 8(d)'s algorithmic bytes over the measured HBM copy peak.  The kernel is not DRAM-bound (traffic = measured "
+                "DRAM bytes per launch, orders of magnitude below the algorithmic bytes: the taps hit L1TEX/L2); what bounds it is in `gather` "
+                "(texture-unit tap rate) and `issue` (SM issue slots under divergence)",
         "bytes_algo_per_launch": int(bytes_algo), "taps_per_launch": int(taps), "tf_lookups_per_launch": int(cnt["tf_lookups"]),
-        "kernel_ms": round(kernel_ms, 4), "gtaps_per_s": round(taps / (kernel_ms * 1e-3) / 1e9, 3),
+        "kernel_ms": round(kernel_ms, 4), "gtaps_per_s": round(gtaps, 3),
         "kernel_share_of_step": round(kernel_ms / (ms / a.steps), 4),
+        "gather": dict(gather, achieved_gtaps_per_s=round(gtaps, 3), frac_of_coherent=round(gtaps / gather["coherent_gtaps_per_s"], 4),
+                       frac_of_random=round(gtaps / gather["random_gtaps_per_s"], 4)),
+        "issue": issue_counters(a.workload, spp, roofline_kernel),
     }
 
     # ---- CPU baseline: the oracle port on a bounded sample (rank 0, N = 1 only)
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline:
-        cpu_baseline = cpu_port_sample(cfg, r, vb, a.cpu_seconds)
+        vox = vb.cpu().numpy().view(S.VOXEL_DTYPES[cfg.fmt]).reshape(cfg.n, cfg.n, cfg.n)
+        cpu_baseline = cpu_port_sample(cfg, vox, base_volume, base_camera, base_lights, a.cpu_seconds)
+        del vox
 
     # ---- the reference's own CUDA kernels on this GPU, bounded sample (context for the 3x target)
     ref_cuda = None
@@ -400,7 +579,7 @@ def run_ours(a):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,  # the reference publishes no number
         "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"{cfg.name}: {cfg.n}^3 {['u8', 'u16', 'f16', 'f32'][cfg.fmt]} procedural {['sphere-falloff', 'CT-like', 'cloud'][cfg.gen]} volume, "
@@ -411,7 +590,7 @@ def run_ours(a):
                            if world > 1 else "single GPU",
             "estimator": {0: "global majorant + XORWOW (reference twin)", 1: "global majorant + Philox", 2: "macrocell local majorants + Philox"}[a.pt_mode],
             "macrocell": cell_used,
-            "l2": f"volume {vb.numel() >> 20} MiB > 126 MB L2 and incoherent taps; no flush between steps",
+            "l2": f"volume {vb.numel() >> 20} MiB > 126 MB L2, every step renders a NEW sample range (other taps than the step before); no flush between steps",
             "image_nonzero_fraction": round(img_nonzero, 4) if img_nonzero is not None else None,
         },
         "e2e": e2e,
@@ -422,24 +601,23 @@ def run_ours(a):
         "reference_cuda": ref_cuda,
         "raycast": raycast,
         "other_workloads": other,
+        "strong_scaling": strong,
+        "c5": c5,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_port_sample(cfg, r, vb, seconds, threads=None):
+def cpu_port_sample(cfg, vox, volume, camera, lights, seconds):
     """The CPU oracle (test infrastructure) timed on an image-wide bounded sample: every 16th row, as
-    many frames as fit in about `seconds`."""
-    import numpy as np
-
+    many frames as fit in about `seconds`.  `vox`: host numpy voxels (z, y, x); the PODs as the entry points get them."""
     from oracle import binding as B
     from sunvolumerender_b200 import scene as S
 
     if not os.path.exists(B.CPU_LIB):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "cpu"], stdout=subprocess.DEVNULL)
-    vox = vb.cpu().numpy().view(S.VOXEL_DTYPES[cfg.fmt]).reshape(cfg.n, cfg.n, cfg.n)
-    o = B.CpuOracle(vox, cfg.fmt, (cfg.n,) * 3, r.volume, S.tf_table(cfg.tf), r.camera, r.lights)
+    o = B.CpuOracle(vox, cfg.fmt, (cfg.n,) * 3, volume, S.tf_table(cfg.tf), camera, lights)
     cores = B.cpu().svr_oracle_threads()
     W, H = cfg.width, cfg.height
     step = 16
@@ -521,39 +699,140 @@ def raycast_lines(r):
     return out
 
 
-def other_workload_lines(r, a):
-    """Context beside the headline: C4 (BASELINE.json configs[3]: 1024^3 f16 high-albedo cloud, traceDepth 32, macrocell
-    majorants, 1920x1080), device-resident, 128 of its 512 spp per launch, best of 3; and the reference's kernels on
-    the same scene (8 frames)."""
+def _best_ms(fn, reps=3, warm=1):
     import torch
 
+    best = None
+    for i in range(reps + warm):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+    return best
+
+
+def other_workload_lines(r, a):
+    """The driver-run record of what the headline does not show (one GPU, device-resident, the reference's kernels beside
+    every line on the same scene):
+      * C3 with the camera moved in so that the body fills the frame (no sky to classify away);
+      * the drop-in protocol: the workload as a reference host renders it, one render_pathtracer call per sample;
+      * C4 (configs[3]) at its full 512 spp, with counted taps and its roofline;
+      * C1 (configs[0]): ray cast + 16-spp path trace;
+      * the reference built with its shipped -maxrregcount=32 beside the uncapped build."""
+    import torch
+
+    from sunvolumerender_b200 import _lib as L
     from sunvolumerender_b200 import scene as S
     from sunvolumerender_b200.render import setup_config
 
+    out = []
+    peak, _ = measured_peak()
+
+    def counted(cfg, spp, first=0):
+        r.set_option(L.OPT_COUNTERS, 1)
+        r.reset_counters()
+        buf = torch.zeros(cfg.width * cfg.height * 4, dtype=torch.float32, device="cuda")
+        r.accumulate(buf, cfg.trace_depth, first, spp, clear=True)
+        torch.cuda.synchronize()
+        c = r.counters()
+        r.set_option(L.OPT_COUNTERS, 0)
+        return c
+
+    # ---- C3, close view and drop-in protocol
+    cfg = S.CONFIGS["C3"]
+    setup_config(r, cfg)
+    npix = cfg.width * cfg.height
+    buf = torch.zeros(npix * 4, dtype=torch.float32, device="cuda")
+    cam0 = r.camera
+    r.set_camera(S.make_camera((0, 0, cam0.pos.z * 0.45), (1, 0, 0), (0, 1, 0), (0, 0, 1), 45.0, 0.0, 1.0, 1.0, cfg.width, cfg.height))
+    ms = _best_ms(lambda i: r.accumulate(buf, cfg.trace_depth, i * cfg.spp, cfg.spp, clear=True))
+    c = counted(cfg, cfg.spp)
+    bytes_algo, taps = algorithmic_bytes(c, cfg.voxel_bytes, npix)
+    out.append({"workload": f"C3 close view: camera at 0.45 x the framing distance, the body fills the frame ({c['scatters'] / c['paths']:.2f} scatter events per "
+                            f"sample against {0.104:.2f} in the default view), {cfg.spp} spp per launch, device-resident",
+                "value": npix * cfg.spp / (ms * 1e-3), "unit": UNIT, "ms_per_launch": ms,
+                "roofline": {"bound": "hbm", "achieved": bytes_algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_algo / (ms * 1e-3) / 1e9 / peak,
+                             "taps_per_launch": int(taps), "gtaps_per_s": taps / (ms * 1e-3) / 1e9, "note": "nominal, see the headline's roofline.note"},
+                "reference_cuda": reference_cuda_sample(cfg, r, 16)})
+    r.set_camera(cam0)
+
+    def protocol(i):
+        r.frame_no = 0
+        for _ in range(cfg.spp):
+            r.render_pathtracer(cfg.trace_depth)   # Canvas::paintGL: one call = one sample, running mean + tone map every call
+
+    ms = _best_ms(protocol, reps=2)
+    out.append({"workload": f"C3 through the drop-in protocol: {cfg.spp} x render_pathtracer(img, renderParams), 1 spp per call (lane-per-pixel kernel, "
+                            f"running mean and tone-mapped image after every call), one final sync",
+                "value": npix * cfg.spp / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "launches_per_step": cfg.spp,
+                "reference_cuda": reference_cuda_sample(cfg, r, cfg.spp, reps=2)})
+    ref_r32 = reference_cuda_sample(cfg, r, 16, r32=True)
+    out.append({"workload": "C3, the reference's kernels built with the shipped -maxrregcount=32 (CMakeLists.txt:9) beside the uncapped build the headline ratio uses",
+                "reference_cuda_r32": ref_r32, "reference_cuda": reference_cuda_sample(cfg, r, 16)})
+    del buf
+
+    # ---- C4 at its full 512 spp: 4 launches of 128
     cfg = S.CONFIGS["C4"]
     try:
         setup_config(r, cfg)
+        npix = cfg.width * cfg.height
+        per, launches = 128, cfg.spp // 128
+        buf = torch.zeros(npix * 4, dtype=torch.float32, device="cuda")
+
+        def c4_step(i):
+            for j in range(launches):
+                r.accumulate(buf, cfg.trace_depth, (i * launches + j) * per, per, clear=(j == 0))
+
+        ms = _best_ms(c4_step, reps=2)
+        c = counted(cfg, per)
+        bytes_algo, taps = algorithmic_bytes(c, cfg.voxel_bytes, npix)
+        bytes_algo, taps = bytes_algo * launches, taps * launches
+        gather = gather_ceilings(r)
+        g = taps / (ms * 1e-3) / 1e9
+        out.append({"workload": f"C4: 1024^3 f16 cloud, 1920x1080, traceDepth {cfg.trace_depth}, {cfg.spp} spp per step ({launches} launches of {per}), "
+                                f"device-resident, scatter-queue kernel",
+                    "value": npix * cfg.spp / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "macrocell": grid_cell(r),
+                    "counted": {"taps_per_step": int(taps), "scatter_events_per_sample": c["scatters"] / c["paths"], "cell_visits_per_sample": c["cells"] / c["paths"]},
+                    "roofline": {"bound": "hbm", "achieved": bytes_algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_algo / (ms * 1e-3) / 1e9 / peak,
+                                 "gtaps_per_s": g, "gather": dict(gather, frac_of_coherent=g / gather["coherent_gtaps_per_s"], frac_of_random=g / gather["random_gtaps_per_s"]),
+                                 "issue": issue_counters("C4", 32, "pathtrace_queue_kernel<0>"), "note": "nominal; taps counted on one 128-spp launch x 4"},
+                    "reference_cuda": reference_cuda_sample(cfg, r, 8)})
+        del buf
     except Exception as e:  # e.g. not enough device memory beside the other buffers
-        return [{"workload": "C4", "unavailable": str(e)}]
-    spp = 128
+        out.append({"workload": "C4", "unavailable": str(e)})
+
+    # ---- C1: ray cast + 16-spp path trace
+    cfg = S.CONFIGS["C1"]
+    setup_config(r, cfg)
+    torch.cuda.empty_cache()
     npix = cfg.width * cfg.height
     buf = torch.zeros(npix * 4, dtype=torch.float32, device="cuda")
-    best = None
-    for i in range(4):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r.accumulate(buf, cfg.trace_depth, 0, spp, clear=True)
-        e1.record()
-        torch.cuda.synchronize()
-        if i:
-            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
-    line = {"workload": f"C4: 1024^3 f16 cloud, 1920x1080, traceDepth {cfg.trace_depth}, {spp} spp per launch, device-resident",
-            "value": npix * spp / (best * 1e-3), "unit": UNIT, "ms_per_launch": best, "macrocell": grid_cell(r),
-            "reference_cuda": reference_cuda_sample(cfg, r, 8)}
-    del buf
-    setup_config(r, S.CONFIGS["C1"])  # drop the 2 GiB array
-    torch.cuda.empty_cache()
-    return [line]
+    step = S.raycast_step_size()
+    ms_rc = _best_ms(lambda i: r.render_raycasting(step), reps=5)
+    r.set_option(L.OPT_PT_WARP_MIN_SPP, 16)
+    ms_pt = _best_ms(lambda i: r.accumulate(buf, cfg.trace_depth, i * cfg.spp, cfg.spp, clear=True), reps=5)
+    r.set_option(L.OPT_PT_WARP_MIN_SPP, 32)
+    ms_pt_mega = _best_ms(lambda i: r.accumulate(buf, cfg.trace_depth, i * cfg.spp, cfg.spp, clear=True), reps=5)
+    line = {"workload": f"C1: 128^3 u8 sphere, 512x512, one area light: front-to-back ray cast, and a {cfg.spp}-spp path trace in one launch",
+            "raycast": {"value": npix / (ms_rc * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": ms_rc},
+            "pathtrace": {"value": npix * cfg.spp / (min(ms_pt, ms_pt_mega) * 1e-3), "unit": UNIT, "ms_per_launch": min(ms_pt, ms_pt_mega),
+                          "ms_sample_parallel_kernel": ms_pt, "ms_lane_per_pixel_kernel": ms_pt_mega},
+            "reference_cuda": reference_cuda_sample(cfg, r, cfg.spp)}
+    try:
+        from oracle import binding as B
+
+        ref = B.RefCuda(cfg.width, cfg.height)
+        ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
+        ms_ref = _best_ms(lambda i: ref.render_raycasting(step), reps=5)
+        line["reference_cuda_raycast"] = {"value": npix / (ms_ref * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": ms_ref}
+    except (FileNotFoundError, OSError) as e:
+        line["reference_cuda_raycast"] = {"unavailable": str(e)}
+    out.append(line)
+    return out
 
 
 def raycast_lines_multi(r, rank, world, dev):
@@ -643,20 +922,20 @@ def raycast_lines_multi(r, rank, world, dev):
     return out
 
 
-def reference_cuda_sample(cfg, r, frames):
+def reference_cuda_sample(cfg, r, frames, reps=3, r32=False):
     import torch
 
     from oracle import binding as B
 
     try:
-        ref = B.RefCuda(cfg.width, cfg.height)
+        ref = B.RefCuda(cfg.width, cfg.height, r32=r32)
     except (FileNotFoundError, OSError) as e:
         return {"unavailable": str(e)}
     ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
     ref.render_pathtracer(2, cfg.trace_depth)
     torch.cuda.synchronize()
     best = None
-    for _ in range(3):
+    for _ in range(reps):
         ref.frame_no = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -665,8 +944,9 @@ def reference_cuda_sample(cfg, r, frames):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         best = ms if best is None else min(best, ms)
-    return {"value": cfg.width * cfg.height * frames / (best * 1e-3), "unit": UNIT,
-            "sample": f"{frames} frames (render_pathtracer x{frames}, 3 launches each) of {cfg.name}, env light off (dead code in the reference), best of 3"}
+    return {"value": cfg.width * cfg.height * frames / (best * 1e-3), "unit": UNIT, "ms": best,
+            "sample": f"{frames} frames (render_pathtracer x{frames}, 3 launches each) of {cfg.name}{', -maxrregcount=32' if r32 else ''}, env light off (dead code in "
+                      f"the reference), best of {reps}"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -676,11 +956,12 @@ def run_reference(a):
     rank = env_int("RANK", 0)
     if rank != 0:
         return  # the reference is single-device: rank 0 alone runs it
+    import numpy as np
     import torch
 
-    from oracle import binding as B
-    from sunvolumerender_b200 import scene as S
-    from sunvolumerender_b200.render import Renderer, setup_config
+    from oracle import binding as B                 # the checkers: the reference's kernels + the plain-cudart scene builder
+    from sunvolumerender_b200 import scene as S     # host-side scene description only (numpy / ctypes structs); the product
+    #                                                 library libsvr_b200.so is NOT loaded anywhere in this arm
 
     cfg = S.CONFIGS[a.workload]
     spp = a.spp or cfg.spp
@@ -692,12 +973,18 @@ def run_reference(a):
         return
     local = env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
-    # scene resources (cudaArray + texture objects with the reference loaders' descriptors, synthetic voxels)
-    # come from this repo's resource builders; every pixel below is produced by the reference's kernels
-    r = Renderer(local)
-    vb = setup_config(r, cfg)
+    torch.zeros(1, device="cuda")  # the primary context the runtime-API calls below share
+    try:
+        scene = B.RefScene(cfg, S.tf_table(cfg.tf))  # cudaArray + texture objects with the reference loaders' descriptors, synthetic voxels
+    except (FileNotFoundError, OSError) as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/libsvr_refscene.so not prebuilt: {e}"}))
+        return
+    camera = S.default_camera(cfg.extent, W, H)
+    lights = [S.default_area_light(cfg.extent)]
+    env = S.constant_env_light()
     if a.ref_device == "cpu":
-        cb = cpu_port_sample(cfg, r, vb, max(10.0, a.cpu_seconds))
+        vox = scene.download(S.VOXEL_DTYPES[cfg.fmt], cfg.n)
+        cb = cpu_port_sample(cfg, vox, scene.volume, camera, lights, max(10.0, a.cpu_seconds))
         line = dict(base, value=cb["value"], ms_per_step=None,
                     config={"workload": f"{cfg.name} (bounded sample: {cb['sample']})"},
                     cpu_baseline=cb, e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
@@ -708,7 +995,7 @@ def run_reference(a):
     except (FileNotFoundError, OSError) as e:
         print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref library for {W}x{H} not prebuilt: {e}"}))
         return
-    ref.setup(r.volume, r.tf, r.camera, r.lights, r.env)
+    ref.setup(scene.volume, scene.tf, camera, lights, env)
     clocks = ClockSampler(local)
 
     def step():
@@ -730,12 +1017,14 @@ def run_reference(a):
     ms = ev0.elapsed_time(ev1)
     HB = ref.HB
     value = W * H * spp * a.steps / (ms * 1e-3)
+    nz = float((ref.ldr_image()[..., :3] > 0).float().mean())
     line = dict(
         base, value=value, ms_per_step=ms / a.steps,
-        config={"workload": f"{cfg.name}: {cfg.n}^3 u16, {W}x{H} path tracing, traceDepth {cfg.trace_depth}, one area light (environment light is dead "
+        config={"workload": f"{cfg.name}: {cfg.n}^3 {['u8', 'u16', 'f16', 'f32'][cfg.fmt]}, {W}x{H} path tracing, traceDepth {cfg.trace_depth}, one area light (environment light is dead "
                             f"code in the reference, pathtracer.cu:233), {spp} spp per step; the reference's unmodified kernels, sm_100, "
-                            f"-use_fast_math{' -maxrregcount=32' if a.ref_r32 else ''}; canvas {W}x{HB} (no bounds guard), {W}x{H} counted",
-                "spp_per_step_per_gpu": spp, "samples_per_step": W * H * spp},
+                            f"-use_fast_math{' -maxrregcount=32' if a.ref_r32 else ''}; canvas {W}x{HB} (no bounds guard), {W}x{H} counted; scene built by "
+                            f"oracle/ref_scene.cu (plain CUDA runtime, same voxels as the other arm's generator)",
+                "spp_per_step_per_gpu": spp, "samples_per_step": W * H * spp, "image_nonzero_fraction": round(nz, 4)},
         e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         gpu_launches=3 * spp * a.steps,
         clocks=clocks.finish(),
@@ -743,6 +1032,11 @@ def run_reference(a):
                       "sample": "the reference has no CPU path; this is its own CUDA implementation (oracle/_ref) on one B200, full workload"},
     )
     print(json.dumps(line), flush=True)
+    scene.close()
+    if os.environ.get("SVR_BENCH_PRINT_MAPS"):  # which of this repository's libraries the arm's process mapped
+        with open("/proc/self/maps") as f:
+            libs = sorted({ln.split()[-1] for ln in f if "svr" in ln and ".so" in ln})
+        print("mapped:", libs, file=sys.stderr)
 
 
 def main():
@@ -764,6 +1058,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-raycast", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="N = 8: skip the C5 line (2048^3 u16, 4K, 1024 spp over the GPUs)")
+    ap.add_argument("--c5", action="store_true", help="run the C5 line at any N > 1")
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--ref-r32", action="store_true", help="reference built with the shipped -maxrregcount=32")
     a = ap.parse_args()

@@ -144,6 +144,38 @@ def ref(width, height, r32=False, f32=False, env=False):
     return lib
 
 
+REFSCENE_LIB = os.path.join(REF_DIR, "libsvr_refscene.so")
+
+
+class RefScene:
+    """Scene resources of bench.py's reference arm, built by oracle/ref_scene.cu with plain CUDA runtime calls (same
+    descriptors as the reference's loaders, same synthetic voxels as the product's generator): the arm's process never
+    maps the product library."""
+
+    def __init__(self, cfg, tf_table):
+        if not os.path.exists(REFSCENE_LIB):
+            raise FileNotFoundError(REFSCENE_LIB)
+        self.lib = C.CDLL(REFSCENE_LIB, mode=C.RTLD_LOCAL)
+        self.lib.ref_scene_create.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(L.Volume), C.POINTER(L.TransferFunction)]
+        self.lib.ref_scene_destroy.argtypes = [C.POINTER(L.Volume), C.POINTER(L.TransferFunction)]
+        self.lib.ref_scene_download.argtypes = [C.POINTER(L.Volume), C.c_void_p, C.c_uint64]
+        table = np.ascontiguousarray(tf_table, dtype=np.float32)
+        self.volume, self.tf = L.Volume(), L.TransferFunction()
+        rc = self.lib.ref_scene_create(cfg.gen, cfg.fmt, cfg.n, cfg.gen_seed, table.ctypes.data, table.shape[0], C.byref(self.volume), C.byref(self.tf))
+        if rc != 0:
+            raise RuntimeError(f"ref_scene_create failed: CUDA error {rc}")
+
+    def download(self, dtype, n):
+        out = np.zeros((n, n, n), dtype)
+        rc = self.lib.ref_scene_download(C.byref(self.volume), out.ctypes.data, out.nbytes)
+        if rc != 0:
+            raise RuntimeError(f"ref_scene_download failed: {rc}")
+        return out
+
+    def close(self):
+        self.lib.ref_scene_destroy(C.byref(self.volume), C.byref(self.tf))
+
+
 class RefCuda:
     """Drives the reference's own kernels the way gui/canvas.cpp does: setup_* once, then
     render_pathtracer per frame with frameNo = 0, 1, ... (canvas.cpp:96,116), or render_raycasting.

@@ -364,3 +364,30 @@ def test_host_that_frees_and_reallocates_the_array_itself_gets_fresh_macrocells(
         assert torch.equal(img_b, img_b_cold) and torch.equal(rc_b, rc_b_cold), f"stale macrocells (attempt {attempt}, handles reused: {reused})"
         assert not torch.equal(img_b, img_a)
     print("array + texture handles reused in", reused, "of 3 attempts")
+
+
+def test_reference_arm_scene_builder_makes_the_same_scene_without_the_product_library(renderer):
+    """bench.py --impl reference builds its volume / transfer function with oracle/ref_scene.cu (plain CUDA runtime, the
+    generator's device code shared through svr_generate.cuh): the voxels, the cudaVolume fields and the images the
+    reference's kernels render from them are those of the product's resource builders, bit for bit."""
+    from oracle import binding as B
+
+    cfg = small_config(n=64, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=1)
+    vox = setup(renderer, cfg)
+    rs = B.RefScene(cfg, S.tf_table(cfg.tf))
+    try:
+        assert np.array_equal(rs.download(np.uint16, cfg.n), vox)
+        a, b = rs.volume, renderer.volume
+        for f in ("densityScale", "invMaxMagnitude", "gradientFactor"):
+            assert getattr(a, f) == getattr(b, f), f
+        assert a.bbox.vmin.tuple() == b.bbox.vmin.tuple() and a.bbox.invSize.tuple() == b.bbox.invSize.tuple()
+        assert rs.tf.maxOpacity == renderer.tf.maxOpacity
+        imgs = []
+        for vol, tf in ((rs.volume, rs.tf), (renderer.volume, renderer.tf)):
+            ref = B.RefCuda(cfg.width, cfg.height)
+            ref.setup(vol, tf, renderer.camera, renderer.lights, renderer.env)
+            ref.render_pathtracer(3, 1)
+            imgs.append(ref.hdr_image().clone())
+        assert float(imgs[0].max()) > 0 and torch.equal(imgs[0], imgs[1])
+    finally:
+        rs.close()
