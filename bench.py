@@ -604,7 +604,7 @@ def run_ours(a):
         "strong_scaling": strong,
         "c5": c5,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -647,8 +647,8 @@ def raycast_lines(r):
     from sunvolumerender_b200.render import setup_config
 
     out = []
-    for tf in ("thin", "default"):
-        cfg = S.Config("C2", 256, 0, 1, 1024, 1024, tf)
+    for label, n, W, H, tf in RAYCAST_WORKLOADS:
+        cfg = S.Config("RC", n, 0, 1, W, H, tf)
         setup_config(r, cfg)
         step = S.raycast_step_size()
         r.render_raycasting(step)
@@ -679,7 +679,7 @@ def raycast_lines(r):
         taps_out = C.c_uint64(0)
         tex_ms = best_of(lambda: L.check(r.lib.svr_microbench_taps(C.byref(r.volume), 0, 1 << 20, 512, C.c_void_p(sink.data_ptr()), C.byref(taps_out))), 3)
         peak = taps_out.value / (tex_ms * 1e-3) / 1e9
-        line = {"workload": f"C2: 256^3 u8 CT-like volume, 1024x1024, TF-{tf}", "value": cfg.width * cfg.height / (ms * 1e-3) / 1e6,
+        line = {"workload": label, "value": cfg.width * cfg.height / (ms * 1e-3) / 1e6,
                 "unit": "Mrays/s", "ms_per_frame": ms, "steps": cnt["steps"], "steps_skipped_as_empty": cnt["skipped"],
                 "taps": cnt["shade_taps"], "tf_lookups": cnt["tf_lookups"],
                 "roofline": {"bound": "l1tex", "achieved": cnt["shade_taps"] / (ms * 1e-3) / 1e9, "peak": peak, "unit": "Gtaps/s",
@@ -835,44 +835,36 @@ def other_workload_lines(r, a):
     return out
 
 
+RAYCAST_WORKLOADS = [
+    # (label, volume edge, width, height, transfer function)
+    ("C2: 256^3 u8 CT-like volume, 1024x1024, TF-thin", 256, 1024, 1024, "thin"),
+    ("C2: 256^3 u8 CT-like volume, 1024x1024, TF-default", 256, 1024, 1024, "default"),
+    ("RC4K: 512^3 u8 CT-like volume, 3840x2160, TF-thin (a frame long enough for a split to pay)", 512, 3840, 2160, "thin"),
+]
+
+
 def raycast_lines_multi(r, rank, world, dev):
-    """Ray casting on N GPUs (the metric's "ray-cast Mrays/s at 1/2/4/8 B200"): C2 replicated, image ROWS split
-    across the ranks (one deterministic pass), the u8 row blocks gathered onto rank 0 with
-    NCCL.  Timed per frame with CUDA events, max over ranks, best of 10 frames; rank 0 also renders the whole
-    frame alone and the gathered image must equal it bit for bit."""
+    """Ray casting on N GPUs (the metric's "ray-cast Mrays/s at 1/2/4/8 B200"): the volume replicated, the image split
+    across the ranks (one deterministic pass), three ways of putting it together on rank 0:
+      gather   contiguous row blocks, NCCL gather of the u8 blocks;
+      reduce   row bands dealt out round robin (balanced), NCCL sum-reduce of the u8 images (disjoint bands: a gather);
+      peer     the same bands written STRAIGHT into rank 0's image through peer mappings over NVLink, completion by a flag in
+               rank 0's memory (distributed.PeerFrame): no collective, no host in the loop.
+    Timed per frame with CUDA events, max over ranks, best of 10 frames; rank 0 also renders the whole frame alone and
+    every assembled image must equal it bit for bit."""
     import torch
     import torch.distributed as dist
 
+    from sunvolumerender_b200 import _lib as L
     from sunvolumerender_b200 import distributed as D
     from sunvolumerender_b200 import scene as S
     from sunvolumerender_b200.render import setup_config
 
-    out = []
-    for tf in ("thin", "default"):
-        cfg = S.Config("C2", 256, 0, 1, 1024, 1024, tf)
-        setup_config(r, cfg)
-        W, H = cfg.width, cfg.height
-        step = S.raycast_step_size()
-        rows = S.split_rows(H, world)
-        y0, y1 = rows[rank]
-        pad = max(b - a for a, b in rows)
-        block = torch.zeros(pad * W * 4, dtype=torch.uint8, device=dev)
-        gathered = [torch.zeros_like(block) for _ in range(world)] if rank == 0 else None
-        img = r.img.view(H, W, 4)
-
-        even = all(b - a == pad for a, b in rows)
-        mine = r.img[y0 * W * 4: y1 * W * 4] if even else block   # a rank's rows are contiguous in the image
-
-        def frame():
-            r.render_raycasting_f32(None, step, rows=(y0, y1), img=r.img)   # this rank's rows of the u8 image
-            if not even:
-                block[: (y1 - y0) * W * 4].copy_(img[y0:y1].reshape(-1))
-            dist.gather(mine, gathered, dst=0)
-
+    def best_frame(frame, n=10):
         frame()
         torch.cuda.synchronize()
         best = None
-        for _ in range(10):
+        for _ in range(n):
             dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -882,43 +874,64 @@ def raycast_lines_multi(r, rank, world, dev):
             torch.cuda.synchronize()
             ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
             best = ms if best is None else min(best, ms)
-        equal = None
-        if rank == 0:
-            full = torch.cat([g[: (b - a) * W * 4] for g, (a, b) in zip(gathered, rows)]).view(H, W, 4)
-            r.render_raycasting(step)
-            torch.cuda.synchronize()
-            equal = bool(torch.equal(full, r.ldr_image()))
-        # the balanced split: row bands dealt out round robin, u8 images (zero outside a rank's bands) sum-reduced
-        def frame_bands():
+        return best
+
+    out = []
+    for label, n, W, H, tf in RAYCAST_WORKLOADS:
+        cfg = S.Config("RC", n, L.VOXEL_U8, L.GEN_CT, W, H, tf)
+        setup_config(r, cfg)
+        step = S.raycast_step_size()
+        rows = S.split_rows(H, world)
+        y0, y1 = rows[rank]
+        pad = max(b - a for a, b in rows)
+        block = torch.zeros(pad * W * 4, dtype=torch.uint8, device=dev)
+        gathered = [torch.zeros_like(block) for _ in range(world)] if rank == 0 else None
+        img = r.img.view(H, W, 4)
+        even = all(b - a == pad for a, b in rows)
+        mine = r.img[y0 * W * 4: y1 * W * 4] if even else block   # a rank's rows are contiguous in the image
+        r.render_raycasting(step)   # builds the macrocell grid; the single-GPU image
+        torch.cuda.synchronize()
+        single = r.ldr_image().clone() if rank == 0 else None
+
+        def frame_gather():
+            r.render_raycasting_f32(None, step, rows=(y0, y1), img=r.img)   # this rank's rows of the u8 image
+            if not even:
+                block[: (y1 - y0) * W * 4].copy_(img[y0:y1].reshape(-1))
+            dist.gather(mine, gathered, dst=0)
+
+        ms_gather = best_frame(frame_gather)
+        eq_gather = bool(torch.equal(torch.cat([g[: (b - a) * W * 4] for g, (a, b) in zip(gathered, rows)]).view(H, W, 4), single)) if rank == 0 else None
+
+        def frame_reduce():
             r.img.zero_()
             r.render_raycasting_bands(rank, world, step)
             dist.reduce(r.img, dst=0, op=dist.ReduceOp.SUM)
 
-        frame_bands()
-        torch.cuda.synchronize()
-        best_b = None
-        for _ in range(10):
-            dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            frame_bands()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
-            best_b = ms if best_b is None else min(best_b, ms)
-        equal_b = None
-        if rank == 0:
-            banded = r.ldr_image().clone()
-            r.render_raycasting(step)
-            torch.cuda.synchronize()
-            equal_b = bool(torch.equal(banded, r.ldr_image()))
-        use_bands = best_b < best
-        out.append({"workload": f"C2: 256^3 u8 CT-like volume, 1024x1024, TF-{tf}, x{world} GPUs, "
-                                + ("row bands dealt round robin, NCCL sum-reduce of the u8 images" if use_bands else "contiguous row blocks, NCCL gather of u8 row blocks"),
-                    "value": W * H / (min(best, best_b) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": min(best, best_b),
-                    "ms_per_frame_contiguous_rows_gather": best, "ms_per_frame_interleaved_bands_reduce": best_b,
-                    "equals_single_gpu_image": bool(equal and equal_b) if rank == 0 else None})
+        ms_reduce = best_frame(frame_reduce)
+        eq_reduce = bool(torch.equal(r.ldr_image(), single)) if rank == 0 else None
+
+        ms_peer, eq_peer, peer_err = None, None, None
+        try:
+            pf = D.PeerFrame(r, W * H * 4)
+
+            def frame_peer():
+                r.render_raycasting_bands(rank, world, step, img_ptr=pf.img_ptr)
+                pf.frame_done()
+
+            ms_peer = best_frame(frame_peer)
+            if rank == 0:
+                eq_peer = bool(torch.equal(pf.image().view(H, W, 4), single))
+            pf.close()
+        except Exception as e:  # no peer access between these GPUs
+            peer_err = str(e)
+        times = {"gather": ms_gather, "reduce": ms_reduce}
+        if ms_peer is not None:
+            times["peer"] = ms_peer
+        how = min(times, key=times.get)
+        out.append({"workload": f"{label}, x{world} GPUs", "value": W * H / (times[how] * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": times[how], "assembled_by": how,
+                    "ms_per_frame_contiguous_rows_nccl_gather": ms_gather, "ms_per_frame_interleaved_bands_nccl_reduce": ms_reduce,
+                    "ms_per_frame_interleaved_bands_peer_writes": ms_peer, "peer_unavailable": peer_err,
+                    "equals_single_gpu_image": bool(eq_gather and eq_reduce and (eq_peer is not False)) if rank == 0 else None})
     return out
 
 
@@ -969,7 +982,7 @@ def run_reference(a):
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
     if not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference", "unavailable": "no CUDA device: the reference's only implementation of the path is CUDA"}))
+        emit({"impl": "reference", "unavailable": "no CUDA device: the reference's only implementation of the path is CUDA"})
         return
     local = env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
@@ -977,7 +990,7 @@ def run_reference(a):
     try:
         scene = B.RefScene(cfg, S.tf_table(cfg.tf))  # cudaArray + texture objects with the reference loaders' descriptors, synthetic voxels
     except (FileNotFoundError, OSError) as e:
-        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/libsvr_refscene.so not prebuilt: {e}"}))
+        emit({"impl": "reference", "unavailable": f"oracle/_ref/libsvr_refscene.so not prebuilt: {e}"})
         return
     camera = S.default_camera(cfg.extent, W, H)
     lights = [S.default_area_light(cfg.extent)]
@@ -988,12 +1001,12 @@ def run_reference(a):
         line = dict(base, value=cb["value"], ms_per_step=None,
                     config={"workload": f"{cfg.name} (bounded sample: {cb['sample']})"},
                     cpu_baseline=cb, e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     try:
         ref = B.RefCuda(W, H, r32=a.ref_r32)
     except (FileNotFoundError, OSError) as e:
-        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref library for {W}x{H} not prebuilt: {e}"}))
+        emit({"impl": "reference", "unavailable": f"oracle/_ref library for {W}x{H} not prebuilt: {e}"})
         return
     ref.setup(scene.volume, scene.tf, camera, lights, env)
     clocks = ClockSampler(local)
@@ -1031,7 +1044,7 @@ def run_reference(a):
         cpu_baseline={"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                       "sample": "the reference has no CPU path; this is its own CUDA implementation (oracle/_ref) on one B200, full workload"},
     )
-    print(json.dumps(line), flush=True)
+    emit(line)
     scene.close()
     if os.environ.get("SVR_BENCH_PRINT_MAPS"):  # which of this repository's libraries the arm's process mapped
         with open("/proc/self/maps") as f:
@@ -1039,7 +1052,23 @@ def run_reference(a):
         print("mapped:", libs, file=sys.stderr)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def main():
+    # Libraries write to stdout behind Python's back (NCCL's "NCCL version ..." banner at communicator creation): route
+    # file descriptor 1 to stderr for the whole run and keep the real stdout for the one JSON line.
+    global _REAL_STDOUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -1070,6 +1099,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -165,6 +165,15 @@ int svr_stage_import(const unsigned char handle[64], void** peer_ptr);
 int svr_stage_release(void* peer_ptr);
 int svr_stage_copy(void* dst, const void* src, uint64_t bytes, void* stream);
 
+/* Completion flags between the GPUs of one box (ray casting on N GPUs without a collective): every rank renders its
+ * bands straight into rank 0's image through a peer mapping of that buffer (svr_stage_alloc / _export / _import; pass
+ * the mapped pointer as `img`), then raises rank 0's flag with svr_peer_signal (a peer mapping of an 8-byte,
+ * zero-initialised svr_stage_alloc buffer: word 0 counts signals, word 1 is set when a wait timed out); rank 0's stream
+ * waits with svr_peer_wait until word 0 has reached `expected` (wrap-safe; gives up after timeout_ms).  Both are
+ * stream-ordered launches on the library's stream: no host synchronisation, no NCCL. */
+int svr_peer_signal(void* peer_flag);
+int svr_peer_wait(void* flag, uint32_t expected, uint32_t timeout_ms);
+
 /* Ray caster variants: float RGBA before quantisation (parity is checked on these), and a row
  * range [y0, y1) for the image-tile split across GPUs.  out/img are full-frame buffers. */
 int svr_render_raycasting_f32(svr_vec4* out, const svr_volume* volume, const svr_transfer_function* tf,
@@ -178,7 +187,10 @@ int svr_render_raycasting_rows(svr_u8vec4* img, svr_vec4* outOrNull, const svr_v
  * call renders bands phase, phase + stride, phase + 2 stride, ... -- rank r of N passes (r, N).  Contiguous row blocks
  * give the ranks that see the body several times the work of the ranks that see its margins; interleaved bands
  * do not.  Rows outside the call's bands are left untouched (zero the image first and sum-reduce the u8 images:
- * disjoint bands make the sum a gather). */
+ * disjoint bands make the sum a gather; or let every rank write into one image through peer mappings, svr_peer_*).
+ * The headless ray-cast entry points (_f32, _rows, _bands) rebuild the empty-space majorants when the transfer function's
+ * HANDLE changes or an edit was announced (setup_transferfunction, svr_tf_upload); only render_raycasting itself also
+ * checks the table's CONTENT on every call (the reference's host may change it behind an unchanged handle). */
 int svr_render_raycasting_bands(svr_u8vec4* img, svr_vec4* outOrNull, const svr_volume* volume,
                                 const svr_transfer_function* tf, const svr_camera* camera, float stepSize,
                                 uint32_t phase, uint32_t stride, uint32_t* bandRows);

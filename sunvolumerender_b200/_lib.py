@@ -143,6 +143,8 @@ SIGNATURES = [
     ("svr_stage_import", C.c_int, [C.POINTER(C.c_ubyte * 64), C.POINTER(C.c_void_p)]),
     ("svr_stage_release", C.c_int, [_P]),
     ("svr_stage_copy", C.c_int, [_P, _P, C.c_uint64, _P]),
+    ("svr_peer_signal", C.c_int, [_P]),
+    ("svr_peer_wait", C.c_int, [_P, C.c_uint32, C.c_uint32]),
     ("svr_volume_invalidate_cache", C.c_int, []),
     ("svr_tf_create", C.c_int, [C.POINTER(TransferFunction), _P, C.c_uint32]),
     ("svr_tf_destroy", C.c_int, [C.POINTER(TransferFunction)]),

@@ -160,7 +160,9 @@ extern "C" int svr_set_device(int device)
     cudaFree(st.dCounters);
     cudaFree(st.dStats);
     cudaFree(st.dFingerprint);
+    cudaFree(st.dTfHash);
     st.dFingerprint = nullptr;
+    st.dTfHash = nullptr;
     st.dStats = nullptr;
     st.autoCell = 0;
     st.dTfSparse = nullptr;

@@ -307,6 +307,22 @@ int launch_fingerprint(HostState& st, int slot)
     return 0;
 }
 
+// 64-bit hash of a transfer-function table: of the linear copy the majorants are built from (tex == 0), or of the live
+// array read through its texture object at the texel centres (where the linear filter returns the texel itself)
+__global__ void tf_hash_kernel(const float4* table, cudaTextureObject_t tex, int n, unsigned long long* out)
+{
+    unsigned long long h = 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float4 v = table ? table[i] : tex1D<float4>(tex, ((float)i + 0.5f) / (float)n);
+        unsigned long long e = ((unsigned long long)__float_as_uint(v.x) << 32 | __float_as_uint(v.y)) * 0x9E3779B97F4A7C15ull;
+        e ^= ((unsigned long long)__float_as_uint(v.z) << 32 | __float_as_uint(v.w)) * 0xC2B2AE3D27D4EB4Full;
+        h += (e ^ (e >> 29)) * ((unsigned long long)i * 2ull + 1ull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
+}
+
 int create_point_view(HostState& st, const cudaResourceDesc& vrd, const cudaChannelFormatDesc& ch)
 {
     if (st.volPointTex) cudaDestroyTextureObject(st.volPointTex);
@@ -467,6 +483,9 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
         SVR_TRY(cudaMemcpy2DFromArrayAsync(st.dTfTable, (size_t)n * sizeof(float4), tarr, 0, 0, (size_t)n * sizeof(float4), 1,
                                            cudaMemcpyDeviceToDevice, st.stream));
         tf_sparse_kernel<<<1, 1024, 0, st.stream>>>(st.dTfTable, n, levels, st.dTfSparse);
+        if (!st.dTfHash) SVR_TRY(cudaMalloc(&st.dTfHash, 2 * sizeof(unsigned long long)));
+        SVR_TRY(cudaMemsetAsync(st.dTfHash, 0, sizeof(unsigned long long), st.stream));
+        tf_hash_kernel<<<1, 256, 0, st.stream>>>(st.dTfTable, 0, n, st.dTfHash);  // of the table these majorants come from
         const int px = st.gridDims.x + 2, py = st.gridDims.y + 2, pz = st.gridDims.z + 2;
         const size_t padded = (size_t)px * py * pz;
         SVR_TRY(cudaMemsetAsync(st.dMajorant, 0, padded * sizeof(float), st.stream));
@@ -479,7 +498,7 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
         dist_axis_kernel<true, false><<<pg, mb, 0, st.stream>>>(nullptr, st.dDist[0], st.dMajorant, px, py, pz, 0, cap);
         dist_axis_kernel<false, false><<<pg, mb, 0, st.stream>>>(st.dDist[0], st.dDist[1], nullptr, px, py, pz, 1, cap);
         dist_axis_kernel<false, true><<<pg, mb, 0, st.stream>>>(st.dDist[1], nullptr, st.dMajorant, px, py, pz, 2, cap);
-        count_launch(6);
+        count_launch(7);
         SVR_TRY(cudaGetLastError());
         if (majorantsRebuilt) *majorantsRebuilt = true;
         st.majorantValid = true;
@@ -534,6 +553,24 @@ static int auto_cell(HostState& st, int current, int* want)
     int e = (int)floor(ideal + 0.5);
     e = e < 2 ? 2 : (e > 5 ? 5 : e);
     *want = 1 << e;
+    return 0;
+}
+
+int tf_content_changed(const svr_transfer_function& tf, bool* changed)
+{
+    HostState& st = state();
+    *changed = true;
+    if (!tf.tex || !st.majorantValid || !st.dTfHash || !st.tfEntries) return 0;
+    cudaResourceDesc trd;
+    SVR_TRY(cudaGetTextureObjectResourceDesc(&trd, tf.tex));
+    if (trd.resType != cudaResourceTypeArray || trd.res.array.array != st.majorantTfArray) return 0;
+    SVR_TRY(cudaMemsetAsync(st.dTfHash + 1, 0, sizeof(unsigned long long), st.stream));
+    tf_hash_kernel<<<1, 256, 0, st.stream>>>(nullptr, tf.tex, st.tfEntries, st.dTfHash + 1);
+    count_launch();
+    unsigned long long h[2] = {0, 1};
+    SVR_TRY(cudaMemcpyAsync(h, st.dTfHash, sizeof(h), cudaMemcpyDeviceToHost, st.stream));
+    SVR_TRY(cudaStreamSynchronize(st.stream));
+    *changed = h[0] != h[1];
     return 0;
 }
 

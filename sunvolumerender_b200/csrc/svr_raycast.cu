@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ De
 }
 
 int launch_raycast(uint32_t* img, float4* outf, const svr_volume* volume, const svr_transfer_function* tf,
-                   const svr_camera* camera, float stepSize, uint32_t y0, uint32_t y1, uint32_t bandPhase = 0, uint32_t bandStride = 1)
+                   const svr_camera* camera, float stepSize, uint32_t y0, uint32_t y1, uint32_t bandPhase = 0, uint32_t bandStride = 1,
+                   bool checkTfContent = false)
 {
     HostState& st = state();
     if (!volume || !tf || !camera) return fail_msg("render_raycasting: null scene argument");
@@ -130,8 +131,18 @@ int launch_raycast(uint32_t* img, float4* outf, const svr_volume* volume, const 
     const bool skip = st.options[SVR_OPT_RC_SKIP] != 0;
     const bool count = st.options[SVR_OPT_COUNTERS] != 0;
     if (skip) {
-        // the TF content may have changed behind the same handles: refresh the majorants every call
-        int rc = ensure_grid(&sc, /*force=*/true, /*maxAutoCell=*/8);
+        // Empty-space skipping needs majorants of the CURRENT table.  Edits that go through setup_transferfunction /
+        // svr_tf_upload, and any change of handle, invalidate them (svr_macrocell.cu).  The reference's own host can also
+        // put new contents behind an unchanged handle without telling anybody (gui/transferfunction.cpp:128-151 destroys and
+        // re-creates the texture; render_raycasting gets the struct by reference): the drop-in entry point therefore
+        // compares a hash of the live table with the hash of the table the majorants came from -- one small launch instead
+        // of the six-launch rebuild it used to force on every frame -- and rebuilds only on a difference.
+        bool changed = false;
+        if (checkTfContent) {
+            int rc = tf_content_changed(sc.tf, &changed);
+            if (rc) return rc;
+        }
+        int rc = ensure_grid(&sc, /*force=*/changed, /*maxAutoCell=*/8);
         if (rc) return rc;
     } else {
         memset(&sc.grid, 0, sizeof(sc.grid));
@@ -167,7 +178,8 @@ using namespace svr;
 extern "C" void render_raycasting(svr_u8vec4* img, svr_volume* volume, svr_transfer_function* transferFunction,
                                   svr_camera* camera, float stepSize)
 {
-    int rc = launch_raycast((uint32_t*)img, nullptr, volume, transferFunction, camera, stepSize, 0, camera ? camera->imageH : 0);
+    int rc = launch_raycast((uint32_t*)img, nullptr, volume, transferFunction, camera, stepSize, 0, camera ? camera->imageH : 0, 0, 1,
+                            /*checkTfContent=*/true);
     if (rc) {
         fprintf(stderr, "CUDA error at %s:%d code=%d \"%s\" \n", __FILE__, __LINE__, rc, svr_last_error());
         cudaDeviceReset();
@@ -194,4 +206,51 @@ extern "C" int svr_render_raycasting_bands(svr_u8vec4* img, svr_vec4* outOrNull,
 {
     if (bandRows) *bandRows = (uint32_t)state().options[SVR_OPT_RC_BLOCK] / 16u;
     return launch_raycast((uint32_t*)img, (float4*)outOrNull, volume, tf, camera, stepSize, 0, camera ? camera->imageH : 0, phase, stride);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Completion flags between the GPUs of a box: a rank that has rendered its bands straight into another rank's image
+// (a peer mapping of that rank's buffer, svr_stage_export / svr_stage_import) raises the owner's flag, the owner's stream
+// waits for all of them -- no collective, no host in the loop.
+// ------------------------------------------------------------------------------------------------
+namespace svr_peer {
+__global__ void peer_signal_kernel(unsigned int* flag)
+{
+    __threadfence_system();  // this stream's earlier writes into the peer's memory are visible before the flag moves
+    atomicAdd_system(flag, 1u);
+}
+
+__global__ void peer_wait_kernel(volatile unsigned int* flag, unsigned int expected, unsigned long long timeoutNs)
+{
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int)(flag[0] - expected) < 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeoutNs) {
+            flag[1] = 1u;  // gave up: a peer never signalled (the caller reads this word)
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+}  // namespace svr_peer
+
+extern "C" int svr_peer_signal(void* peer_flag)
+{
+    if (!peer_flag) return fail_msg("svr_peer_signal: null flag");
+    svr_peer::peer_signal_kernel<<<1, 1, 0, state().stream>>>((unsigned int*)peer_flag);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svr_peer_wait(void* flag, uint32_t expected, uint32_t timeout_ms)
+{
+    if (!flag) return fail_msg("svr_peer_wait: null flag");
+    svr_peer::peer_wait_kernel<<<1, 1, 0, state().stream>>>((volatile unsigned int*)flag, expected, (unsigned long long)timeout_ms * 1000000ull);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
 }

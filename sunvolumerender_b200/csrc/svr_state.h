@@ -41,6 +41,7 @@ struct HostState {
     bool majorantValid = false;           // false after setup_volume/setup_transferfunction
     float majorantDensityScale = 0.f;
     cudaArray_t majorantTfArray = nullptr;
+    unsigned long long* dTfHash = nullptr;  // [0] hash of the TF table the majorants were built from, [1] scratch
 
     // automatic macrocell size (SVR_OPT_MACROCELL_SIZE = 0): the choice and the scene it was made for
     int autoCell = 0;
@@ -88,6 +89,11 @@ int fail_msg(const char* msg);
 // `maxAutoCell` caps the automatic cell size: delta tracking through a thin medium wants large cells, the
 // ray caster (which only skips empty space with the grid) never gains from cells above 8 voxels.
 int ensure_grid(DevScene* scene, bool force, int maxAutoCell = 32);
+
+// true when the transfer-function table behind `tf` differs from the one the majorants were built from (one small
+// launch + an 16-byte read-back; the ray caster's drop-in entry point, whose host may edit the table behind an unchanged
+// handle, gui/transferfunction.cpp:128-151).  Also true when no majorants exist yet.
+int tf_content_changed(const svr_transfer_function& tf, bool* changed);
 
 inline void count_launch(int n = 1) { state().launches += (unsigned long long)n; }
 

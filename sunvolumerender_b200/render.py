@@ -245,12 +245,13 @@ class Renderer:
             "svr_render_raycasting_rows",
         )
 
-    def render_raycasting_bands(self, phase, stride, step_size=None, out=None):
-        """Row bands phase, phase + stride, ... of the u8 image (the balanced multi-GPU split); returns the band height."""
+    def render_raycasting_bands(self, phase, stride, step_size=None, out=None, img_ptr=None):
+        """Row bands phase, phase + stride, ... of the u8 image (the balanced multi-GPU split); returns the band height.
+        img_ptr: a raw device pointer to render into instead of self.img (e.g. a peer mapping of another rank's image)."""
         if step_size is None:
             step_size = S.raycast_step_size(self.volume.spacing.tuple())
         rows = C.c_uint32(0)
-        L.check(self.lib.svr_render_raycasting_bands(_ptr(self.img), _ptr(out), C.byref(self.volume), C.byref(self.tf), C.byref(self.camera), step_size,
+        L.check(self.lib.svr_render_raycasting_bands(img_ptr if img_ptr is not None else _ptr(self.img), _ptr(out), C.byref(self.volume), C.byref(self.tf), C.byref(self.camera), step_size,
                                                      phase, stride, C.byref(rows)), "svr_render_raycasting_bands")
         return int(rows.value)
 

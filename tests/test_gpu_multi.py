@@ -1,5 +1,6 @@
 """Two-GPU tests (skipped on a one-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`):
-the sample split + NCCL sum-reduce of bench.py against a single-GPU render of the same samples, and
+the sample split + NCCL sum-reduce of bench.py against a single-GPU render of the same samples, the ray caster's
+row bands written by both ranks into rank 0's image through peer mappings (distributed.PeerFrame), and
 render.VolumeStream's three fan-outs (copy-engine pushes into peer-mapped staging buffers, NCCL broadcast, one
 upload per rank) against direct uploads."""
 import os
@@ -98,6 +99,24 @@ def _worker(rank, world_size, port, out_dir):
         if rank == 0:
             np.save(os.path.join(out_dir, "fanouts.npy"), np.array([used[k] for k in ("p2p", "nvlink", "pcie")]))
         dist.barrier()
+
+        # ---- ray casting split into row bands, every rank writing STRAIGHT into rank 0's image (distributed.PeerFrame)
+        r.upload_volume(frames[0])
+        r.set_transfer_function(S.tf_table("thin"))
+        r.render_raycasting()
+        torch.cuda.synchronize()
+        whole = r.ldr_image().clone()
+        pf = D.PeerFrame(r, W * H * 4)
+        for it in range(3):   # three frames into the same buffer, separated by barriers
+            r.render_raycasting_bands(rank, world_size, img_ptr=pf.img_ptr)
+            pf.frame_done()
+            torch.cuda.synchronize()
+            if rank == 0:
+                assert torch.equal(pf.image().view(H, W, 4), whole), it
+            dist.barrier()
+        pf.close()
+        if rank == 0:
+            np.save(os.path.join(out_dir, "peer_frame_ok.npy"), np.array([1]))
     finally:
         dist.destroy_process_group()
 
@@ -114,3 +133,4 @@ def test_two_gpu_split_and_volume_stream(tmp_path):
     assert single.mean() > 0
     used = list(np.load(tmp_path / "fanouts.npy"))
     assert used[1:] == ["nvlink", "pcie"] and used[0] in ("p2p", "nvlink")  # p2p falls back where CUDA IPC is unavailable
+    assert os.path.exists(tmp_path / "peer_frame_ok.npy")

@@ -391,3 +391,60 @@ def test_reference_arm_scene_builder_makes_the_same_scene_without_the_product_li
         assert float(imgs[0].max()) > 0 and torch.equal(imgs[0], imgs[1])
     finally:
         rs.close()
+
+
+def test_raycaster_notices_a_table_edited_behind_an_unchanged_handle(renderer):
+    """The reference's host re-creates the transfer-function texture on every edit (gui/transferfunction.cpp:128-151) and
+    hands render_raycasting the struct by reference: new contents can sit behind the handle the majorants were built for.
+    The drop-in entry point compares the table's hash on every call (one small launch) and rebuilds on a difference."""
+    rt = _cudart()
+    rt.cudaMemcpy2DToArray.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+    cfg = small_config(n=64, w=96, h=96, gen=L.GEN_CT, fmt=L.VOXEL_U16, tf="default")
+    setup(renderer, cfg)
+    r = renderer
+    r.render_raycasting()
+    torch.cuda.synchronize()
+    before = r.ldr_image().clone()
+    launches0 = r.launch_count()
+    r.render_raycasting()
+    torch.cuda.synchronize()
+    assert r.launch_count() - launches0 == 2          # unchanged table: the hash check + the ray-cast kernel, no rebuild
+    assert torch.equal(r.ldr_image(), before)
+    # new contents behind the same array and texture object, without telling the library: air becomes fog
+    table = S.tf_table("thin").copy()
+    table[:, 3] = np.maximum(table[:, 3], 0.01)
+    desc = (C.c_uint64 * 8)()
+    assert rt.cudaGetTextureObjectResourceDesc(desc, r.tf.tex) == 0
+    assert rt.cudaMemcpy2DToArray(C.c_void_p(desc[1]), 0, 0, C.c_void_p(table.ctypes.data), table.shape[0] * 16, table.shape[0] * 16, 1, 1) == 0
+    r.tf.maxOpacity = float(table[:, 3].max())
+    r.render_raycasting()
+    torch.cuda.synchronize()
+    edited = r.ldr_image().clone()
+    assert not torch.equal(edited, before)
+    # ground truth: the same table through the announced path, and without empty-space skipping at all
+    r.set_transfer_function(table)
+    r.render_raycasting()
+    torch.cuda.synchronize()
+    assert torch.equal(r.ldr_image(), edited)
+    r.set_option(L.OPT_RC_SKIP, 0)
+    r.render_raycasting()
+    torch.cuda.synchronize()
+    assert torch.equal(r.ldr_image(), edited)
+    r.set_option(L.OPT_RC_SKIP, 1)
+
+
+def test_peer_frame_on_one_gpu_is_the_plain_image(renderer):
+    """distributed.PeerFrame with a single rank: bands rendered into the stage buffer, frame_done a no-op."""
+    from sunvolumerender_b200 import distributed as D
+
+    cfg = small_config(n=48, w=80, h=64, gen=L.GEN_CT, fmt=L.VOXEL_U16, tf="thin")
+    setup(renderer, cfg)
+    renderer.render_raycasting()
+    torch.cuda.synchronize()
+    whole = renderer.ldr_image().clone()
+    pf = D.PeerFrame(renderer, cfg.width * cfg.height * 4)
+    for phase in range(3):   # three "ranks" one after the other on this GPU
+        renderer.render_raycasting_bands(phase, 3, img_ptr=pf.img_ptr)
+    pf.frame_done()
+    assert torch.equal(pf.image().view(cfg.height, cfg.width, 4), whole)
+    pf.close()
