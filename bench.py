@@ -225,12 +225,18 @@ def timed_steps(fn, steps, warmup, barrier, dev):
 
 
 def strong_scaling_line(r, a, cfg, sum_buf, rank, world, dev, barrier):
-    """north_star's multi-GPU split: the workload's spp DIVIDED over the GPUs (C3: 256 / N per GPU), one NCCL sum-reduce
-    of the float4 accumulators onto rank 0, resolve there -- everything inside the timed region.  The speed-up over one
-    GPU is computed by whoever reads the N = 1 line; the parts are reported so that the limiter can be named."""
+    """north_star's multi-GPU split of ONE frame (C3: 256 spp per pixel in all), everything inside the timed region, two ways:
+      samples  the spp divided over the GPUs (256 / N each), one NCCL sum-reduce of the float4 accumulators onto rank 0,
+               resolve there;
+      bands    the IMAGE divided: row bands dealt out round robin, every GPU renders all 256 spp of its pixels straight into
+               rank 0's accumulator through peer mappings over NVLink (svr_pathtracer_accumulate_bands + distributed.PeerFrame:
+               no collective), rank 0 resolves.  Per-pixel set-up is divided as well, and the frame is bit-identical to the
+               single-GPU frame (checked here).
+    The speed-up over one GPU is computed by whoever reads the N = 1 line."""
     import torch
     import torch.distributed as dist
 
+    from sunvolumerender_b200 import distributed as D
     from sunvolumerender_b200 import scene as S
 
     spp = a.spp or cfg.spp
@@ -254,19 +260,52 @@ def strong_scaling_line(r, a, cfg, sum_buf, rank, world, dev, barrier):
     ms = timed_steps(step, a.steps, max(a.warmup, 3), barrier, dev)
     ms_render = timed_steps(lambda: step(True, False), max(3, a.steps // 2), 1, barrier, dev)
     ms_reduce = timed_steps(lambda: step(False, True), max(3, a.steps // 2), 1, barrier, dev)
-    return {"workload": f"{cfg.name}: {spp} spp split over {world} GPUs ({count} per GPU on this rank), NCCL sum-reduce of {npix * 16 / 1e6:.1f} MB float4 "
-                        f"accumulators + resolve on rank 0 inside the timed region",
-            "scaling": "strong", "value": npix * spp / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "spp_total": spp,
-            "ms_render_only": ms_render, "ms_reduce_and_resolve_only": ms_reduce,
-            "limiter": "render time shrinks with N, the reduce of the full-frame accumulator and the resolve do not"}
+    line = {"workload": f"{cfg.name}: ONE frame of {spp} spp on {world} GPUs, device-resident, assembly and resolve on rank 0 inside the timed region",
+            "scaling": "strong", "unit": UNIT, "spp_total": spp,
+            "split_samples": {"value": npix * spp / (ms * 1e-3), "ms_per_step": ms, "spp_per_gpu": count, "ms_render_only": ms_render,
+                              "ms_reduce_and_resolve_only": ms_reduce, "exchange": f"NCCL sum-reduce of {npix * 16 / 1e6:.1f} MB float4 accumulators",
+                              "limiter": "the per-pixel set-up (classification, accumulator pass) is paid by every GPU for every pixel: render time does not shrink like 1/N"}}
+    try:
+        pf = D.PeerFrame(r, npix * 16)
+        gb = [0]
+
+        def step_bands():
+            base = gb[0] * spp
+            gb[0] += 1
+            r.accumulate_bands(pf.img_ptr, cfg.trace_depth, base, spp, rank, world, clear=True)
+            pf.frame_done()
+            if rank == 0:
+                r.resolve(pf.img_ptr)
+            dist.barrier()  # the next frame goes into the same buffer (a real host would double-buffer; the barrier is timed)
+
+        ms_b = timed_steps(step_bands, a.steps, max(a.warmup, 3), barrier, dev)
+        same = None
+        if rank == 0:   # the last frame against the same samples on one GPU
+            assembled = r.hdr.clone()
+            r.accumulate(sum_buf, cfg.trace_depth, (gb[0] - 1) * spp, spp, clear=True)
+            r.resolve(sum_buf)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(assembled, r.hdr))
+        barrier()
+        pf.close()
+        line["split_bands"] = {"value": npix * spp / (ms_b * 1e-3), "ms_per_step": ms_b, "exchange": "peer writes into rank 0's accumulator, completion flags, no collective "
+                               "(+ one barrier per frame, timed, because frames share the buffer)", "equals_single_gpu_frame": same}
+    except Exception as e:  # no peer access between these GPUs
+        line["split_bands"] = {"unavailable": str(e)}
+    best = max((v for v in (line["split_samples"], line["split_bands"]) if "value" in v), key=lambda v: v["value"])
+    line["value"], line["ms_per_step"] = best["value"], best["ms_per_step"]
+    line["split"] = "bands" if best is line["split_bands"] else "samples"
+    return line
 
 
 def c5_line(r, a, rank, world, dev, barrier):
     """BASELINE.json configs[4]: 2048^3 u16 (16 GiB, replicated on every GPU), 3840x2160, 1024 spp split across the GPUs of the
-    box with one NCCL reduce of the accumulation buffers.  Run when the box has 8 GPUs (or --c5) and the memory for it."""
+    box with one NCCL reduce of the accumulation buffers; and the same frame with the image split instead (row bands, peer
+    writes, see strong_scaling_line).  Run when the box has 8 GPUs (or --c5) and the memory for it."""
     import torch
     import torch.distributed as dist
 
+    from sunvolumerender_b200 import distributed as D
     from sunvolumerender_b200 import scene as S
     from sunvolumerender_b200.render import setup_config
 
@@ -296,10 +335,31 @@ def c5_line(r, a, rank, world, dev, barrier):
 
     ms = timed_steps(step, 3, 2, barrier, dev)
     nz = float((r.ldr_image()[..., :3] > 0).float().mean()) if rank == 0 else None
-    line = {"workload": f"C5: 2048^3 u16 (16 GiB replicated), {W}x{H}, {spp} spp split over {world} GPUs ({count} per GPU), NCCL sum-reduce of "
-                        f"{W * H * 16 / 1e6:.0f} MB accumulators + resolve inside the timed region, device-resident, 3 steps",
-            "scaling": "strong", "value": W * H * spp / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "macrocell": grid_cell(r),
-            "image_nonzero_fraction": nz}
+    line = {"workload": f"C5: 2048^3 u16 (16 GiB replicated), {W}x{H}, ONE frame of {spp} spp on {world} GPUs, device-resident, assembly + resolve on rank 0 inside "
+                        f"the timed region, 3 steps",
+            "scaling": "strong", "unit": UNIT, "macrocell": grid_cell(r), "image_nonzero_fraction": nz,
+            "split_samples": {"value": W * H * spp / (ms * 1e-3), "ms_per_step": ms, "spp_per_gpu": count, "exchange": f"NCCL sum-reduce of {W * H * 16 / 1e6:.0f} MB accumulators"}}
+    try:
+        pf = D.PeerFrame(r, W * H * 16)
+        gb = [0]
+
+        def step_bands():
+            base = gb[0] * spp
+            gb[0] += 1
+            r.accumulate_bands(pf.img_ptr, cfg.trace_depth, base, spp, rank, world, clear=True)
+            pf.frame_done()
+            if rank == 0:
+                r.resolve(pf.img_ptr)
+            dist.barrier()
+
+        ms_b = timed_steps(step_bands, 3, 2, barrier, dev)
+        pf.close()
+        line["split_bands"] = {"value": W * H * spp / (ms_b * 1e-3), "ms_per_step": ms_b, "exchange": "peer writes into rank 0's accumulator, completion flags, one barrier per frame"}
+    except Exception as e:
+        line["split_bands"] = {"unavailable": str(e)}
+    best = max((v for v in (line["split_samples"], line["split_bands"]) if "value" in v), key=lambda v: v["value"])
+    line["value"], line["ms_per_step"] = best["value"], best["ms_per_step"]
+    line["split"] = "bands" if best is line["split_bands"] else "samples"
     del buf
     setup_config(r, S.CONFIGS["C1"])  # drop the 16 GiB array
     torch.cuda.empty_cache()

@@ -147,6 +147,15 @@ int svr_render_pathtracer_spp(svr_u8vec4* img, const svr_render_params* renderPa
  * root calls svr_pathtracer_resolve: hdr = rgb / w (optional packed-vec3 output) and the
  * tone-mapped image (tonemapping.h:13-27), fused in one pass. */
 int svr_pathtracer_accumulate(svr_vec4* sum, uint32_t traceDepth, uint32_t firstSample, uint32_t nSamples, int clear);
+/* The IMAGE split of the multi-GPU path tracer ("interleaved image tiles, no reduce needed, only a
+ * gather"): as svr_pathtracer_accumulate, for the row bands phase, phase + stride, ... only (bands of *bandRows rows, the
+ * chosen kernel's block height, counted from row 0); rank r of N passes (r, N).  Pixels outside the call's bands are not
+ * touched, so N ranks writing into ONE buffer (peer mappings of rank 0's buffer, svr_stage_*, svr_peer_*) assemble the frame
+ * without a reduce, and every pixel's samples are summed by one GPU in the single-GPU order: the frame is bit-identical to
+ * a single-GPU render.  Preferable to the sample split when there are few samples per GPU (per-pixel set-up is divided
+ * too). */
+int svr_pathtracer_accumulate_bands(svr_vec4* sum, uint32_t traceDepth, uint32_t firstSample, uint32_t nSamples, int clear,
+                                    uint32_t phase, uint32_t stride, uint32_t* bandRows);
 int svr_pathtracer_resolve(svr_u8vec4* img, svr_vec3* hdrOut, const svr_vec4* sum);
 
 /* Staging buffers for streaming volumes to replicated scenes (the volume is replicated

@@ -129,6 +129,7 @@ SIGNATURES = [
     ("svr_get_option", C.c_int, [C.c_int]),
     ("svr_render_pathtracer_spp", C.c_int, [_P, C.POINTER(RenderParams), C.c_uint32]),
     ("svr_pathtracer_accumulate", C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+    ("svr_pathtracer_accumulate_bands", C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("svr_pathtracer_resolve", C.c_int, [_P, _P, _P]),
     ("svr_render_raycasting_f32", C.c_int, [_P, C.POINTER(Volume), C.POINTER(TransferFunction), C.POINTER(Camera), C.c_float]),
     ("svr_render_raycasting_rows", C.c_int, [_P, _P, C.POINTER(Volume), C.POINTER(TransferFunction), C.POINTER(Camera), C.c_float, C.c_uint32, C.c_uint32]),

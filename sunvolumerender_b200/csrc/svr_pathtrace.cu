@@ -68,6 +68,8 @@ struct PtLaunch {
     int32_t warpPixels;    // sample-parallel kernel: pixels one warp renders one after the other
     int32_t lightCull;     // 1 = classify_pixel may rule out camera-ray light hits (SVR_OPT_PT_LIGHT_CULL)
     int32_t clipped;       // some clip plane is active: the volume's box is smaller than its texture
+    uint32_t bandRows;               // (out) rows per band of the kernel shape chosen
+    uint32_t bandPhase, bandStride;  // this launch renders the row bands (block rows) phase, phase + stride, ... (1 GPU: 0, 1)
 };
 
 template <int MODE>
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idx = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 4) + (warp >> 1) * 4u + (lane >> 3);
+    const uint32_t idy = a.y0 + (blockIdx.y * a.bandStride + a.bandPhase) * (blockDim.x >> 4) + (warp >> 1) * 4u + (lane >> 3);
     const bool inside = idx < s.cam.imageW && idy < a.y1;
     LocalCounters<COUNT> lc;
     if (inside) {
@@ -686,7 +688,7 @@ template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtrace_warp_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 5) + warp;
+    const uint32_t idy = a.y0 + (blockIdx.y * a.bandStride + a.bandPhase) * (blockDim.x >> 5) + warp;
     LocalCounters<COUNT> lc;
     if (idy < a.y1) {
         PathState<MODE> ps;
@@ -782,7 +784,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_QUEUE_BLOCKS) patht
     constexpr int MODE = 2;
     __shared__ float queues[SVR_PT_MAX_THREADS / 32][SVR_QUEUE_WORDS * SVR_QUEUE_CAP];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 5) + warp;
+    const uint32_t idy = a.y0 + (blockIdx.y * a.bandStride + a.bandPhase) * (blockDim.x >> 5) + warp;
     float* q = queues[warp];
     LocalCounters<COUNT> lc;
     if (idy < a.y1) {
@@ -1063,7 +1065,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_PROFILE_BLOCKS) pat
     __shared__ float queues[SVR_PT_MAX_THREADS / 32][SVR_QUEUE_WORDS * SVR_QUEUE_CAP];
     __shared__ float profiles[SVR_PT_MAX_THREADS / 32][SVR_PROF_FLOATS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 5) + warp;
+    const uint32_t idy = a.y0 + (blockIdx.y * a.bandStride + a.bandPhase) * (blockDim.x >> 5) + warp;
     float* q = queues[warp];
     float* C = profiles[warp] + SVR_PROF_C;
     float* M = profiles[warp] + SVR_PROF_M;
@@ -1310,7 +1312,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idx = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t idy = a.y0 + blockIdx.y * (blockDim.x >> 4) + (warp >> 1) * 4u + (lane >> 3);
+    const uint32_t idy = a.y0 + (blockIdx.y * a.bandStride + a.bandPhase) * (blockDim.x >> 4) + (warp >> 1) * 4u + (lane >> 3);
     const bool inside = idx < s.cam.imageW && idy < a.y1;
     const uint32_t offset = idy * s.cam.imageW + idx;
     LocalCounters<COUNT> lc;
@@ -1455,7 +1457,7 @@ void launch_mode(int shape, dim3 grid, int block, cudaStream_t stream, const Dev
     }
 }
 
-int launch_pathtrace(PtLaunch a)
+int launch_pathtrace(PtLaunch& a)
 {
     HostState& st = state();
     DevScene sc = st.scene;
@@ -1504,7 +1506,12 @@ int launch_pathtrace(PtLaunch a)
         tileW = (uint32_t)a.warpPixels;
         tileH = (uint32_t)block / 32u;
     }
-    dim3 grid((sc.cam.imageW + tileW - 1u) / tileW, ((a.y1 - a.y0) + tileH - 1u) / tileH);
+    if (a.bandStride == 0) a.bandStride = 1;
+    if (a.bandPhase >= a.bandStride) return fail_msg("render_pathtracer: band phase must be below the band stride");
+    const uint32_t bands = ((a.y1 - a.y0) + tileH - 1u) / tileH;
+    if (a.bandPhase >= bands) return 0;
+    a.bandRows = tileH;
+    dim3 grid((sc.cam.imageW + tileW - 1u) / tileW, (bands - a.bandPhase + a.bandStride - 1u) / a.bandStride);
     switch (mode) {
         case 0: launch_mode<0>(shape, grid, block, st.stream, sc, a, cnt); break;
         case 1: launch_mode<1>(shape, grid, block, st.stream, sc, a, cnt); break;
@@ -1568,6 +1575,26 @@ extern "C" int svr_pathtracer_accumulate(svr_vec4* sum, uint32_t traceDepth, uin
     a.sum = (float4*)sum;
     a.clearSum = clear;
     return launch_pathtrace(a);
+}
+
+extern "C" int svr_pathtracer_accumulate_bands(svr_vec4* sum, uint32_t traceDepth, uint32_t firstSample, uint32_t nSamples, int clear,
+                                               uint32_t phase, uint32_t stride, uint32_t* bandRows)
+{
+    if (!sum) return fail_msg("svr_pathtracer_accumulate_bands: sum is null");
+    PtLaunch a;
+    memset(&a, 0, sizeof(a));
+    a.traceDepth = traceDepth;
+    a.firstSample = firstSample;
+    a.nSamples = nSamples;
+    a.y0 = 0;
+    a.y1 = 0xffffffffu;
+    a.sum = (float4*)sum;
+    a.clearSum = clear;
+    a.bandPhase = phase;
+    a.bandStride = stride;
+    int rc = launch_pathtrace(a);
+    if (bandRows) *bandRows = a.bandRows;
+    return rc;
 }
 
 extern "C" int svr_pathtracer_resolve(svr_u8vec4* img, svr_vec3* hdrOut, const svr_vec4* sum)

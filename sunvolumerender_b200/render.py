@@ -228,8 +228,18 @@ class Renderer:
     def accumulate(self, sum_buf, trace_depth, first_sample, n_samples, clear=True):
         L.check(self.lib.svr_pathtracer_accumulate(_ptr(sum_buf), trace_depth, first_sample, n_samples, 1 if clear else 0), "svr_pathtracer_accumulate")
 
+    def accumulate_bands(self, sum_buf, trace_depth, first_sample, n_samples, phase, stride, clear=True):
+        """The image split: this rank's row bands (phase, phase + stride, ...) of the float4 sum buffer -- a tensor or a raw
+        device pointer (e.g. distributed.PeerFrame.img_ptr, a peer mapping of rank 0's buffer).  Returns the band height."""
+        rows = C.c_uint32(0)
+        ptr = sum_buf if isinstance(sum_buf, C.c_void_p) else _ptr(sum_buf)
+        L.check(self.lib.svr_pathtracer_accumulate_bands(ptr, trace_depth, first_sample, n_samples, 1 if clear else 0, phase, stride, C.byref(rows)),
+                "svr_pathtracer_accumulate_bands")
+        return int(rows.value)
+
     def resolve(self, sum_buf, want_hdr=True):
-        L.check(self.lib.svr_pathtracer_resolve(_ptr(self.img), _ptr(self.hdr if want_hdr else None), _ptr(sum_buf)), "svr_pathtracer_resolve")
+        ptr = sum_buf if isinstance(sum_buf, C.c_void_p) else _ptr(sum_buf)
+        L.check(self.lib.svr_pathtracer_resolve(_ptr(self.img), _ptr(self.hdr if want_hdr else None), ptr), "svr_pathtracer_resolve")
 
     def render_raycasting(self, step_size=None):
         if step_size is None:

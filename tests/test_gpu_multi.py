@@ -115,6 +115,21 @@ def _worker(rank, world_size, port, out_dir):
                 assert torch.equal(pf.image().view(H, W, 4), whole), it
             dist.barrier()
         pf.close()
+
+        # ---- the path tracer's IMAGE split: both ranks render all samples of their row bands straight into rank 0's
+        # accumulator; the frame is the single-GPU frame bit for bit
+        r.set_transfer_function(S.tf_table("default"))
+        pf = D.PeerFrame(r, W * H * 16)
+        r.accumulate_bands(pf.img_ptr, DEPTH, 0, SPP, rank, world_size, clear=True)
+        pf.frame_done()
+        torch.cuda.synchronize()
+        if rank == 0:
+            got = pf.image().view(torch.float32)
+            r.accumulate(buf, DEPTH, 0, SPP, clear=True)
+            torch.cuda.synchronize()
+            assert torch.equal(got, buf)
+        dist.barrier()
+        pf.close()
         if rank == 0:
             np.save(os.path.join(out_dir, "peer_frame_ok.npy"), np.array([1]))
     finally:

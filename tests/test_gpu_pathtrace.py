@@ -584,3 +584,29 @@ def test_scene_parameters_reach_the_path_tracer(renderer, variant):
     assert (np.abs(renderer.ldr_image().cpu().numpy().astype(int) - ref.ldr_image().cpu().numpy().astype(int)).max(axis=2) <= 1).mean() >= 0.998
     del ref
     _statistical_parity(renderer, cfg, depth, 8, 32, lambda: renderer.set_option(L.OPT_PT_MODE, 2), mean_tol=0.02)
+
+
+def test_row_bands_assemble_to_the_single_launch_frame(renderer):
+    """The image split of the multi-GPU path tracer (svr_pathtracer_accumulate_bands): bands rendered by separate launches
+    into one buffer are the full-frame launch bit for bit, for every kernel shape; pixels outside a launch's bands are not
+    touched."""
+    cfg = small_config(n=64, w=150, h=101, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=2)
+    setup(renderer, cfg)
+    W, H = cfg.width, cfg.height
+    for shape, spp, stride in ((2, 40, 3), (1, 5, 4), (3, 40, 2), (0, 3, 5)):
+        renderer.set_option(L.OPT_PT_KERNEL, shape)
+        renderer.set_option(L.OPT_PT_QUEUE_MIN_DEPTH, 0)
+        whole = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
+        renderer.accumulate(whole, 2, 7, spp, clear=True)
+        parts = torch.full((H * W * 4,), -1.0, dtype=torch.float32, device="cuda")
+        rows = None
+        for phase in range(stride):
+            rows = renderer.accumulate_bands(parts, 2, 7, spp, phase, stride, clear=True)
+            if phase == 0:   # only this launch's bands have been written
+                torch.cuda.synchronize()
+                v = parts.view(H, W, 4)
+                band = (torch.arange(H, device="cuda") // rows) % stride
+                assert bool((v[band != 0] == -1.0).all()) and bool((v[band == 0][..., 3] == spp).all())
+        torch.cuda.synchronize()
+        assert rows in (4, 8)
+        assert torch.equal(parts, whole), shape
