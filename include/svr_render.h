@@ -90,7 +90,8 @@ enum svr_option {
      * the same pixel), 1 = megakernel (one pixel per lane, samples one after the other),
      * 0 = phase-scheduled warp (generate / march / collide / event / bounce phases, the warp
      * votes each round and runs the phase most lanes wait in), 3 = sample-parallel warp with the scatter
-     * queue at every depth (see SVR_OPT_PT_QUEUE_MIN_DEPTH), 4 = majorant-profile kernel (see SVR_OPT_PT_PROFILE) */
+     * queue at every depth (see SVR_OPT_PT_QUEUE_MIN_DEPTH), 4 = majorant-profile kernel (see SVR_OPT_PT_PROFILE),
+     * 5 = ray pool + event queue per warp: lanes take rays and scatter events from per-warp queues instead of owning a path */
     SVR_OPT_PT_KERNEL = 9,
     /* phase-scheduled kernel: macrocell visits per MARCH round (0 = default 4) */
     SVR_OPT_PT_ROUNDS = 10,
@@ -128,6 +129,9 @@ enum svr_option {
     SVR_OPT_PT_PROFILE = 18,
     /* shape 4: idle lanes take the pixel's next camera samples together once this many lanes wait (1..32, 0 = default 8) */
     SVR_OPT_PT_REFILL = 19,
+    /* kernel shape 5 (ray pool + event queue per warp, SVR_OPT_PT_KERNEL = 5): pixels in a warp's run (1..16, 0 = default 16);
+     * rays of all of them share the warp's pool */
+    SVR_OPT_PT_POOL_PIXELS = 20,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

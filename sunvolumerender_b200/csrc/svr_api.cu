@@ -43,7 +43,7 @@ HostState& state()
         static const struct { const char* name; int key, lo, hi; } kEnv[] = {
             {"SVR_PT_MODE", SVR_OPT_PT_MODE, 0, 2},           {"SVR_SHADOW_ESTIMATOR", SVR_OPT_SHADOW_ESTIMATOR, 0, 1},
             {"SVR_ENV_ENABLED", SVR_OPT_ENV_ENABLED, 0, 1},   {"SVR_RC_SKIP", SVR_OPT_RC_SKIP, 0, 1},
-            {"SVR_SEED", SVR_OPT_SEED, INT32_MIN, INT32_MAX}, {"SVR_PT_KERNEL", SVR_OPT_PT_KERNEL, 0, 4},
+            {"SVR_SEED", SVR_OPT_SEED, INT32_MIN, INT32_MAX}, {"SVR_PT_KERNEL", SVR_OPT_PT_KERNEL, 0, 5},
         };
         for (const auto& e : kEnv) {
             const char* v = getenv(e.name);
@@ -197,7 +197,7 @@ extern "C" int svr_set_option(int key, int value)
             if (value != 64 && value != 128 && value != 256) return fail_msg("block size must be 64, 128 or 256");
             break;
         case SVR_OPT_PT_KERNEL:
-            if (value < 0 || value > 4) return fail_msg("SVR_OPT_PT_KERNEL must be 0, 1, 2, 3 or 4");
+            if (value < 0 || value > 5) return fail_msg("SVR_OPT_PT_KERNEL must be 0 .. 5");
             break;
         case SVR_OPT_PT_WARP_PIXELS:
             if (value < 1 || value > 64) return fail_msg("SVR_OPT_PT_WARP_PIXELS must be in 1..64");
@@ -207,6 +207,9 @@ extern "C" int svr_set_option(int key, int value)
             break;
         case SVR_OPT_PT_QUEUE_MIN_DEPTH:
             if (value < 0) return fail_msg("SVR_OPT_PT_QUEUE_MIN_DEPTH must be >= 0");
+            break;
+        case SVR_OPT_PT_POOL_PIXELS:
+            if (value < 0 || value > 16) return fail_msg("SVR_OPT_PT_POOL_PIXELS must be in 0..16");
             break;
         case SVR_OPT_PT_REFILL:
             if (value < 0 || value > 32) return fail_msg("SVR_OPT_PT_REFILL must be in 0..32");

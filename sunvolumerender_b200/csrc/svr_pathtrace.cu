@@ -1303,6 +1303,409 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_PROFILE_BLOCKS) pat
 }
 
 // ---------------------------------------------------------------------------------------------
+// kernel shape 5: ray pool + event queue per warp (deep paths in media that scatter many times).
+//
+// ncu on C4 (1024^3 cloud, traceDepth 32) with shape 3: 6.9 of 32 lanes active per instruction (profiles/r02).  Shape 3
+// starts every round with 32 busy lanes, but a round is "one scatter event, then one shadow flight, then one bounce
+// flight" per lane, and flights last anything from one cell to hundreds: the warp waits for its longest flight twice per
+// round, and at the end of every pixel for the last few paths that are still bouncing.  Here the unit of work is smaller
+// and lanes are not tied to paths:
+//   * a RAY (camera ray, bounce ray or shadow ray) is an item in a per-warp pool in shared memory; a scatter EVENT (a
+//     collision waiting to be shaded) is an item in a per-warp queue;
+//   * the flight phase: lanes take rays from the pool and walk them; a lane whose ray has ended takes the next one (lanes
+//     re-fill together once a few are idle, so the re-fill code runs with several lanes); a ray that is not done after
+//     SVR_POOL_CHUNK cell visits goes back into the pool with its remaining optical depth, so no lane holds the others up
+//     for longer than a chunk.  A bounce or camera ray that collides becomes an event; a shadow ray that escapes adds its
+//     contribution;
+//   * the event phase: 32 events at a time, all lanes: shade, sample the light (-> a shadow ray, which carries its
+//     contribution and owes nothing to the path afterwards), sample the BSDF (-> the bounce ray);
+//   * the warp renders a RUN of pixels, not one pixel after the other: rays of different pixels share the pool, so the few
+//     long paths of one pixel bounce on while the next pixels' camera rays keep the lanes busy.  Radiance is summed per
+//     pixel in 64-bit fixed point (2^-32) with shared-memory atomics: integer sums do not depend on the order of the
+//     additions, so the image is deterministic and independent of how the lanes happened to be scheduled.
+// A path is still a pure function of (seed, pixel, sample); the shadow ray draws from a stream of its own (it flies
+// concurrently with the bounce ray), so walks differ from shapes 1-3: parity is statistical.
+// ---------------------------------------------------------------------------------------------
+// Capacities: every ray in the pool can become one event, so nEv + nPool <= SVR_EVQ_CAP is kept at all times (a flight
+// phase can then always empty the pool); an event phase turns up to 32 events into up to 64 rays, a camera batch adds 32.
+// The more rays a flight phase starts with, the better its lanes stay packed (rays per lane), at the price of shared memory.
+// Measured on C4 (128 spp per launch, round 2): 64 / 64 at 6 blocks per SM 153.6 ms, 96 / 128 at 4 blocks 185 ms, 128 / 160 at
+// 3 blocks 211 ms, 192 / 224 at 2 blocks 259 ms -- the kernel is bound by memory latency, and resident warps buy more than
+// packed lanes (shape 3 at 8 blocks per SM: 120.8 ms).
+#ifndef SVR_POOL_CAP
+#define SVR_POOL_CAP 64
+#endif
+#ifndef SVR_EVQ_CAP
+#define SVR_EVQ_CAP 64
+#endif
+constexpr int SVR_ITEM_WORDS = 13;   // orig 3, dir 3, a 3 (throughput / contribution), x (optical depth left | collision parameter), meta, c0, c1
+constexpr int SVR_POOL_SLOTS = 16;   // pixels of a warp's run
+#ifndef SVR_POOL_CHUNK
+#define SVR_POOL_CHUNK 24
+#endif
+#ifndef SVR_PT_POOL_BLOCKS
+#define SVR_PT_POOL_BLOCKS 6
+#endif
+enum RayKind { RAY_CAMERA = 0, RAY_BOUNCE = 1, RAY_SHADOW = 2 };
+
+struct WorkItem {
+    float3 o, d, a;
+    float x;
+    uint32_t meta, c0, c1;  // meta: bounce count (20 bits) | pixel slot << 20 | kind << 26
+    SVR_DEV uint32_t k() const { return meta & 0xfffffu; }
+    SVR_DEV uint32_t slot() const { return (meta >> 20) & 63u; }
+    SVR_DEV uint32_t kind() const { return meta >> 26; }
+    static SVR_DEV uint32_t pack(uint32_t k, uint32_t slot, uint32_t kind) { return k | (slot << 20) | (kind << 26); }
+};
+
+template <int CAP>
+SVR_DEV void item_store(float* q, int idx, const WorkItem& it)
+{
+    q[0 * CAP + idx] = it.o.x;
+    q[1 * CAP + idx] = it.o.y;
+    q[2 * CAP + idx] = it.o.z;
+    q[3 * CAP + idx] = it.d.x;
+    q[4 * CAP + idx] = it.d.y;
+    q[5 * CAP + idx] = it.d.z;
+    q[6 * CAP + idx] = it.a.x;
+    q[7 * CAP + idx] = it.a.y;
+    q[8 * CAP + idx] = it.a.z;
+    q[9 * CAP + idx] = it.x;
+    q[10 * CAP + idx] = __uint_as_float(it.meta);
+    q[11 * CAP + idx] = __uint_as_float(it.c0);
+    q[12 * CAP + idx] = __uint_as_float(it.c1);
+}
+
+template <int CAP>
+SVR_DEV WorkItem item_load(const float* q, int idx)
+{
+    WorkItem it;
+    it.o = f3(q[0 * CAP + idx], q[1 * CAP + idx], q[2 * CAP + idx]);
+    it.d = f3(q[3 * CAP + idx], q[4 * CAP + idx], q[5 * CAP + idx]);
+    it.a = f3(q[6 * CAP + idx], q[7 * CAP + idx], q[8 * CAP + idx]);
+    it.x = q[9 * CAP + idx];
+    it.meta = __float_as_uint(q[10 * CAP + idx]);
+    it.c0 = __float_as_uint(q[11 * CAP + idx]);
+    it.c1 = __float_as_uint(q[12 * CAP + idx]);
+    return it;
+}
+
+// radiance into the pixel's fixed-point sum (2^-32; contributions are non-negative)
+SVR_DEV void accum_add(unsigned long long* acc, uint32_t slot, float3 v)
+{
+    const float sc = 4294967296.f, top = 4.0e9f;
+    if (v.x > 0.f) atomicAdd(acc + slot * 3 + 0, (unsigned long long)(fminf(v.x, top) * sc));
+    if (v.y > 0.f) atomicAdd(acc + slot * 3 + 1, (unsigned long long)(fminf(v.y, top) * sc));
+    if (v.z > 0.f) atomicAdd(acc + slot * 3 + 2, (unsigned long long)(fminf(v.z, top) * sc));
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_POOL_BLOCKS) pathtrace_pool_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NW = SVR_PT_MAX_THREADS / 32;
+    extern __shared__ float poolMem[];  // per warp: the ray pool, then the event queue (dynamic: above 48 KB per block)
+    __shared__ unsigned long long accums[NW][SVR_POOL_SLOTS * 3];
+    __shared__ float tskips[NW][SVR_POOL_SLOTS];
+    __shared__ uint32_t pflags[NW][SVR_POOL_SLOTS];  // bit 0: a camera ray of the pixel may hit a light; bit 1: every sample is the constant sky
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t idy = a.y0 + (blockIdx.y * a.bandStride + a.bandPhase) * (blockDim.x >> 5) + warp;
+    float* pool = poolMem + warp * (SVR_ITEM_WORDS * (SVR_POOL_CAP + SVR_EVQ_CAP));
+    float* evq = pool + SVR_ITEM_WORDS * SVR_POOL_CAP;
+    unsigned long long* acc = accums[warp];
+    float* tskip = tskips[warp];
+    uint32_t* pflag = pflags[warp];
+    LocalCounters<COUNT> lc;
+    if (idy < a.y1) {
+        const svr_camera& cam = s.cam;
+        const uint32_t runPixels = min((uint32_t)a.warpPixels, (uint32_t)SVR_POOL_SLOTS);
+        const uint32_t x0 = blockIdx.x * runPixels;
+        const uint32_t nPix = x0 < cam.imageW ? min(runPixels, cam.imageW - x0) : 0u;
+        // ---- the run's pixels: classification (one lane per pixel), sums cleared; all-sky pixels are finished on the spot
+        if (lane < SVR_POOL_SLOTS * 3) acc[lane] = 0ull;
+        if (lane + 32 < SVR_POOL_SLOTS * 3) acc[lane + 32] = 0ull;
+        __syncwarp();
+        if (lane < nPix) {
+            const PixelInfo pi = classify_pixel(s, x0 + lane, idy, true, a.entryCache != 0, a.lightCull != 0);
+            const bool sky = pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0);
+            tskip[lane] = pi.tSkip;
+            pflag[lane] = (pi.lights ? 1u : 0u) | ((sky || a.traceDepth == 0) ? 2u : 0u);
+            if (sky && a.traceDepth != 0 && s.envEnabled) {
+                const float3 v = f3(s.env.defaultRadiance) * (s.env.intensity * (float)a.nSamples);
+                const double sc = 4294967296.0;
+                acc[lane * 3 + 0] = (unsigned long long)((double)v.x * sc);
+                acc[lane * 3 + 1] = (unsigned long long)((double)v.y * sc);
+                acc[lane * 3 + 2] = (unsigned long long)((double)v.z * sc);
+            }
+            if (COUNT && (sky || a.traceDepth == 0)) lc.add(SVR_CNT_PATHS, a.nSamples);
+        }
+        __syncwarp();
+        uint32_t curSlot = 0, curSample = 0;  // next camera sample to hand out (warp-uniform)
+        while (curSlot < nPix && (pflag[curSlot] & 2u)) ++curSlot;
+        int nPool = 0, nEv = 0;               // items in the pool / the event queue (warp-uniform)
+        const float3 camPos = f3(cam.pos);
+        while (true) {
+            const bool camLeft = curSlot < nPix;
+            // what next: events (if their rays fit), else camera rays (if they fit), else fly what is in the pool
+            const bool roomEv = nPool + 64 <= SVR_POOL_CAP && nEv + nPool + 32 <= SVR_EVQ_CAP;
+            const bool roomCam = camLeft && nPool + 32 <= SVR_POOL_CAP && nEv + nPool + 32 <= SVR_EVQ_CAP;
+            if ((nEv >= 32 && roomEv) || (nEv > 0 && nPool == 0 && !roomCam)) {
+                // ================= event phase: up to 32 collisions, one scatter event each (pathtracer.cu:214-276) =================
+                const int take = nEv < 32 ? nEv : 32;
+                nEv -= take;
+                const bool active = (int)lane < take;
+                bool haveShadow = false, haveBounce = false;
+                WorkItem sh, bo;
+                if (active) {
+                    const WorkItem ev = item_load<SVR_EVQ_CAP>(evq, nEv + (int)lane);
+                    const uint32_t k = ev.k(), slot = ev.slot();
+                    const float t = ev.x;
+                    bool done = false;
+                    if (k == 0 && (pflag[slot] & 1u)) {
+                        // the camera ray may hit a light before its collision (pathtracer.cu:214-229)
+                        Ray cr;
+                        cr.orig = ev.o;
+                        cr.dir = ev.d;
+                        LightHit ls;
+                        if (nearest_light(s, cr, &ls) && ls.t < t) {
+                            const float cosTerm = dot(ls.normal, -ev.d);
+                            accum_add(acc, slot, ev.a * ls.radiance * (cosTerm <= 0.f ? 0.f : 1.f));
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        Philox rng;
+                        rng.c0 = ev.c0;
+                        rng.c1 = ev.c1;
+                        rng.r1 = 0;
+                        rng.have = 0;
+                        VolumeSample vs;
+                        vs.wo = -ev.d;
+                        vs.ptInWorld = ev.o + t * ev.d;
+                        const float intensity = intensity_at(s.vol, vs.ptInWorld);
+                        vs.color_opacity = tf_at(s.tf, intensity);
+                        vs.gradient = gradient_at(s.vol, vs.ptInWorld);
+                        const float gradientMagnitude = sqrtf(dot(vs.gradient, vs.gradient));
+                        lc.add(SVR_CNT_SHADE_TAPS, 7);
+                        lc.add(SVR_CNT_TF_LOOKUPS, 1);
+                        lc.add(SVR_CNT_SCATTERS, 1);
+                        const float gf = s.vol.gradientFactor;
+                        const float Pbrdf = vs.color_opacity.w * (1.f - expf(-25.f * gf * gf * gf * gradientMagnitude * 65535.f * s.vol.invMaxMagnitude));
+                        const ShadingType st = (rng.next() < Pbrdf) ? BRDF : ISOTROPIC;
+                        // estimate_direct_light (pathtracer.cu:171-198): the shadow ray carries T * nLights * bsdf * Li / pdf
+                        if (s.numLights != 0) {
+                            int lightId = (int)((float)s.numLights * rng.next());
+                            lightId = lightId < (int)s.numLights ? lightId : (int)s.numLights - 1;
+                            float3 lightPos, wi;
+                            float pdf;
+                            const float3 Li = sample_light<false>(s.lights[lightId], vs.ptInWorld, rng, &lightPos, &wi, &pdf);
+                            if (pdf > 0.f && max3(Li) > 0.f) {
+                                sh.o = vs.ptInWorld;
+                                sh.d = normalize(lightPos - vs.ptInWorld);
+                                sh.a = ev.a * ((float)s.numLights * bsdf(vs, wi, st) * Li / pdf);
+                                sh.x = -1.f;
+                                sh.meta = WorkItem::pack(k, slot, RAY_SHADOW);
+                                sh.c0 = rng.c0;
+                                sh.c1 = ev.c1 ^ 0xA511E9B3u;  // a stream of its own: it flies beside the bounce ray
+                                haveShadow = max3(sh.a) > 0.f;
+                            }
+                        }
+                        // the bounce (pathtracer.cu:257-276); the last bounce's BSDF sample would never be used
+                        if (k + 1 < a.traceDepth) {
+                            float3 wi = f3(0.f);
+                            float pdf = 0.f;
+                            const float3 f = sample_bsdf<false>(vs, &wi, &pdf, rng, st);
+                            const float cosTerm = fabsf(dot(normalize(vs.gradient), wi));
+                            float3 T = ev.a;
+                            if (max3(f) > 0.f && pdf > 0.f) {
+                                if (st == ISOTROPIC) T *= f / (pdf * (1.f - Pbrdf));
+                                else T *= f * cosTerm / (pdf * Pbrdf);
+                            }
+                            bool alive = true;
+                            if (k >= 3) alive = !russian_roulette<false>(&T, rng);
+                            if (alive) {
+                                bo.o = vs.ptInWorld;
+                                bo.d = wi;
+                                bo.a = T;
+                                bo.x = -1.f;
+                                bo.meta = WorkItem::pack(k + 1, slot, RAY_BOUNCE);
+                                bo.c0 = rng.c0;
+                                bo.c1 = ev.c1;
+                                haveBounce = true;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();  // every load of the phase precedes every store
+                const unsigned mS = __ballot_sync(FULL, haveShadow), mB = __ballot_sync(FULL, haveBounce);
+                const unsigned below = (1u << lane) - 1u;
+                if (haveShadow) item_store<SVR_POOL_CAP>(pool, nPool + __popc(mS & below), sh);
+                nPool += __popc(mS);
+                if (haveBounce) item_store<SVR_POOL_CAP>(pool, nPool + __popc(mB & below), bo);
+                nPool += __popc(mB);
+                __syncwarp();
+                continue;
+            }
+            if (roomCam) {
+                // ================= camera rays: the next (up to 32) samples of the current pixel go into the pool =================
+                const uint32_t left = a.nSamples - curSample;
+                const uint32_t n = left < 32u ? left : 32u;
+                if (lane < n) {
+                    lc.add(SVR_CNT_PATHS, 1);
+                    Philox rng;
+                    rng.init(s.seedKey, idy * cam.imageW + x0 + curSlot, a.firstSample + curSample + lane);
+                    const Ray cr = camera_ray_jittered<false>(cam, x0 + curSlot, idy, rng);
+                    WorkItem it;
+                    it.o = cr.orig;
+                    it.d = cr.dir;
+                    it.a = f3(1.f);
+                    it.x = -1.f;
+                    it.meta = WorkItem::pack(0, curSlot, RAY_CAMERA);
+                    it.c0 = rng.c0;
+                    it.c1 = rng.c1;
+                    item_store<SVR_POOL_CAP>(pool, nPool + (int)lane, it);
+                }
+                nPool += (int)n;
+                curSample += n;
+                if (curSample >= a.nSamples) {
+                    curSample = 0;
+                    ++curSlot;
+                    while (curSlot < nPix && (pflag[curSlot] & 2u)) ++curSlot;
+                }
+                __syncwarp();
+                continue;
+            }
+            if (nPool == 0) break;  // (no events, no rays, no camera samples left)
+            // ================= flight phase: the pool is emptied; collisions of camera / bounce rays become events =================
+            {
+                bool flying = false;
+                TrackLocal trk;
+                Philox rng;
+                Ray ray;
+                float3 av = f3(0.f);
+                uint32_t meta = 0;
+                int steps = 0;
+                float ratioAcc = 1.f;  // ratio tracking: transmittance of the stretch this lane has flown
+                ray.orig = ray.dir = f3(0.f);
+                rng.c0 = rng.c1 = rng.r1 = rng.have = 0;
+                while (true) {
+                    // ---- idle lanes take rays, together
+                    const unsigned idle = __ballot_sync(FULL, !flying);
+                    if (idle == FULL && nPool == 0) break;
+                    if (nPool > 0 && (__popc(idle) >= a.marchBurst || idle == FULL)) {
+                        const int rank = __popc(idle & ((1u << lane) - 1u));
+                        if (!flying && rank < nPool) {
+                            const WorkItem it = item_load<SVR_POOL_CAP>(pool, nPool - 1 - rank);
+                            ray.orig = it.o;
+                            ray.dir = it.d;
+                            av = it.a;
+                            meta = it.meta;
+                            rng.c0 = it.c0;
+                            rng.c1 = it.c1;
+                            rng.r1 = 0;
+                            rng.have = 0;
+                            steps = 0;
+                            ratioAcc = 1.f;
+                            flying = true;
+                            const bool ok = trk.begin(s, ray, rng, it.kind() == RAY_CAMERA ? tskip[it.slot()] : 0.f);
+                            if (ok && it.x >= 0.f) trk.tau = it.x;  // a ray that went back into the pool keeps its optical depth
+                            if (!ok) trk.t = FLT_MAX;               // cannot collide: it escapes at the first look
+                        }
+                        const int taken = __popc(idle) < nPool ? __popc(idle) : nPool;
+                        nPool -= taken;
+                    }
+                    __syncwarp();  // pops before pushes
+                    // ---- one cell visit (and the collision it may end in) for every lane that holds a ray
+                    int fin = 0;  // 1: collided (camera / bounce: an event), 2: escaped, 3: back into the pool
+                    if (flying) {
+                        const uint32_t kind = meta >> 26;
+                        VisitResult v = trk.t == FLT_MAX ? VISIT_ESCAPED : trk.template visit<COUNT>(s, ray, rng, lc);
+                        if (v == VISIT_COLLIDE) {
+                            const bool ratio = kind == RAY_SHADOW && s.shadowEstimator != 0;
+                            float Tr = 1.f;
+                            const bool real = trk.template collide<COUNT>(s, ray, rng, lc, kind == RAY_SHADOW ? SVR_CNT_SHADOW_TAPS : SVR_CNT_TRACK_TAPS,
+                                                                          ratio ? &Tr : nullptr);
+                            if (ratio) {
+                                // ratio tracking: the contribution is attenuated and the ray flies on; Russian roulette once the
+                                // transmittance of this stretch has fallen below 2 % (ratio_roulette)
+                                av = av * Tr;
+                                ratioAcc *= Tr;
+                                if (ratioAcc < 0.02f) {
+                                    if (rng.next() * 0.02f >= ratioAcc) {
+                                        fin = 1;  // terminated with nothing to add
+                                    } else {
+                                        av = av * (0.02f / ratioAcc);
+                                        ratioAcc = 0.02f;
+                                    }
+                                }
+                            } else if (real) {
+                                fin = 1;
+                            }
+                        } else if (v == VISIT_ESCAPED) {
+                            fin = 2;
+                        }
+                        if (fin == 0 && ++steps >= SVR_POOL_CHUNK && kind != RAY_CAMERA) fin = 3;
+                    }
+                    // ---- what the finished rays leave behind
+                    const unsigned below = (1u << lane) - 1u;
+                    const bool toEvent = fin == 1 && (meta >> 26) != RAY_SHADOW;
+                    const unsigned mE = __ballot_sync(FULL, toEvent), mR = __ballot_sync(FULL, fin == 3);
+                    if (toEvent) {
+                        WorkItem ev;
+                        ev.o = ray.orig;
+                        ev.d = ray.dir;
+                        ev.a = av;
+                        ev.x = trk.t;
+                        ev.meta = WorkItem::pack(meta & 0xfffffu, (meta >> 20) & 63u, RAY_BOUNCE);
+                        ev.c0 = rng.c0;
+                        ev.c1 = rng.c1;
+                        item_store<SVR_EVQ_CAP>(evq, nEv + __popc(mE & below), ev);
+                    }
+                    nEv += __popc(mE);
+                    if (fin == 3) {
+                        WorkItem it;
+                        it.o = ray.orig + trk.t * ray.dir;
+                        it.d = ray.dir;
+                        it.a = av;
+                        it.x = trk.tau;
+                        it.meta = meta;
+                        it.c0 = rng.c0;
+                        it.c1 = rng.c1;
+                        item_store<SVR_POOL_CAP>(pool, nPool + __popc(mR & below), it);
+                    }
+                    nPool += __popc(mR);
+                    if (fin == 2) {
+                        const uint32_t kind = meta >> 26, slot = (meta >> 20) & 63u;
+                        if (kind == RAY_SHADOW) {
+                            accum_add(acc, slot, av);  // unoccluded (binary estimator) / what ratio tracking left of it
+                        } else {
+                            // a camera / bounce ray left the medium: pathtracer.cu:214-234 with t < 0
+                            LightHit ls;
+                            if (kind == RAY_CAMERA && (pflag[slot] & 1u) && nearest_light(s, ray, &ls)) {
+                                const float cosTerm = dot(ls.normal, -ray.dir);
+                                accum_add(acc, slot, av * ls.radiance * (cosTerm <= 0.f ? 0.f : 1.f));
+                            } else if (s.envEnabled) {
+                                accum_add(acc, slot, av * env_radiance(s.env, ray.dir));
+                            }
+                        }
+                    }
+                    if (fin != 0) flying = false;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- the run's pixels: merge into the caller's accumulator, tone map
+        __syncwarp();
+        if (lane < nPix) {
+            const double inv = 1.0 / 4294967296.0;
+            const float3 sum = f3((float)((double)acc[lane * 3 + 0] * inv), (float)((double)acc[lane * 3 + 1] * inv), (float)((double)acc[lane * 3 + 2] * inv));
+            write_pixel(s, a, idy * cam.imageW + x0 + lane, sum);
+        }
+    }
+    lc.flush(cnt);
+}
+
+// ---------------------------------------------------------------------------------------------
 // kernel shape 0: phase-scheduled warp
 // ---------------------------------------------------------------------------------------------
 enum Phase { PH_GEN = 0, PH_MARCH = 1, PH_COLLIDE = 2, PH_EVENT = 3, PH_BOUNCE = 4, PH_DONE = 5 };
@@ -1439,7 +1842,17 @@ __global__ void resolve_kernel(const float4* __restrict__ sum, float* __restrict
 template <int MODE>
 void launch_mode(int shape, dim3 grid, int block, cudaStream_t stream, const DevScene& sc, const PtLaunch& a, Counters* cnt)
 {
-    if (shape == 4) {  // launch_pathtrace() only picks it for MODE 2 with a pinhole camera
+    if (shape == 5) {  // launch_pathtrace() only picks it for MODE 2
+        const size_t shm = sizeof(float) * SVR_ITEM_WORDS * (SVR_POOL_CAP + SVR_EVQ_CAP) * (size_t)(block / 32);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(pathtrace_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SVR_ITEM_WORDS * (SVR_POOL_CAP + SVR_EVQ_CAP) * (SVR_PT_MAX_THREADS / 32)));
+            cudaFuncSetAttribute(pathtrace_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SVR_ITEM_WORDS * (SVR_POOL_CAP + SVR_EVQ_CAP) * (SVR_PT_MAX_THREADS / 32)));
+            attr = true;
+        }
+        if (cnt) pathtrace_pool_kernel<true><<<grid, block, shm, stream>>>(sc, a, cnt);
+        else pathtrace_pool_kernel<false><<<grid, block, shm, stream>>>(sc, a, cnt);
+    } else if (shape == 4) {  // launch_pathtrace() only picks it for MODE 2 with a pinhole camera
         if (cnt) pathtrace_profile_kernel<true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_profile_kernel<false><<<grid, block, 0, stream>>>(sc, a, cnt);
     } else if (shape == 3) {  // launch_pathtrace() only picks it for MODE 2
@@ -1497,10 +1910,13 @@ int launch_pathtrace(PtLaunch& a)
     // local majorants and the camera is a pinhole (one origin per pixel); it has shape 3's scatter queue built in
     if ((shape == 2 || shape == 3) && mode == 2 && st.options[SVR_OPT_PT_PROFILE] && sc.cam.apeture == 0.f) shape = 4;
     if (shape == 4 && (mode != 2 || sc.cam.apeture != 0.f)) shape = 2;
+    if (shape == 5 && mode != 2) shape = 2;
     if (shape >= 2 && a.nSamples < (uint32_t)st.options[SVR_OPT_PT_WARP_MIN_SPP]) shape = 1;
     // shape 4: idle lanes take new camera samples together, once this many wait (SVR_OPT_PT_REFILL)
     if (shape == 4) a.marchBurst = st.options[SVR_OPT_PT_REFILL] > 0 ? st.options[SVR_OPT_PT_REFILL] : 8;
+    if (shape == 5) a.marchBurst = st.options[SVR_OPT_PT_REFILL] > 0 ? st.options[SVR_OPT_PT_REFILL] : 8;
     a.warpPixels = st.options[SVR_OPT_PT_WARP_PIXELS];
+    if (shape == 5) a.warpPixels = st.options[SVR_OPT_PT_POOL_PIXELS] > 0 ? st.options[SVR_OPT_PT_POOL_PIXELS] : 16;
     uint32_t tileW = 16u, tileH = (uint32_t)block / 16u;
     if (shape >= 2) {
         tileW = (uint32_t)a.warpPixels;

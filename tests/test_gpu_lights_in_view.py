@@ -174,7 +174,7 @@ def test_light_cull_is_bit_exact(renderer, name):
     every disk, as the reference does, and the image must not change in a single bit."""
     depth = 2
     cfg = _setup(renderer, name, depth, False)
-    for mode, shape, spp in ((2, 4, 40), (2, 2, 40), (2, 1, 5), (2, 3, 40), (1, 2, 33), (0, 1, 2)):
+    for mode, shape, spp in ((2, 5, 40), (2, 4, 40), (2, 2, 40), (2, 1, 5), (2, 3, 40), (1, 2, 33), (0, 1, 2)):
         renderer.set_option(L.OPT_PT_MODE, mode)
         renderer.set_option(L.OPT_PT_KERNEL, shape)
         renderer.set_option(L.OPT_PT_WARP_MIN_SPP, 1)

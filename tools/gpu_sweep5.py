@@ -13,7 +13,7 @@ r = Renderer(0)
 def run(cfg, t, spp, reps=4):
     buf = torch.zeros(cfg.width * cfg.height * 4, dtype=torch.float32, device="cuda")
     for o in optsets:
-        defaults = {"profile": 1, "refill": 0, "kernel": 2, "cell": 0, "wp": 4, "qdepth": 8, "block": 128, "shadow": 0}
+        defaults = {"profile": 0, "refill": 0, "kernel": 2, "cell": 0, "wp": 4, "qdepth": 8, "block": 128, "shadow": 0}
         for kv in o.split(","):
             if kv:
                 k, v = kv.split("="); defaults[k] = int(v)
@@ -28,17 +28,18 @@ def run(cfg, t, spp, reps=4):
         r.set_option(L.OPT_COUNTERS, 1); r.reset_counters(); r.accumulate(buf, cfg.trace_depth, 0, spp, clear=True); torch.cuda.synchronize()
         c = r.counters(); r.set_option(L.OPT_COUNTERS, 0)
         print(f"{tag:10s} {t:8s} {o:28s} {best:8.3f} ms {cfg.width*cfg.height*spp/best/1e6:7.2f} Gs/s mean {chk:.6f} taps/path trk {c['track_taps']/c['paths']:.3f} shd {c['shadow_taps']/c['paths']:.3f} cells {c['cells']/c['paths']:.2f} scat {c['scatters']/c['paths']:.4f}", flush=True)
-cfg = S.CONFIGS["C3"]; setup_config(r, cfg)
-cam0 = r.camera
-run(cfg, "C3", 256)
-r.set_camera(S.make_camera((0, 0, cam0.pos.z * 0.45), (1, 0, 0), (0, 1, 0), (0, 0, 1), 45.0, 0.0, 1.0, 1.0, cfg.width, cfg.height))
-run(cfg, "C3close", 256, 3)
+if "--noc3" not in sys.argv:
+    cfg = S.CONFIGS["C3"]; setup_config(r, cfg)
+    cam0 = r.camera
+    run(cfg, "C3", 256)
+    r.set_camera(S.make_camera((0, 0, cam0.pos.z * 0.45), (1, 0, 0), (0, 1, 0), (0, 0, 1), 45.0, 0.0, 1.0, 1.0, cfg.width, cfg.height))
+    run(cfg, "C3close", 256, 3)
 if "--c1" in sys.argv:
     cfg = S.CONFIGS["C1"]; setup_config(r, cfg)
     run(cfg, "C1x256", 256, 3)
 if "--c4" in sys.argv:
     cfg = S.CONFIGS["C4"]; setup_config(r, cfg)
-    run(cfg, "C4", 32, 3)
+    run(cfg, "C4", 128 if "--c4spp128" in sys.argv else 32, 3)
 '''
 args = [a for a in sys.argv[1:] if not a.startswith("--") and a.endswith(".so")]
 flags = [a for a in sys.argv[1:] if a.startswith("--") and a != "--opts"]
