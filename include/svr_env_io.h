@@ -26,6 +26,11 @@ int svr_hdr_read(const char* path, float* rgb_out, uint32_t* w, uint32_t* h);
  * does (intensity 1, offset 0).  Destroy with svr_env_destroy (svr_render.h). */
 int svr_env_load_hdr(const char* path, svr_env_light* out);
 
+/* Inspection hook: the importance sampler SVR_OPT_ENV_NEE uses for the environment light last passed to setup_env_lights --
+ * cumulative row probabilities (*h + 1 floats) and per-row cumulative cell probabilities (*h rows of *w + 1 floats) over
+ * the direction grid (u, v) = (phi / 2 pi, theta / pi).  Either pointer may be NULL. */
+int svr_env_sampler_copy(float* host_marg, float* host_cond, uint32_t* w, uint32_t* h);
+
 #ifdef __cplusplus
 }
 #endif

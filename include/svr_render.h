@@ -132,6 +132,13 @@ enum svr_option {
     /* kernel shape 5 (ray pool + event queue per warp, SVR_OPT_PT_KERNEL = 5): pixels in a warp's run (1..16, 0 = default 16);
      * rays of all of them share the warp's pool */
     SVR_OPT_PT_POOL_PIXELS = 20,
+    /* 1 = the environment light (when SVR_OPT_ENV_ENABLED) is a NEXT-EVENT target beside the area lights: at every scatter
+     * event one of (area lights + environment) is picked uniformly; the environment is sampled by importance from its
+     * luminance (a 512 x 256 direction grid built from the map, its offset and intensity; rebuilt when they change) and
+     * weighted with both lobes of the shading model; bounce rays that leave the medium then add nothing.  Same
+     * expectation as collecting the sky on escape (0, default: what the reference's commented-out line would do), far
+     * lower variance for maps with small bright features.  Ignored by the reference-twin mode and kernel shape 5. */
+    SVR_OPT_ENV_NEE = 21,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

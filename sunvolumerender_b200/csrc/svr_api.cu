@@ -161,6 +161,10 @@ extern "C" int svr_set_device(int device)
     cudaFree(st.dStats);
     cudaFree(st.dFingerprint);
     cudaFree(st.dTfHash);
+    cudaFree(st.dEnvMarg);
+    cudaFree(st.dEnvCond);
+    st.dEnvMarg = st.dEnvCond = nullptr;
+    st.envSamplerValid = false;
     st.dFingerprint = nullptr;
     st.dTfHash = nullptr;
     st.dStats = nullptr;

@@ -183,3 +183,129 @@ extern "C" int svr_env_load_hdr(const char* path, svr_env_light* out)
         return fail_msg("svr_env_load_hdr: out of host memory");
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Importance sampler of the environment light (SVR_OPT_ENV_NEE).  A fixed grid of direction cells over (u, v) =
+// (phi / 2 pi, theta / pi); the weight of a cell is (the largest luminance GetEnvRadiance returns at four points of the
+// cell -- so offset, wrap and filtering are whatever the renderer will see -- plus a floor of 5 % of the mean, so that no
+// direction with radiance has probability 0) times sin(theta).  Three small launches; rebuilt only when the light changes.
+// ------------------------------------------------------------------------------------------------
+namespace svr {
+namespace {
+constexpr int ENV_W = 512, ENV_H = 256;
+
+__device__ float cell_luminance(const svr_env_light& env, int i, int j)
+{
+    float m = 0.f;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const float3 d = env_direction(((float)i + 0.25f + 0.5f * (float)a) / (float)ENV_W, ((float)j + 0.25f + 0.5f * (float)b) / (float)ENV_H);
+            const float3 L = env_radiance(env, d);
+            m = fmaxf(m, 0.2126f * L.x + 0.7152f * L.y + 0.0722f * L.z);
+        }
+    return (m == m && m < 3.0e38f) ? fmaxf(m, 0.f) : 0.f;
+}
+
+// one block per row: luminance into cond (temporarily), the row's sum into marg[j + 1] (temporarily), total into *total
+__global__ void env_lum_kernel(svr_env_light env, float* cond, float* marg, double* total)
+{
+    const int j = blockIdx.x, i = threadIdx.x;
+    const float lum = cell_luminance(env, i, j);
+    cond[(size_t)j * (ENV_W + 1) + i + 1] = lum;
+    __shared__ float red[ENV_W];
+    red[i] = lum;
+    __syncthreads();
+    for (int o = ENV_W / 2; o > 0; o >>= 1) {
+        if (i < o) red[i] += red[i + o];
+        __syncthreads();
+    }
+    if (i == 0) {
+        marg[j + 1] = red[0];
+        atomicAdd(total, (double)red[0] * (double)__sinf(SVR_PI_F * ((float)j + 0.5f) / (float)ENV_H));
+    }
+}
+
+// one block per row: weights = (lum + floor) sin(theta), inclusive scan -> the row's conditional CDF; the row's weight sum -> marg[j + 1]
+__global__ void env_cond_kernel(float* cond, float* marg, const double* total, double sinSum)
+{
+    const int j = blockIdx.x, i = threadIdx.x;
+    const float mean = (float)(*total / sinSum) / (float)ENV_W;
+    const float floorLum = mean > 0.f ? 0.05f * mean : 1.f;
+    const float sinT = __sinf(SVR_PI_F * ((float)j + 0.5f) / (float)ENV_H);
+    float* row = cond + (size_t)j * (ENV_W + 1);
+    __shared__ float sc[ENV_W];
+    sc[i] = (row[i + 1] + floorLum) * sinT;
+    __syncthreads();
+    for (int o = 1; o < ENV_W; o <<= 1) {
+        const float v = i >= o ? sc[i - o] : 0.f;
+        __syncthreads();
+        sc[i] += v;
+        __syncthreads();
+    }
+    const float sum = sc[ENV_W - 1];
+    row[i + 1] = i == ENV_W - 1 ? 1.f : sc[i] / sum;
+    if (i == 0) {
+        row[0] = 0.f;
+        marg[j + 1] = sum;
+    }
+}
+
+__global__ void env_marg_kernel(float* marg)
+{
+    const int j = threadIdx.x;
+    __shared__ float sc[ENV_H];
+    sc[j] = marg[j + 1];
+    __syncthreads();
+    for (int o = 1; o < ENV_H; o <<= 1) {
+        const float v = j >= o ? sc[j - o] : 0.f;
+        __syncthreads();
+        sc[j] += v;
+        __syncthreads();
+    }
+    const float sum = sc[ENV_H - 1];
+    marg[j + 1] = j == ENV_H - 1 ? 1.f : sc[j] / sum;
+    if (j == 0) marg[0] = 0.f;
+}
+}  // namespace
+
+int ensure_env_sampler(DevScene* scene)
+{
+    HostState& st = state();
+    const svr_env_light& e = scene->env;
+    if (!st.envSamplerValid || memcmp(&st.envSamplerKey, &e, sizeof(e)) != 0) {
+        if (!st.dEnvMarg) SVR_TRY(cudaMalloc(&st.dEnvMarg, (ENV_H + 1) * sizeof(float)));
+        if (!st.dEnvCond) SVR_TRY(cudaMalloc(&st.dEnvCond, (size_t)ENV_H * (ENV_W + 1) * sizeof(float)));
+        if (!st.dStats) SVR_TRY(cudaMalloc(&st.dStats, 16));
+        SVR_TRY(cudaMemsetAsync(st.dStats, 0, 16, st.stream));
+        double sinSum = 0.0;
+        for (int j = 0; j < ENV_H; ++j) sinSum += (double)sinf(SVR_PI_F * ((float)j + 0.5f) / (float)ENV_H);
+        env_lum_kernel<<<ENV_H, ENV_W, 0, st.stream>>>(e, st.dEnvCond, st.dEnvMarg, (double*)st.dStats);
+        env_cond_kernel<<<ENV_H, ENV_W, 0, st.stream>>>(st.dEnvCond, st.dEnvMarg, (const double*)st.dStats, sinSum);
+        env_marg_kernel<<<1, ENV_H, 0, st.stream>>>(st.dEnvMarg);
+        count_launch(3);
+        SVR_TRY(cudaGetLastError());
+        st.envSamplerKey = e;
+        st.envSamplerValid = true;
+    }
+    scene->envS.marg = st.dEnvMarg;
+    scene->envS.cond = st.dEnvCond;
+    scene->envS.w = ENV_W;
+    scene->envS.h = ENV_H;
+    return 0;
+}
+}  // namespace svr
+
+// Inspection hook (tests): the sampler's cumulative tables for the current environment light, ENV_H + 1 and ENV_H * (ENV_W + 1) floats.
+extern "C" int svr_env_sampler_copy(float* host_marg, float* host_cond, uint32_t* w, uint32_t* h)
+{
+    HostState& st = state();
+    DevScene sc = st.scene;
+    int rc = ensure_env_sampler(&sc);
+    if (rc) return rc;
+    SVR_TRY(cudaStreamSynchronize(st.stream));
+    if (w) *w = ENV_W;
+    if (h) *h = ENV_H;
+    if (host_marg) SVR_TRY(cudaMemcpy(host_marg, st.dEnvMarg, (ENV_H + 1) * sizeof(float), cudaMemcpyDeviceToHost));
+    if (host_cond) SVR_TRY(cudaMemcpy(host_cond, st.dEnvCond, (size_t)ENV_H * (ENV_W + 1) * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}

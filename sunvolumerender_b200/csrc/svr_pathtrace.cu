@@ -256,6 +256,12 @@ template <>
 struct TrackOf<2> {
     typedef TrackLocal type;
 };
+// MODE 3 (internal): mode 2 with the environment light as a next-event target (SVR_OPT_ENV_NEE).  An estimator of its own
+// so that the code it adds costs the other modes' kernels no registers.
+template <>
+struct TrackOf<3> {
+    typedef TrackLocal type;
+};
 
 // What is known about ALL camera rays of a pixel before any sample is drawn.  With a pinhole
 // (aperture 0) the samples of a pixel share the origin and differ by at most half a pixel diagonal in
@@ -409,6 +415,32 @@ SVR_DEV float3 sample_bsdf(const VolumeSample& vs, float3* wi, float* pdf, Rng& 
     return color * lambert_f() * kd / (1.f - p);
 }
 
+// What a bounce collects per unit radiance arriving from wi, in expectation over sample_bsdf and the lobe choice of
+// pathtracer.cu:250-267: the lobes the bounce can take -- the phase function unless Pbrdf is 1, the BRDF with its cosine
+// unless Pbrdf is 0 -- weighted as sample_bsdf weights them (Fresnel of the OUTGOING direction, pathtracer.cu:143-153;
+// bsdf(), which the area lights use, takes the Fresnel term of the incoming one, :118-121).  Used by the environment
+// light's next-event estimation, which replaces exactly that collection.
+SVR_DEV float3 lobes_as_sampled(const VolumeSample& vs, float3 wi, float Pbrdf)
+{
+    const float3 color = f3(vs.color_opacity.x, vs.color_opacity.y, vs.color_opacity.z);
+    float3 f = f3(0.f);
+    if (Pbrdf < 1.f) f += color * hg_phase_f();
+    if (Pbrdf > 0.f) {
+        float3 normal = normalize(vs.gradient);
+        float cosO = dot(vs.wo, normal);
+        if (cosO < 0.f) {
+            cosO = -cosO;
+            normal = -normal;
+        }
+        const float cosI = dot(wi, normal);
+        if (cosI > 0.f) {
+            const float ks = schlick_fresnel(1.f, SVR_IOR, cosO), kd = 1.f - ks;
+            f += (kd * lambert_f() * color + f3(ks * microfacet_f(wi, vs.wo, normal, SVR_IOR, SVR_ALPHA))) * cosI;
+        }
+    }
+    return f;
+}
+
 // pathtracer.cu:96-103 (the 0.0722 term is a double product in the reference)
 template <bool EXACT, class Rng>
 SVR_DEV bool russian_roulette(float3* T, Rng& rng)
@@ -440,6 +472,8 @@ struct PathState {
     ShadingType st;
     bool shadow;      // the tracked ray is a shadow ray
     bool camLights;   // a camera ray of this pixel may hit a light (PixelInfo::lights)
+    bool envEsc;      // the ray being tracked adds the environment light if it escapes (always, unless the environment is a
+                      // next-event target and this is a bounce ray whose vertex has already been lit by it)
 };
 
 // what a lane does next
@@ -457,6 +491,7 @@ SVR_DEV bool path_begin(const DevScene& s, PathState<MODE>& ps, uint32_t idx, ui
     ps.T = f3(1.f);
     ps.k = 0;
     ps.shadow = false;
+    if (MODE == 3) ps.envEsc = true;
     ps.ray = camera_ray_jittered<EXACT_PI>(s.cam, idx, idy, ps.rng);
     return ps.trk.begin(s, ps.ray, ps.rng, tSkip);
 }
@@ -464,7 +499,7 @@ SVR_DEV bool path_begin(const DevScene& s, PathState<MODE>& ps, uint32_t idx, ui
 // A camera / bounce flight ended at distance t (or left the volume: t = -FLT_MAX):
 // pathtracer.cu:214-255 plus estimate_direct_light up to the shadow ray (:171-191).
 template <int MODE, bool COUNT>
-SVR_DEV Next event_flight_end(const DevScene& s, PathState<MODE>& ps, float t, LocalCounters<COUNT>& lc)
+SVR_DEV Next event_flight_end(const DevScene& s, PathState<MODE>& ps, float t, uint32_t traceDepth, LocalCounters<COUNT>& lc)
 {
     constexpr bool EXACT_PI = MODE == 0;
     if (ps.k == 0) {
@@ -481,7 +516,7 @@ SVR_DEV Next event_flight_end(const DevScene& s, PathState<MODE>& ps, float t, L
         }
     }
     if (t < 0.f) {
-        if (s.envEnabled) ps.L += ps.T * env_radiance(s.env, ps.ray.dir);  // the line commented out at pathtracer.cu:233
+        if (s.envEnabled && (MODE != 3 || ps.envEsc)) ps.L += ps.T * env_radiance(s.env, ps.ray.dir);  // the line commented out at pathtracer.cu:233
         return NEXT_PATH_DONE;
     }
     VolumeSample& vs = ps.vs;
@@ -502,18 +537,38 @@ SVR_DEV Next event_flight_end(const DevScene& s, PathState<MODE>& ps, float t, L
     ps.shadow = true;
     ps.pending = f3(0.f);
     ps.ratioT = 1.f;
-    if (s.numLights != 0) {
-        int lightId = (int)((float)s.numLights * ps.rng.next());
-        lightId = lightId < (int)s.numLights ? lightId : (int)s.numLights - 1;
-        float3 lightPos, wi;
-        float pdf;
-        float3 Li = sample_light<EXACT_PI>(s.lights[lightId], vs.ptInWorld, ps.rng, &lightPos, &wi, &pdf);
-        if (pdf > 0.f && max3(Li) > 0.f) {
-            ps.pending = (float)s.numLights * bsdf(vs, wi, ps.st) * Li / pdf;
-            // transmittance.h:10-17: track from the sample toward the light through the whole box
-            ps.ray.orig = vs.ptInWorld;
-            ps.ray.dir = normalize(lightPos - vs.ptInWorld);
-            return ps.trk.begin(s, ps.ray, ps.rng, 0.f) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+    // One light is picked uniformly (pathtracer.cu:179).  With SVR_OPT_ENV_NEE the environment light is one more candidate:
+    // sampled by importance from its luminance (sample_env) and weighted with BOTH lobes of the hybrid model -- exactly what
+    // the bounce ray would have collected from the sky on leaving the medium (it no longer does: event_bounce clears envEsc).
+    // (the sky reaches a vertex through the ray that leaves it, and the reference traces that ray only if another iteration
+    // of its bounce loop follows, pathtracer.cu:216: the last vertex of a path gets no environment light)
+    const bool envNee = MODE == 3 && ps.k + 1 < traceDepth;
+    const uint32_t nPick = s.numLights + (envNee ? 1u : 0u);
+    if (nPick != 0) {
+        int lightId = (int)((float)nPick * ps.rng.next());
+        lightId = lightId < (int)nPick ? lightId : (int)nPick - 1;
+        if (lightId < (int)s.numLights) {
+            float3 lightPos, wi;
+            float pdf;
+            float3 Li = sample_light<EXACT_PI>(s.lights[lightId], vs.ptInWorld, ps.rng, &lightPos, &wi, &pdf);
+            if (pdf > 0.f && max3(Li) > 0.f) {
+                ps.pending = (float)nPick * bsdf(vs, wi, ps.st) * Li / pdf;
+                // transmittance.h:10-17: track from the sample toward the light through the whole box
+                ps.ray.orig = vs.ptInWorld;
+                ps.ray.dir = normalize(lightPos - vs.ptInWorld);
+                return ps.trk.begin(s, ps.ray, ps.rng, 0.f) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+            }
+        } else if (envNee) {
+            float pdf;
+            const float xi1 = ps.rng.next(), xi2 = ps.rng.next();
+            const float3 wi = sample_env(s.envS, xi1, xi2, &pdf);
+            const float3 Li = env_radiance(s.env, wi);
+            if (pdf > 0.f && max3(Li) > 0.f) {
+                ps.pending = (float)nPick * lobes_as_sampled(vs, wi, ps.Pbrdf) * Li / pdf;
+                ps.ray.orig = vs.ptInWorld;
+                ps.ray.dir = wi;
+                return ps.trk.begin(s, ps.ray, ps.rng, 0.f) ? NEXT_TRACK : NEXT_FLIGHT_MISSED;
+            }
         }
     }
     return NEXT_BOUNCE;  // no shadow ray to fly: bounce with nothing pending
@@ -535,12 +590,17 @@ SVR_DEV Next event_bounce(const DevScene& s, PathState<MODE>& ps, bool occluded,
     float pdf = 0.f;
     float3 f = sample_bsdf<EXACT_PI>(vs, &wi, &pdf, ps.rng, ps.st);
     float cosTerm = fabsf(dot(normalize(vs.gradient), wi));
-    if (max3(f) > 0.f && pdf > 0.f) {
+    const bool sampled = max3(f) > 0.f && pdf > 0.f;
+    if (sampled) {
         if (ps.st == ISOTROPIC)
             ps.T *= f / (pdf * (1.f - ps.Pbrdf));
         else
             ps.T *= f * cosTerm / (pdf * ps.Pbrdf);
     }
+    // With the environment as a next-event target this vertex has been lit by it through both lobes; the bounce ray must not
+    // collect it again.  A bounce whose BSDF sample was void keeps its throughput in the reference (the `if` above): that part
+    // of the reference's estimator is not covered by the lobes, so such a ray still collects the sky on leaving.
+    if (MODE == 3) ps.envEsc = !sampled;
     ps.ray.orig = vs.ptInWorld;
     ps.ray.dir = wi;
     if (ps.k >= 3) {
@@ -652,7 +712,7 @@ SVR_DEV void trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE>&
         if (next == NEXT_BOUNCE || ps.shadow)
             next = event_bounce<MODE, COUNT>(s, ps, occluded_at(ps.trk, t), a.traceDepth, lc);
         else
-            next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
+            next = event_flight_end<MODE, COUNT>(s, ps, t, a.traceDepth, lc);
     }
     path_end<MODE>(ps);
 }
@@ -667,7 +727,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     LocalCounters<COUNT> lc;
     if (inside) {
         const uint32_t offset = idy * s.cam.imageW + idx;
-        const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0, a.lightCull != 0);
+        const PixelInfo pi = classify_pixel(s, idx, idy, MODE >= 2, a.entryCache != 0, a.lightCull != 0);
         PathState<MODE> ps;
         pixel_begin<MODE>(ps);
         for (uint32_t n = 0; n < a.nSamples; ++n) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
@@ -696,7 +756,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
-            const PixelInfo pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0, a.lightCull != 0);
+            const PixelInfo pi = classify_pixel(s, idx, idy, MODE >= 2, a.entryCache != 0, a.lightCull != 0);
             pixel_begin<MODE>(ps);
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
                 // every sample of this pixel is the constant sky (see trace_sample): the same additions, nothing else
@@ -845,7 +905,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_QUEUE_BLOCKS) patht
                                 break;
                             }
                             own = false;
-                            next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
+                            next = event_flight_end<MODE, COUNT>(s, ps, t, a.traceDepth, lc);
                         }
                         if (next == NEXT_PATH_DONE) break;
                     }
@@ -1181,7 +1241,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_PROFILE_BLOCKS) pat
                                     break;
                                 }
                                 own = false;
-                                next = event_flight_end<MODE, COUNT>(s, ps, t, lc);
+                                next = event_flight_end<MODE, COUNT>(s, ps, t, a.traceDepth, lc);
                             }
                             if (next == NEXT_PATH_DONE) break;
                         }
@@ -1729,7 +1789,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     pi.tSkip = 0.f;
     pi.lights = true;
     pi.empty = false;
-    if (inside) pi = classify_pixel(s, idx, idy, MODE == 2, a.entryCache != 0, a.lightCull != 0);
+    if (inside) pi = classify_pixel(s, idx, idy, MODE >= 2, a.entryCache != 0, a.lightCull != 0);
     ps.camLights = pi.lights;
     const float tSkip = pi.tSkip;
 
@@ -1749,7 +1809,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
 
         if (pick == PH_MARCH) {
             // a burst of macrocell visits (mode 2) / one free-flight draw (modes 0, 1)
-            const int burst = MODE == 2 ? a.marchBurst : 1;
+            const int burst = MODE >= 2 ? a.marchBurst : 1;
             for (int i = 0; i < burst; ++i) {
                 if (phase == PH_MARCH) {
                     VisitResult v = ps.trk.template visit<COUNT>(s, ps.ray, ps.rng, lc);
@@ -1790,7 +1850,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             }
         } else if (pick == PH_EVENT) {
             if (phase == PH_EVENT) {
-                Next nx = event_flight_end<MODE, COUNT>(s, ps, tEvent, lc);
+                Next nx = event_flight_end<MODE, COUNT>(s, ps, tEvent, a.traceDepth, lc);
                 if (nx == NEXT_TRACK) phase = PH_MARCH;
                 else if (nx == NEXT_PATH_DONE) {
                     path_end<MODE>(ps);
@@ -1878,6 +1938,13 @@ int launch_pathtrace(PtLaunch& a)
     if (sc.cam.imageW == 0 || sc.cam.imageH == 0) return fail_msg("render_pathtracer: setup_camera not called");
     const int mode = st.options[SVR_OPT_PT_MODE];
     sc.envEnabled = st.options[SVR_OPT_ENV_ENABLED];
+    sc.envNee = 0;
+    memset(&sc.envS, 0, sizeof(sc.envS));
+    if (sc.envEnabled && st.options[SVR_OPT_ENV_NEE] && mode == 2) {
+        int rc = ensure_env_sampler(&sc);
+        if (rc) return rc;
+        sc.envNee = 1;
+    }
     sc.shadowEstimator = st.options[SVR_OPT_SHADOW_ESTIMATOR];
     sc.seedKey = wang_hash((uint32_t)st.options[SVR_OPT_SEED]);
     if (mode == 2) {
@@ -1911,6 +1978,7 @@ int launch_pathtrace(PtLaunch& a)
     if ((shape == 2 || shape == 3) && mode == 2 && st.options[SVR_OPT_PT_PROFILE] && sc.cam.apeture == 0.f) shape = 4;
     if (shape == 4 && (mode != 2 || sc.cam.apeture != 0.f)) shape = 2;
     if (shape == 5 && mode != 2) shape = 2;
+    if (sc.envNee && shape >= 3) shape = 2;  // environment next-event estimation lives in the shared event code of shapes 0-2
     if (shape >= 2 && a.nSamples < (uint32_t)st.options[SVR_OPT_PT_WARP_MIN_SPP]) shape = 1;
     // shape 4: idle lanes take new camera samples together, once this many wait (SVR_OPT_PT_REFILL)
     if (shape == 4) a.marchBurst = st.options[SVR_OPT_PT_REFILL] > 0 ? st.options[SVR_OPT_PT_REFILL] : 8;
@@ -1928,10 +1996,11 @@ int launch_pathtrace(PtLaunch& a)
     if (a.bandPhase >= bands) return 0;
     a.bandRows = tileH;
     dim3 grid((sc.cam.imageW + tileW - 1u) / tileW, (bands - a.bandPhase + a.bandStride - 1u) / a.bandStride);
-    switch (mode) {
+    switch (sc.envNee ? 3 : mode) {
         case 0: launch_mode<0>(shape, grid, block, st.stream, sc, a, cnt); break;
         case 1: launch_mode<1>(shape, grid, block, st.stream, sc, a, cnt); break;
-        default: launch_mode<2>(shape, grid, block, st.stream, sc, a, cnt); break;
+        case 2: launch_mode<2>(shape, grid, block, st.stream, sc, a, cnt); break;
+        default: launch_mode<3>(shape, grid, block, st.stream, sc, a, cnt); break;
     }
     count_launch();
     SVR_TRY(cudaGetLastError());

@@ -30,6 +30,15 @@ struct DevGrid {
     SVR_DEV float at(float3 cf) const { return __ldg(cells + ((int)fmaf(cf.z, pyF, cf.y) * px + (int)cf.x)); }
 };
 
+// Importance sampler of the environment light: a grid of w x h direction cells over (u, v) = (phi / 2 pi, theta / pi), cell
+// probability proportional to (luminance + a floor) * sin(theta).  marg[0..h]: cumulative row probabilities;
+// cond[j * (w + 1) + 0..w]: cumulative cell probabilities within row j.  Built by svr_env_io.cu: env_sampler_build.
+struct DevEnvSampler {
+    const float* marg;
+    const float* cond;
+    int w, h;
+};
+
 struct DevScene {
     svr_volume vol;
     svr_transfer_function tf;
@@ -42,6 +51,8 @@ struct DevScene {
     uint32_t seedKey;
     int3 volDim;
     DevGrid grid;
+    int32_t envNee;           // 1 = the environment light is a next-event target (SVR_OPT_ENV_NEE); escaped bounce rays then add nothing
+    DevEnvSampler envS;
 };
 
 // ---- counters (SVR_OPT_COUNTERS) -------------------------------------------------------------
@@ -254,6 +265,46 @@ SVR_DEV float3 env_radiance(const svr_env_light& e, float3 dir)
     float v = theta * SVR_INV_PI_F;
     float4 val = tex2D<float4>(e.tex, u + e.offset.x, v + e.offset.y);
     return f3(val.x, val.y, val.z) * e.intensity;
+}
+
+// direction of (u, v) in the parameterisation env_radiance inverts: theta = acos(dir.y) = pi v, phi = atan2(dir.x, dir.z) = 2 pi u
+SVR_DEV float3 env_direction(float u, float v)
+{
+    float st, ct, sp, cp;
+    __sincosf(SVR_PI_F * v, &st, &ct);
+    __sincosf(2.f * SVR_PI_F * u, &sp, &cp);
+    return f3(st * sp, ct, st * cp);
+}
+
+// A direction with probability density *pdf (per unit solid angle) proportional to the sampler's cell weights: row by the
+// marginal, cell by the row's conditional, uniform in (u, v) within the cell.
+SVR_DEV float3 sample_env(const DevEnvSampler& e, float xi1, float xi2, float* pdf)
+{
+    int lo = 0, hi = e.h - 1;
+    while (lo < hi) {  // largest row j with marg[j] <= xi1
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(e.marg + mid) <= xi1) lo = mid;
+        else hi = mid - 1;
+    }
+    const int j = lo;
+    const float m0 = __ldg(e.marg + j), m1 = __ldg(e.marg + j + 1);
+    const float* row = e.cond + (size_t)j * (e.w + 1);
+    lo = 0;
+    hi = e.w - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(row + mid) <= xi2) lo = mid;
+        else hi = mid - 1;
+    }
+    const int i = lo;
+    const float c0 = __ldg(row + i), c1 = __ldg(row + i + 1);
+    const float pRow = m1 - m0, pCell = c1 - c0;
+    const float dv = pRow > 0.f ? (xi1 - m0) / pRow : 0.5f, du = pCell > 0.f ? (xi2 - c0) / pCell : 0.5f;
+    const float u = ((float)i + fminf(fmaxf(du, 0.f), 0.999999f)) / (float)e.w, v = ((float)j + fminf(fmaxf(dv, 0.f), 0.999999f)) / (float)e.h;
+    const float sinTheta = __sinf(SVR_PI_F * v);
+    // density in (u, v): pRow * pCell * w * h; d omega = 2 pi^2 sin(theta) du dv
+    *pdf = sinTheta > 0.f ? pRow * pCell * (float)e.w * (float)e.h / (2.f * SVR_PI_F * SVR_PI_F * sinTheta) : 0.f;
+    return env_direction(u, v);
 }
 
 // ---- BSDFs (core/bsdf/) ------------------------------------------------------------------------

@@ -50,6 +50,12 @@ struct HostState {
     unsigned autoEpoch = 0, uploadEpoch = 0;  // uploadEpoch counts svr_volume_upload / svr_tf_upload calls
     void* dStats = nullptr;
 
+    // importance sampler of the environment light (svr_env_io.cu), keyed on what it was built from
+    float* dEnvMarg = nullptr;
+    float* dEnvCond = nullptr;
+    svr_env_light envSamplerKey = {};
+    bool envSamplerValid = false;
+
     Counters* dCounters = nullptr;
     unsigned long long launches = 0;
     std::string lastError;
@@ -94,6 +100,9 @@ int ensure_grid(DevScene* scene, bool force, int maxAutoCell = 32);
 // launch + an 16-byte read-back; the ray caster's drop-in entry point, whose host may edit the table behind an unchanged
 // handle, gui/transferfunction.cpp:128-151).  Also true when no majorants exist yet.
 int tf_content_changed(const svr_transfer_function& tf, bool* changed);
+
+// Builds / refreshes the environment light's importance sampler for scene->env and fills scene->envS.
+int ensure_env_sampler(DevScene* scene);
 
 inline void count_launch(int n = 1) { state().launches += (unsigned long long)n; }
 

@@ -56,3 +56,54 @@ def test_rejected_files(tmp_path):
         assert rc != 0 and "svr_hdr_read" in err, name
     rc, _, err = _read(tmp_path / "missing.hdr")
     assert rc != 0 and "unable to load" in err
+
+
+def _stb():
+    """The reference's own decoder (stbi_loadf of utils/stb_image.h, compiled where it lies: oracle/Makefile, stbhdr)."""
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libsvr_stbhdr.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.ref_stbi_loadf.restype = C.POINTER(C.c_float)
+    return lib
+
+
+def test_decode_is_bit_exact_against_the_references_stb_image_golden(tmp_path):
+    """tests/golden/hdr_stb.npz: files and what stbi_loadf (the call at core/lights/lights.cpp:34) decodes from them,
+    frozen by tests/golden/make_hdr_golden.py where /root/reference is mounted."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hdr_stb.npz"))
+    names = sorted(k[:-5] for k in g.files if k.endswith("_file"))
+    assert len(names) >= 5
+    for name in names:
+        p = tmp_path / (name + ".hdr")
+        p.write_bytes(g[name + "_file"].tobytes())
+        rc, img, err = _read(p)
+        assert rc == 0, (name, err)
+        ref = g[name + "_stb"]
+        assert img.shape == ref.shape and np.array_equal(img.view(np.uint32), ref.view(np.uint32)), name
+    assert bool(g["stb_rejects_rgbe_signature"][0])   # a superset: this library also reads the "#?RGBE" signature
+
+
+def test_decode_is_bit_exact_against_stb_image_live(tmp_path):
+    """The same against the decoder itself on fresh random pictures (skipped where oracle/_ref/libsvr_stbhdr.so is absent)."""
+    lib = _stb()
+    if lib is None:
+        pytest.skip("oracle/_ref/libsvr_stbhdr.so not built (needs /root/reference)")
+    rng = np.random.default_rng(11)
+    for i in range(12):
+        w, h = int(rng.integers(1, 200)), int(rng.integers(1, 40))
+        img = rng.uniform(0, 1, (h, w, 3)) ** 4 * 10.0 ** rng.uniform(-6, 4)
+        img[rng.uniform(0, 1, (h, w)) < 0.2] = 0.0
+        p = H.write_hdr(tmp_path / f"r{i}.hdr", H.float_to_rgbe(img), rle=bool(i % 2))
+        wi, hi, ni = C.c_int(), C.c_int(), C.c_int()
+        ptr = lib.ref_stbi_loadf(str(p).encode(), C.byref(wi), C.byref(hi), C.byref(ni))
+        assert ptr and (wi.value, hi.value, ni.value) == (w, h, 3)
+        ref = np.ctypeslib.as_array(ptr, shape=(h, w, 3)).copy()
+        lib.ref_stbi_free(ptr)
+        rc, mine, err = _read(p)
+        assert rc == 0, err
+        assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32)), (i, w, h)
