@@ -32,11 +32,12 @@
 #include "svr_state.h"
 
 // Launch bounds of the path-tracing kernels: at most SVR_PT_MAX_THREADS threads per block and at least
-// SVR_PT_MIN_BLOCKS resident blocks per SM, i.e. a register budget of 65536 / (128 * 7) = 72 per thread
-// (28 warps per SM).  Chosen by measurement: unbounded the kernel takes 85
-// registers (20 warps per SM) and is 12% slower; at 64 registers it spills and gains nothing more.
+// SVR_PT_MIN_BLOCKS resident blocks per SM, i.e. a register budget of 65536 / (128 * 9) = 56 per thread
+// (36 warps per SM).  Chosen by measurement (DESIGN.md section 3.1, round 2, C3 per 256-spp launch): 6 blocks (80
+// registers) 9.01 ms, 7 (72) 8.55, 8 (64) 8.31, 9 (56, 314 B of spills) 8.22, 10 (48) 8.40, 12 (40) 8.43 -- the kernel
+// waits on dependent latencies (cell code, tap, table look-up), and resident warps hide them better than registers do.
 #ifndef SVR_PT_MIN_BLOCKS
-#define SVR_PT_MIN_BLOCKS 7
+#define SVR_PT_MIN_BLOCKS 9
 #endif
 #ifndef SVR_PT_MAX_THREADS
 #define SVR_PT_MAX_THREADS 128
@@ -45,8 +46,9 @@
 #ifndef SVR_PT_PROFILE_BLOCKS
 #define SVR_PT_PROFILE_BLOCKS 7
 #endif
+// (C4, one 512-spp launch: 8 blocks 431 ms, 9 blocks 419 ms, 10 blocks 429 ms)
 #ifndef SVR_PT_QUEUE_BLOCKS
-#define SVR_PT_QUEUE_BLOCKS (SVR_PT_MIN_BLOCKS + 1)
+#define SVR_PT_QUEUE_BLOCKS 9
 #endif
 
 namespace svr {
@@ -752,11 +754,25 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     LocalCounters<COUNT> lc;
     if (idy < a.y1) {
         PathState<MODE> ps;
+        PixelInfo mine;  // the classification of pixel (run start + lane): the run's pixels are classified side by side, one per lane
+        mine.tSkip = 0.f;
+        mine.lights = mine.empty = false;
         for (uint32_t i = 0; i < (uint32_t)a.warpPixels; ++i) {
             const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
-            const PixelInfo pi = classify_pixel(s, idx, idy, MODE >= 2, a.entryCache != 0, a.lightCull != 0);
+            if ((i & 31u) == 0u) {
+                // classify_pixel is a serial walk along the pixel's centre ray: 32 lanes repeating it for one pixel cost what one
+                // lane costs, so every lane takes a pixel of its own (the walk of the longest one is what the warp pays, once)
+                const uint32_t px = idx + lane;
+                if (i + lane < (uint32_t)a.warpPixels && px < s.cam.imageW)
+                    mine = classify_pixel(s, px, idy, MODE >= 2, a.entryCache != 0, a.lightCull != 0);
+                __syncwarp();
+            }
+            PixelInfo pi;
+            pi.tSkip = __shfl_sync(0xffffffffu, mine.tSkip, (int)(i & 31u));
+            pi.lights = __shfl_sync(0xffffffffu, (int)mine.lights, (int)(i & 31u)) != 0;
+            pi.empty = __shfl_sync(0xffffffffu, (int)mine.empty, (int)(i & 31u)) != 0;
             pixel_begin<MODE>(ps);
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
                 // every sample of this pixel is the constant sky (see trace_sample): the same additions, nothing else

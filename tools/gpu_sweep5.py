@@ -39,7 +39,8 @@ if "--c1" in sys.argv:
     run(cfg, "C1x256", 256, 3)
 if "--c4" in sys.argv:
     cfg = S.CONFIGS["C4"]; setup_config(r, cfg)
-    run(cfg, "C4", 128 if "--c4spp128" in sys.argv else 32, 3)
+    for c4spp in ([512, 128] if "--c4big" in sys.argv else [128 if "--c4spp128" in sys.argv else 32]):
+        run(cfg, f"C4x{c4spp}", c4spp, 2 if c4spp > 128 else 3)
 '''
 args = [a for a in sys.argv[1:] if not a.startswith("--") and a.endswith(".so")]
 flags = [a for a in sys.argv[1:] if a.startswith("--") and a != "--opts"]
