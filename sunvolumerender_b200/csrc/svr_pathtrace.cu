@@ -191,6 +191,7 @@ struct TrackLocal {
     float tau;  // optical depth still to travel before the next tentative collision
     float sig;  // majorant of the cell the tentative collision lies in
     CellRay cr;
+    float epsT;  // cr.eps(): the step that carries the walk across a cell face, computed once per ray (-1 % on C3)
 
     SVR_DEV bool begin(const DevScene& s, const Ray& ray, Philox& rng, float tSkip)
     {
@@ -209,12 +210,13 @@ struct TrackLocal {
         tMax = fminf(tFar, tB);
         if (!(t < tMax)) return false;
         tau = -logf(rng.next_one_minus());
+        epsT = cr.eps();
         return true;
     }
     template <bool COUNT>
     SVR_DEV VisitResult visit(const DevScene& s, const Ray& ray, Philox&, LocalCounters<COUNT>& lc)
     {
-        const float te = t + cr.eps();
+        const float te = t + epsT;
         const float3 cf = cr.locate(te);
         const float m = s.grid.at(cf);
         lc.add(SVR_CNT_CELLS, 1);
@@ -775,14 +777,14 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             pi.empty = __shfl_sync(0xffffffffu, (int)mine.empty, (int)(i & 31u)) != 0;
             pixel_begin<MODE>(ps);
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
-                // every sample of this pixel is the constant sky (see trace_sample): the same additions, nothing else
+                // every sample of this pixel is the constant sky (see trace_sample): nSamples times the same value, written by one lane
                 const float3 sky = (a.traceDepth != 0 && s.envEnabled) ? f3(s.env.defaultRadiance) * s.env.intensity : f3(0.f);
-                for (uint32_t n = lane; n < a.nSamples; n += 32u) {
-                    lc.add(SVR_CNT_PATHS, 1);
-                    if (MODE == 0) ps.sum += sky;
-                    else ps.L += sky;
+                if (lane == 0) {
+                    lc.add(SVR_CNT_PATHS, a.nSamples);
+                    write_pixel(s, a, offset, sky * (float)a.nSamples);
                 }
-            } else
+                continue;
+            }
             for (uint32_t n = lane; n < a.nSamples; n += 32u) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
             float3 sum = pixel_sum<MODE>(ps);
             __syncwarp();

@@ -103,7 +103,7 @@ def _lit_by_camera_rays(renderer, cfg, name):
         den = d @ n
         with np.errstate(divide="ignore", invalid="ignore"):
             t = ((c - o) @ n) / den
-        p = o + t[..., None] * d
+            p = o + t[..., None] * d
         hit |= (np.abs(den) > 1e-6) & (t >= 0) & (np.linalg.norm(p - c, axis=-1) <= l.disk.radius)
     return hit
 
