@@ -859,7 +859,7 @@ def other_workload_lines(r, a):
                     "counted": {"taps_per_step": int(taps), "scatter_events_per_sample": c["scatters"] / c["paths"], "cell_visits_per_sample": c["cells"] / c["paths"]},
                     "roofline": {"bound": "hbm", "achieved": bytes_algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_algo / (ms * 1e-3) / 1e9 / peak,
                                  "gtaps_per_s": g, "gather": dict(gather, frac_of_coherent=g / gather["coherent_gtaps_per_s"], frac_of_random=g / gather["random_gtaps_per_s"]),
-                                 "issue": issue_counters("C4", 32, "pathtrace_queue_kernel<0>"), "note": "nominal; taps counted on a launch of the same size"},
+                                 "issue": issue_counters("C4", 128, "pathtrace_queue_kernel<0>"), "note": "nominal; taps counted on a launch of the same size"},
                     "reference_cuda": reference_cuda_sample(cfg, r, 8)})
         del buf
     except Exception as e:  # e.g. not enough device memory beside the other buffers

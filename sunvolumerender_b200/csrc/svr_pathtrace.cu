@@ -653,6 +653,35 @@ SVR_DEV void write_pixel(const DevScene& s, const PtLaunch& a, uint32_t offset, 
     }
 }
 
+// The same for a pixel a whole warp has rendered (every lane holds the reduced sum): lanes 0..2 read-modify-write one
+// component each of the packed vec3 accumulator -- one coalesced 12-byte access instead of three scalar ones by one lane --
+// and tone-map it; lane 0 packs the three bytes and writes the u8vec4, and the float4 of the multi-GPU partial sums.
+SVR_DEV void write_pixel_warp(const DevScene& s, const PtLaunch& a, uint32_t offset, float3 sum, uint32_t lane)
+{
+    if (a.sum && lane == 0) {
+        float4 prev = a.clearSum ? make_float4(0.f, 0.f, 0.f, 0.f) : a.sum[offset];
+        a.sum[offset] = make_float4(prev.x + sum.x, prev.y + sum.y, prev.z + sum.z, prev.w + (float)a.nSamples);
+    }
+    if (a.hdr) {
+        float byteF = 0.f;
+        if (lane < 3) {
+            float* h = a.hdr + 3 * (size_t)offset + lane;
+            const float mine = lane == 0 ? sum.x : (lane == 1 ? sum.y : sum.z);
+            const float N0 = (float)a.firstSample;
+            float acc = a.firstSample == 0 ? 0.f : *h;  // frameNo==0 clears (pathtracer.cu:297-300)
+            if (a.nSamples == 1) acc = acc + (mine - acc) / (N0 + 1.f);  // running_estimate (pathtracer.cu:81-84); its closed form for a batch
+            else acc = (acc * N0 + mine) / (N0 + (float)a.nSamples);
+            *h = acc;
+            // hdr_to_ldr, pathtracer.cu:282-290 (component-wise: tone_map)
+            byteF = powf(1.f - expf(-(acc * 16.f) * s.cam.exposure), 1.f / (1.f / 2.2f)) * 255.f;
+        }
+        if (a.img) {
+            const float g = __shfl_sync(0xffffffffu, byteF, 1), b = __shfl_sync(0xffffffffu, byteF, 2);
+            if (lane == 0) a.img[offset] = pack_u8x4(byteF, g, b, 255.f);
+        }
+    }
+}
+
 // the flight's verdict for the binary transmittance estimator, transmittance.h:14-15
 SVR_DEV bool occluded_at(const TrackGlobal& trk, float t) { return (t > trk.tMin) && (t < trk.tMax); }
 // local-majorant flights report either a collision strictly inside (tMin, tMax) or -FLT_MAX
@@ -794,7 +823,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
                 sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
                 sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
             }
-            if (lane == 0) write_pixel(s, a, offset, sum);
+            write_pixel_warp(s, a, offset, sum, lane);
         }
     }
     lc.flush(cnt);
@@ -941,7 +970,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_QUEUE_BLOCKS) patht
                 sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
                 sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
             }
-            if (lane == 0) write_pixel(s, a, offset, sum);
+            write_pixel_warp(s, a, offset, sum, lane);
         }
     }
     lc.flush(cnt);
@@ -1374,7 +1403,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_PROFILE_BLOCKS) pat
                 sum.y += __shfl_xor_sync(FULL, sum.y, o);
                 sum.z += __shfl_xor_sync(FULL, sum.z, o);
             }
-            if (lane == 0) write_pixel(s, a, offset, sum);
+            write_pixel_warp(s, a, offset, sum, lane);
         }
     }
     lc.flush(cnt);
