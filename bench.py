@@ -280,16 +280,20 @@ def strong_scaling_line(r, a, cfg, sum_buf, rank, world, dev, barrier):
             dist.barrier()  # the next frame goes into the same buffer (a real host would double-buffer; the barrier is timed)
 
         ms_b = timed_steps(step_bands, a.steps, max(a.warmup, 3), barrier, dev)
-        # with few pixels per GPU the frame ends when the last block does: shorter blocks (runs of 1 pixel per warp) shorten that tail
-        wp0, wp_used = r.get_option(L.OPT_PT_WARP_PIXELS), r.get_option(L.OPT_PT_WARP_PIXELS)
-        if world >= 4 and wp0 > 1:
-            r.set_option(L.OPT_PT_WARP_PIXELS, 1)
-            ms_b1 = timed_steps(step_bands, a.steps, 2, barrier, dev)
-            if ms_b1 < ms_b:
-                ms_b, wp_used = ms_b1, 1
-            else:
-                r.set_option(L.OPT_PT_WARP_PIXELS, wp0)
-                step_bands()   # the last frame (checked below) is rendered with the setting that is reported
+        # With few pixels per GPU the frame ends when the last block does: shorter blocks shorten that tail -- runs of 1 pixel
+        # per warp, and / or the warps of a block splitting the samples of one row's pixels (SVR_OPT_PT_BLOCK_SPLIT).
+        wp0 = r.get_option(L.OPT_PT_WARP_PIXELS)
+        best_cfg = (wp0, 0)
+        if world >= 4:
+            for cand in ((1, 0), (wp0, 1), (1, 1)):
+                r.set_option(L.OPT_PT_WARP_PIXELS, cand[0])
+                r.set_option(L.OPT_PT_BLOCK_SPLIT, cand[1])
+                ms_c = timed_steps(step_bands, a.steps, 2, barrier, dev)
+                if ms_c < ms_b:
+                    ms_b, best_cfg = ms_c, cand
+            r.set_option(L.OPT_PT_WARP_PIXELS, best_cfg[0])
+            r.set_option(L.OPT_PT_BLOCK_SPLIT, best_cfg[1])
+            step_bands()   # the last frame (checked below) is rendered with the setting that is reported
         same = None
         if rank == 0:   # the last frame against the same samples on one GPU
             assembled = r.hdr.clone()
@@ -300,7 +304,8 @@ def strong_scaling_line(r, a, cfg, sum_buf, rank, world, dev, barrier):
         barrier()
         pf.close()
         r.set_option(L.OPT_PT_WARP_PIXELS, wp0)
-        line["split_bands"] = {"value": npix * spp / (ms_b * 1e-3), "ms_per_step": ms_b, "pixels_per_warp_run": wp_used, "exchange": "peer writes into rank 0's accumulator, completion flags, no collective "
+        r.set_option(L.OPT_PT_BLOCK_SPLIT, 0)
+        line["split_bands"] = {"value": npix * spp / (ms_b * 1e-3), "ms_per_step": ms_b, "pixels_per_warp_run": best_cfg[0], "block_split": best_cfg[1], "exchange": "peer writes into rank 0's accumulator, completion flags, no collective "
                                "(+ one barrier per frame, timed, because frames share the buffer)", "equals_single_gpu_frame": same}
     except Exception as e:  # no peer access between these GPUs
         line["split_bands"] = {"unavailable": str(e)}

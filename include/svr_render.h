@@ -139,6 +139,11 @@ enum svr_option {
      * expectation as collecting the sky on escape (0, default: what the reference's commented-out line would do), far
      * lower variance for maps with small bright features.  Ignored by the reference-twin mode and kernel shape 5. */
     SVR_OPT_ENV_NEE = 21,
+    /* sample-parallel kernel (shape 2): 1 = the warps of a block share one row of pixels and split every pixel's samples
+     * between them (batches of at least 32 samples per warp); 0 (default) = one row per warp.  A pixel then occupies a warp
+     * for a quarter of the time: shorter blocks, a shorter end of the launch -- for short frames (one frame divided over
+     * several GPUs).  The image differs from 0 only in the order of four float additions per pixel. */
+    SVR_OPT_PT_BLOCK_SPLIT = 22,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

@@ -71,6 +71,7 @@ struct PtLaunch {
     int32_t lightCull;     // 1 = classify_pixel may rule out camera-ray light hits (SVR_OPT_PT_LIGHT_CULL)
     int32_t clipped;       // some clip plane is active: the volume's box is smaller than its texture
     uint32_t bandRows;               // (out) rows per band of the kernel shape chosen
+    int32_t blockSplit;              // shape 2: the warps of a block split the samples of one row's pixels (SVR_OPT_PT_BLOCK_SPLIT)
     uint32_t bandPhase, bandStride;  // this launch renders the row bands (block rows) phase, phase + stride, ... (1 GPU: 0, 1)
 };
 
@@ -777,11 +778,16 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
 // scheduling is a few pixels instead of a 16 x 8 tile x all samples, so expensive image regions
 // spread over all SMs.  The pixel's sum is a fixed-order butterfly over the lanes: deterministic.
 // ---------------------------------------------------------------------------------------------
-template <int MODE, bool COUNT>
+// SPLIT (SVR_OPT_PT_BLOCK_SPLIT): the warps of a block share ONE row of pixels and split every pixel's samples between them
+// (warp w takes the rounds w, w + nWarps, ...; their sums meet in shared memory in a fixed order) instead of taking a row
+// each.  A pixel then occupies a warp for a quarter of the time, which shortens the end of a launch -- the last blocks of a
+// frame run with the machine half empty -- and matters when a frame is short (one frame divided over 8 GPUs).
+template <int MODE, bool COUNT, bool SPLIT>
 __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtrace_warp_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t idy = a.y0 + (blockIdx.y * a.bandStride + a.bandPhase) * (blockDim.x >> 5) + warp;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nWarps = blockDim.x >> 5;
+    const uint32_t idy = a.y0 + (blockIdx.y * a.bandStride + a.bandPhase) * (SPLIT ? 1u : nWarps) + (SPLIT ? 0u : warp);
+    __shared__ float part[SPLIT ? SVR_PT_MAX_THREADS / 32 : 1][3];
     LocalCounters<COUNT> lc;
     if (idy < a.y1) {
         PathState<MODE> ps;
@@ -808,13 +814,14 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
                 // every sample of this pixel is the constant sky (see trace_sample): nSamples times the same value, written by one lane
                 const float3 sky = (a.traceDepth != 0 && s.envEnabled) ? f3(s.env.defaultRadiance) * s.env.intensity : f3(0.f);
-                if (lane == 0) {
+                if (lane == 0 && (!SPLIT || warp == 0)) {
                     lc.add(SVR_CNT_PATHS, a.nSamples);
                     write_pixel(s, a, offset, sky * (float)a.nSamples);
                 }
                 continue;
             }
-            for (uint32_t n = lane; n < a.nSamples; n += 32u) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
+            for (uint32_t n = lane + (SPLIT ? 32u * warp : 0u); n < a.nSamples; n += (SPLIT ? 32u * nWarps : 32u))
+                trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
             float3 sum = pixel_sum<MODE>(ps);
             __syncwarp();
 #pragma unroll
@@ -823,7 +830,22 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
                 sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
                 sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
             }
-            write_pixel_warp(s, a, offset, sum, lane);
+            if (SPLIT) {
+                if (lane == 0) {
+                    part[warp][0] = sum.x;
+                    part[warp][1] = sum.y;
+                    part[warp][2] = sum.z;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    sum = f3(part[0][0], part[0][1], part[0][2]);
+                    for (uint32_t w = 1; w < nWarps; ++w) sum += f3(part[w][0], part[w][1], part[w][2]);  // fixed order: deterministic
+                    write_pixel_warp(s, a, offset, sum, lane);
+                }
+                __syncthreads();  // `part` is free for the next pixel
+            } else {
+                write_pixel_warp(s, a, offset, sum, lane);
+            }
         }
     }
     lc.flush(cnt);
@@ -1965,9 +1987,12 @@ void launch_mode(int shape, dim3 grid, int block, cudaStream_t stream, const Dev
     } else if (shape == 3) {  // launch_pathtrace() only picks it for MODE 2
         if (cnt) pathtrace_queue_kernel<true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_queue_kernel<false><<<grid, block, 0, stream>>>(sc, a, cnt);
+    } else if (shape == 2 && a.blockSplit) {
+        if (cnt) pathtrace_warp_kernel<MODE, true, true><<<grid, block, 0, stream>>>(sc, a, cnt);
+        else pathtrace_warp_kernel<MODE, false, true><<<grid, block, 0, stream>>>(sc, a, cnt);
     } else if (shape == 2) {
-        if (cnt) pathtrace_warp_kernel<MODE, true><<<grid, block, 0, stream>>>(sc, a, cnt);
-        else pathtrace_warp_kernel<MODE, false><<<grid, block, 0, stream>>>(sc, a, cnt);
+        if (cnt) pathtrace_warp_kernel<MODE, true, false><<<grid, block, 0, stream>>>(sc, a, cnt);
+        else pathtrace_warp_kernel<MODE, false, false><<<grid, block, 0, stream>>>(sc, a, cnt);
     } else if (shape == 1) {
         if (cnt) pathtrace_mega_kernel<MODE, true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_mega_kernel<MODE, false><<<grid, block, 0, stream>>>(sc, a, cnt);
@@ -2037,6 +2062,8 @@ int launch_pathtrace(PtLaunch& a)
         tileW = (uint32_t)a.warpPixels;
         tileH = (uint32_t)block / 32u;
     }
+    a.blockSplit = shape == 2 && st.options[SVR_OPT_PT_BLOCK_SPLIT] != 0 && a.nSamples >= 32u * ((uint32_t)block / 32u);
+    if (a.blockSplit) tileH = 1u;
     if (a.bandStride == 0) a.bandStride = 1;
     if (a.bandPhase >= a.bandStride) return fail_msg("render_pathtracer: band phase must be below the band stride");
     const uint32_t bands = ((a.y1 - a.y0) + tileH - 1u) / tileH;

@@ -610,3 +610,45 @@ def test_row_bands_assemble_to_the_single_launch_frame(renderer):
         torch.cuda.synchronize()
         assert rows in (4, 8)
         assert torch.equal(parts, whole), shape
+
+
+def test_block_split_equals_one_row_per_warp_up_to_summation_order(renderer):
+    """SVR_OPT_PT_BLOCK_SPLIT: the warps of a block split the samples of one row's pixels.  Every sample is the same pure
+    function of (seed, pixel, sample); four partial sums per pixel are added in a fixed order instead of one butterfly."""
+    cfg = small_config(n=96, w=150, h=101, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=3)
+    setup(renderer, cfg)
+    W, H = cfg.width, cfg.height
+    for mode, spp in ((2, 256), (2, 160), (0, 128)):
+        renderer.set_option(L.OPT_PT_MODE, mode)
+        imgs = {}
+        for split, wp, blk in ((0, 2, 128), (1, 2, 128), (1, 1, 128), (1, 5, 64)):
+            renderer.set_option(L.OPT_PT_BLOCK_SPLIT, split)
+            renderer.set_option(L.OPT_PT_WARP_PIXELS, wp)
+            renderer.set_option(L.OPT_PT_BLOCK, blk)
+            renderer.frame_no = 0
+            renderer.render_pathtracer_spp(spp, 3)
+            torch.cuda.synchronize()
+            imgs[(split, wp, blk)] = renderer.hdr_image().clone()
+        base = imgs[(0, 2, 128)]
+        assert float(base.max()) > 0
+        assert torch.allclose(imgs[(1, 2, 128)], base, rtol=2e-5, atol=1e-6)
+        assert torch.equal(imgs[(1, 1, 128)], imgs[(1, 2, 128)])      # the run length does not enter the result
+        assert torch.allclose(imgs[(1, 5, 64)], base, rtol=2e-5, atol=1e-6)   # two warps per block: another fixed order
+    # row bands (one row per band when the block is split) assemble to the single-launch frame, bit for bit
+    renderer.set_option(L.OPT_PT_MODE, 2)
+    renderer.set_option(L.OPT_PT_BLOCK_SPLIT, 1)
+    renderer.set_option(L.OPT_PT_WARP_PIXELS, 2)
+    renderer.set_option(L.OPT_PT_BLOCK, 128)
+    whole = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
+    renderer.accumulate(whole, 3, 0, 128, clear=True)
+    parts = torch.full((H * W * 4,), -1.0, dtype=torch.float32, device="cuda")
+    for phase in range(3):
+        rows = renderer.accumulate_bands(parts, 3, 0, 128, phase, 3, clear=True)
+    torch.cuda.synchronize()
+    assert rows == 1 and torch.equal(parts, whole)
+    # a batch too small to give every warp a round falls back to one row per warp
+    renderer.accumulate(whole, 3, 0, 64, clear=True)
+    renderer.set_option(L.OPT_PT_BLOCK_SPLIT, 0)
+    renderer.accumulate(parts, 3, 0, 64, clear=True)
+    torch.cuda.synchronize()
+    assert torch.equal(parts, whole)

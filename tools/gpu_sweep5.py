@@ -8,12 +8,12 @@ from sunvolumerender_b200 import _lib as L, scene as S
 from sunvolumerender_b200.render import Renderer, setup_config
 tag, optsets = sys.argv[1], sys.argv[2].split(";")
 KEYS = {"profile": L.OPT_PT_PROFILE, "refill": L.OPT_PT_REFILL, "kernel": L.OPT_PT_KERNEL, "cell": L.OPT_MACROCELL_SIZE, "wp": L.OPT_PT_WARP_PIXELS,
-        "qdepth": L.OPT_PT_QUEUE_MIN_DEPTH, "block": L.OPT_PT_BLOCK, "shadow": L.OPT_SHADOW_ESTIMATOR}
+        "qdepth": L.OPT_PT_QUEUE_MIN_DEPTH, "block": L.OPT_PT_BLOCK, "shadow": L.OPT_SHADOW_ESTIMATOR, "split": L.OPT_PT_BLOCK_SPLIT}
 r = Renderer(0)
 def run(cfg, t, spp, reps=4):
     buf = torch.zeros(cfg.width * cfg.height * 4, dtype=torch.float32, device="cuda")
     for o in optsets:
-        defaults = {"profile": 0, "refill": 0, "kernel": 2, "cell": 0, "wp": 4, "qdepth": 8, "block": 128, "shadow": 0}
+        defaults = {"profile": 0, "refill": 0, "kernel": 2, "cell": 0, "wp": 2, "qdepth": 8, "block": 128, "shadow": 0, "split": 0}
         for kv in o.split(","):
             if kv:
                 k, v = kv.split("="); defaults[k] = int(v)
