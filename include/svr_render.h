@@ -144,6 +144,11 @@ enum svr_option {
      * for a quarter of the time: shorter blocks, a shorter end of the launch -- for short frames (one frame divided over
      * several GPUs).  The image differs from 0 only in the order of four float additions per pixel. */
     SVR_OPT_PT_BLOCK_SPLIT = 22,
+    /* 1 (default) = the lane-per-pixel kernel (render_pathtracer: one sample per call) keeps every pixel's classification --
+     * how far its camera rays can skip empty space, whether they can hit a light, whether the pixel is all sky -- across the
+     * frames of a progressive render and recomputes it only after something a pixel can see has changed (any setup_*, upload or
+     * option).  Images are bit-identical either way (only empty space is skipped); 0 = classify in every call. */
+    SVR_OPT_PT_PIXEL_CACHE = 23,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the

@@ -38,6 +38,7 @@ HostState& state()
         p->options[SVR_OPT_PT_LIGHT_CULL] = 1;
         p->options[SVR_OPT_PT_PROFILE] = 0;  // measured slower than shape 2 on every BASELINE configuration
         p->options[SVR_OPT_PT_REFILL] = 0;
+        p->options[SVR_OPT_PT_PIXEL_CACHE] = 1;
         // A host that only knows the reference's seven entry points (gui/canvas.cpp) cannot call
         // svr_set_option: the same switches are read once from the environment.
         static const struct { const char* name; int key, lo, hi; } kEnv[] = {
@@ -101,6 +102,7 @@ extern "C" void setup_volume(const svr_volume* vol)
     // sampled fingerprint of the voxels is compared against the one taken when the ranges were built.
     if (st.gridArray && !same_volume_resource(st.scene.vol, *vol)) release_grid(st);
     st.scene.vol = *vol;
+    st.sceneEpoch++;
     st.majorantValid = false;  // densityScale / array may have changed
     st.fingerprintDue = true;  // checked at the next grid use (needs the stream; setup_* must stay cheap)
     if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
@@ -110,6 +112,7 @@ extern "C" void setup_transferfunction(const svr_transfer_function* tf)
 {
     HostState& st = state();
     st.scene.tf = *tf;
+    st.sceneEpoch++;
     st.majorantValid = false;  // every TF edit invalidates the local majorants
     if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
 }
@@ -118,6 +121,7 @@ extern "C" void setup_camera(const svr_camera* cam)
 {
     HostState& st = state();
     st.scene.cam = *cam;
+    st.sceneEpoch++;
     if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
 }
 
@@ -125,6 +129,7 @@ extern "C" void setup_env_lights(const svr_env_light* light)
 {
     HostState& st = state();
     st.scene.env = *light;
+    st.sceneEpoch++;
     if (st.options[SVR_OPT_SETUP_SYNC]) SVR_FATAL(cudaDeviceSynchronize());
 }
 
@@ -134,6 +139,7 @@ extern "C" void setup_area_lights(svr_area_light* lights, uint32_t n)
     if (n > SVR_MAX_LIGHT_SOURCES) n = SVR_MAX_LIGHT_SOURCES;
     HostState& st = state();
     st.scene.numLights = n;
+    st.sceneEpoch++;
     for (uint32_t i = 0; i < n; ++i) st.scene.lights[i] = lights[i];
 }
 
@@ -161,6 +167,10 @@ extern "C" int svr_set_device(int device)
     cudaFree(st.dStats);
     cudaFree(st.dFingerprint);
     cudaFree(st.dTfHash);
+    cudaFree(st.dPixelCache);
+    st.dPixelCache = nullptr;
+    st.pixelCacheCap = 0;
+    st.sceneEpoch++;
     cudaFree(st.dEnvMarg);
     cudaFree(st.dEnvCond);
     st.dEnvMarg = st.dEnvCond = nullptr;
@@ -224,6 +234,7 @@ extern "C" int svr_set_option(int key, int value)
         default: break;
     }
     st.options[key] = value;
+    st.sceneEpoch++;
     return 0;
 }
 
@@ -409,6 +420,7 @@ extern "C" int svr_volume_upload(const svr_volume* vol, const void* data, int da
     // same dims, new contents: the grid's allocations stay, its range stage reruns at the next render
     if (rd.res.array.array == st.gridArray) st.rangeValid = false;
     st.uploadEpoch++;
+    st.sceneEpoch++;
     return 0;
 }
 
@@ -483,6 +495,7 @@ extern "C" int svr_tf_upload(svr_transfer_function* tf, const float* host_rgba, 
     tf->maxOpacity = maxOpacity;
     st.majorantValid = false;
     st.uploadEpoch++;
+    st.sceneEpoch++;
     return 0;
 }
 

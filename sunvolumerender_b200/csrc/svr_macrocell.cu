@@ -353,6 +353,7 @@ void release_grid(HostState& st)
     st.dMajorant = nullptr;
     st.dDist[0] = st.dDist[1] = nullptr;
     st.dOcc = nullptr;
+    st.sceneEpoch++;
     st.gridArray = nullptr;
     st.autoArray = nullptr;  // the automatic cell size is re-derived for whatever volume comes next
     st.rangeValid = false;
@@ -501,6 +502,7 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
         count_launch(7);
         SVR_TRY(cudaGetLastError());
         if (majorantsRebuilt) *majorantsRebuilt = true;
+        st.sceneEpoch++;
         st.majorantValid = true;
         st.majorantDensityScale = vol.densityScale;
         st.majorantTfArray = tarr;

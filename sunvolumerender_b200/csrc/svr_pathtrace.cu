@@ -71,6 +71,8 @@ struct PtLaunch {
     int32_t lightCull;     // 1 = classify_pixel may rule out camera-ray light hits (SVR_OPT_PT_LIGHT_CULL)
     int32_t clipped;       // some clip plane is active: the volume's box is smaller than its texture
     uint32_t bandRows;               // (out) rows per band of the kernel shape chosen
+    int32_t pixelCache;              // shape 1: 0 classify, 1 classify (with the walk) and store into pixelInfo, 2 load from pixelInfo
+    float2* pixelInfo;               // (tSkip, flags: bit 0 lights, bit 1 empty) per pixel
     int32_t blockSplit;              // shape 2: the warps of a block split the samples of one row's pixels (SVR_OPT_PT_BLOCK_SPLIT)
     uint32_t bandPhase, bandStride;  // this launch renders the row bands (block rows) phase, phase + stride, ... (1 GPU: 0, 1)
 };
@@ -761,7 +763,18 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     LocalCounters<COUNT> lc;
     if (inside) {
         const uint32_t offset = idy * s.cam.imageW + idx;
-        const PixelInfo pi = classify_pixel(s, idx, idy, MODE >= 2, a.entryCache != 0, a.lightCull != 0);
+        PixelInfo pi;
+        if (a.pixelCache == 2) {
+            // a later frame of a progressive render: what was found out about this pixel in the first one
+            const float2 c = a.pixelInfo[offset];
+            const uint32_t f = __float_as_uint(c.y);
+            pi.tSkip = c.x;
+            pi.lights = (f & 1u) != 0u;
+            pi.empty = (f & 2u) != 0u;
+        } else {
+            pi = classify_pixel(s, idx, idy, MODE >= 2, a.entryCache != 0 || a.pixelCache == 1, a.lightCull != 0);
+            if (a.pixelCache == 1) a.pixelInfo[offset] = make_float2(pi.tSkip, __uint_as_float((pi.lights ? 1u : 0u) | (pi.empty ? 2u : 0u)));
+        }
         PathState<MODE> ps;
         pixel_begin<MODE>(ps);
         for (uint32_t n = 0; n < a.nSamples; ++n) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
@@ -2062,6 +2075,30 @@ int launch_pathtrace(PtLaunch& a)
         tileW = (uint32_t)a.warpPixels;
         tileH = (uint32_t)block / 32u;
     }
+    // the lane-per-pixel kernel keeps its per-pixel classification across the frames of a progressive render
+    a.pixelCache = 0;
+    a.pixelInfo = nullptr;
+    bool storeCache = false;
+    if (shape == 1 && st.options[SVR_OPT_PT_PIXEL_CACHE] && a.y0 == 0 && a.y1 >= sc.cam.imageH && a.bandStride <= 1) {
+        const size_t npix = (size_t)sc.cam.imageW * sc.cam.imageH;
+        if (st.pixelCacheCap < npix) {
+            cudaFree(st.dPixelCache);
+            st.dPixelCache = nullptr;
+            st.pixelCacheCap = 0;
+            if (cudaMalloc(&st.dPixelCache, npix * sizeof(float2)) == cudaSuccess) st.pixelCacheCap = npix;
+            else cudaGetLastError();
+            st.pixelCacheEpoch = 0;
+        }
+        if (st.dPixelCache) {
+            const int key = sc.envNee ? 3 : mode;
+            const bool valid = st.pixelCacheEpoch == st.sceneEpoch && st.pixelCacheW == sc.cam.imageW && st.pixelCacheH == sc.cam.imageH &&
+                               st.pixelCacheMode == key;
+            a.pixelCache = valid ? 2 : 1;
+            a.pixelInfo = st.dPixelCache;
+            storeCache = !valid;
+            st.pixelCacheMode = key;
+        }
+    }
     a.blockSplit = shape == 2 && st.options[SVR_OPT_PT_BLOCK_SPLIT] != 0 && a.nSamples >= 32u * ((uint32_t)block / 32u);
     if (a.blockSplit) tileH = 1u;
     if (a.bandStride == 0) a.bandStride = 1;
@@ -2078,6 +2115,11 @@ int launch_pathtrace(PtLaunch& a)
     }
     count_launch();
     SVR_TRY(cudaGetLastError());
+    if (storeCache) {
+        st.pixelCacheEpoch = st.sceneEpoch;
+        st.pixelCacheW = sc.cam.imageW;
+        st.pixelCacheH = sc.cam.imageH;
+    }
     return 0;
 }
 

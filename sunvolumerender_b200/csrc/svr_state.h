@@ -56,6 +56,14 @@ struct HostState {
     svr_env_light envSamplerKey = {};
     bool envSamplerValid = false;
 
+    // Per-pixel classification (classify_pixel: entry skip, light cull, all-sky flag) kept across the 1-sample-per-call frames
+    // of a progressive render: valid while sceneEpoch has not moved since it was stored
+    float2* dPixelCache = nullptr;
+    size_t pixelCacheCap = 0;
+    unsigned long long sceneEpoch = 1, pixelCacheEpoch = 0;  // sceneEpoch: bumped by everything that can change what a pixel sees
+    uint32_t pixelCacheW = 0, pixelCacheH = 0;
+    int pixelCacheMode = -1;
+
     Counters* dCounters = nullptr;
     unsigned long long launches = 0;
     std::string lastError;
