@@ -51,6 +51,7 @@
 #define SVR_PT_QUEUE_BLOCKS 9
 #endif
 
+
 namespace svr {
 Counters* device_counters();
 
@@ -918,8 +919,171 @@ SVR_DEV float queue_pop(const float* q, int idx, PathState<2>& ps)
     return q[6 * SVR_QUEUE_CAP + idx];
 }
 
+// ---- work items, the scatter event as a function and paired flights (shared by shapes 3 and 5) -------------------------------
+// Capacities: every ray in the pool can become one event, so nEv + nPool <= SVR_EVQ_CAP is kept at all times (a flight
+// phase can then always empty the pool); an event phase turns up to 32 events into up to 64 rays, a camera batch adds 32.
+// The more rays a flight phase starts with, the better its lanes stay packed (rays per lane), at the price of shared memory.
+// Measured on C4 (128 spp per launch, round 2): 64 / 64 at 6 blocks per SM 153.6 ms, 96 / 128 at 4 blocks 185 ms, 128 / 160 at
+// 3 blocks 211 ms, 192 / 224 at 2 blocks 259 ms -- the kernel is bound by memory latency, and resident warps buy more than
+// packed lanes (shape 3 at 8 blocks per SM: 120.8 ms).
+#ifndef SVR_POOL_CAP
+#define SVR_POOL_CAP 64
+#endif
+#ifndef SVR_EVQ_CAP
+#define SVR_EVQ_CAP 64
+#endif
+constexpr int SVR_ITEM_WORDS = 13;   // orig 3, dir 3, a 3 (throughput / contribution), x (optical depth left | collision parameter), meta, c0, c1
+constexpr int SVR_POOL_SLOTS = 16;   // pixels of a warp's run
+#ifndef SVR_POOL_CHUNK
+#define SVR_POOL_CHUNK 24
+#endif
+#ifndef SVR_PT_POOL_BLOCKS
+#define SVR_PT_POOL_BLOCKS 6
+#endif
+enum RayKind { RAY_CAMERA = 0, RAY_BOUNCE = 1, RAY_SHADOW = 2 };
+
+struct WorkItem {
+    float3 o, d, a;
+    float x;
+    uint32_t meta, c0, c1;  // meta: bounce count (20 bits) | pixel slot << 20 | kind << 26
+    SVR_DEV uint32_t k() const { return meta & 0xfffffu; }
+    SVR_DEV uint32_t slot() const { return (meta >> 20) & 63u; }
+    SVR_DEV uint32_t kind() const { return meta >> 26; }
+    static SVR_DEV uint32_t pack(uint32_t k, uint32_t slot, uint32_t kind) { return k | (slot << 20) | (kind << 26); }
+};
+
+template <int CAP>
+SVR_DEV void item_store(float* q, int idx, const WorkItem& it)
+{
+    q[0 * CAP + idx] = it.o.x;
+    q[1 * CAP + idx] = it.o.y;
+    q[2 * CAP + idx] = it.o.z;
+    q[3 * CAP + idx] = it.d.x;
+    q[4 * CAP + idx] = it.d.y;
+    q[5 * CAP + idx] = it.d.z;
+    q[6 * CAP + idx] = it.a.x;
+    q[7 * CAP + idx] = it.a.y;
+    q[8 * CAP + idx] = it.a.z;
+    q[9 * CAP + idx] = it.x;
+    q[10 * CAP + idx] = __uint_as_float(it.meta);
+    q[11 * CAP + idx] = __uint_as_float(it.c0);
+    q[12 * CAP + idx] = __uint_as_float(it.c1);
+}
+
+template <int CAP>
+SVR_DEV WorkItem item_load(const float* q, int idx)
+{
+    WorkItem it;
+    it.o = f3(q[0 * CAP + idx], q[1 * CAP + idx], q[2 * CAP + idx]);
+    it.d = f3(q[3 * CAP + idx], q[4 * CAP + idx], q[5 * CAP + idx]);
+    it.a = f3(q[6 * CAP + idx], q[7 * CAP + idx], q[8 * CAP + idx]);
+    it.x = q[9 * CAP + idx];
+    it.meta = __float_as_uint(q[10 * CAP + idx]);
+    it.c0 = __float_as_uint(q[11 * CAP + idx]);
+    it.c1 = __float_as_uint(q[12 * CAP + idx]);
+    return it;
+}
+
+// radiance into the pixel's fixed-point sum (2^-32; contributions are non-negative)
+SVR_DEV void accum_add(unsigned long long* acc, uint32_t slot, float3 v)
+{
+    const float sc = 4294967296.f, top = 4.0e9f;
+    if (v.x > 0.f) atomicAdd(acc + slot * 3 + 0, (unsigned long long)(fminf(v.x, top) * sc));
+    if (v.y > 0.f) atomicAdd(acc + slot * 3 + 1, (unsigned long long)(fminf(v.y, top) * sc));
+    if (v.z > 0.f) atomicAdd(acc + slot * 3 + 2, (unsigned long long)(fminf(v.z, top) * sc));
+}
+
+
+// One scatter event as a function of the collision alone (pathtracer.cu:214-276): the camera ray's light hit, shading, the
+// light sample -- which becomes a SHADOW ray that carries its whole contribution T * nLights * bsdf * Li / pdf and a random
+// stream of its own, and owes the path nothing afterwards -- and the BSDF sample with Russian roulette, which becomes the
+// BOUNCE ray.  `direct`: radiance to add at once (a camera ray that meets a light before its collision ends there).
+template <bool COUNT>
+SVR_DEV void scatter_event(const DevScene& s, uint32_t traceDepth, bool camLights, const WorkItem& ev, WorkItem& sh, bool& haveShadow, WorkItem& bo,
+                           bool& haveBounce, float3& direct, LocalCounters<COUNT>& lc)
+{
+    const uint32_t k = ev.k(), slot = ev.slot();
+    const float t = ev.x;
+    haveShadow = haveBounce = false;
+    if (k == 0 && camLights) {
+        // the camera ray may hit a light before its collision (pathtracer.cu:214-229)
+        Ray cr;
+        cr.orig = ev.o;
+        cr.dir = ev.d;
+        LightHit ls;
+        if (nearest_light(s, cr, &ls) && ls.t < t) {
+            const float cosTerm = dot(ls.normal, -ev.d);
+            direct = ev.a * ls.radiance * (cosTerm <= 0.f ? 0.f : 1.f);
+            return;
+        }
+    }
+    Philox rng;
+    rng.c0 = ev.c0;
+    rng.c1 = ev.c1;
+    rng.r1 = 0;
+    rng.have = 0;
+    VolumeSample vs;
+    vs.wo = -ev.d;
+    vs.ptInWorld = ev.o + t * ev.d;
+    const float intensity = intensity_at(s.vol, vs.ptInWorld);
+    vs.color_opacity = tf_at(s.tf, intensity);
+    vs.gradient = gradient_at(s.vol, vs.ptInWorld);
+    const float gradientMagnitude = sqrtf(dot(vs.gradient, vs.gradient));
+    lc.add(SVR_CNT_SHADE_TAPS, 7);
+    lc.add(SVR_CNT_TF_LOOKUPS, 1);
+    lc.add(SVR_CNT_SCATTERS, 1);
+    const float gf = s.vol.gradientFactor;
+    const float Pbrdf = vs.color_opacity.w * (1.f - expf(-25.f * gf * gf * gf * gradientMagnitude * 65535.f * s.vol.invMaxMagnitude));
+    const ShadingType st = (rng.next() < Pbrdf) ? BRDF : ISOTROPIC;
+    // estimate_direct_light (pathtracer.cu:171-198)
+    if (s.numLights != 0) {
+        int lightId = (int)((float)s.numLights * rng.next());
+        lightId = lightId < (int)s.numLights ? lightId : (int)s.numLights - 1;
+        float3 lightPos, wi;
+        float pdf;
+        const float3 Li = sample_light<false>(s.lights[lightId], vs.ptInWorld, rng, &lightPos, &wi, &pdf);
+        if (pdf > 0.f && max3(Li) > 0.f) {
+            sh.o = vs.ptInWorld;
+            sh.d = normalize(lightPos - vs.ptInWorld);
+            sh.a = ev.a * ((float)s.numLights * bsdf(vs, wi, st) * Li / pdf);
+            sh.x = -1.f;
+            sh.meta = WorkItem::pack(k, slot, RAY_SHADOW);
+            sh.c0 = rng.c0;
+            sh.c1 = ev.c1 ^ 0xA511E9B3u;  // a stream of its own: it flies beside the bounce ray
+            haveShadow = max3(sh.a) > 0.f;
+        }
+    }
+    // the bounce (pathtracer.cu:257-276); the last bounce's BSDF sample would never be used
+    if (k + 1 < traceDepth) {
+        float3 wi = f3(0.f);
+        float pdf = 0.f;
+        const float3 f = sample_bsdf<false>(vs, &wi, &pdf, rng, st);
+        const float cosTerm = fabsf(dot(normalize(vs.gradient), wi));
+        float3 T = ev.a;
+        if (max3(f) > 0.f && pdf > 0.f) {
+            if (st == ISOTROPIC) T *= f / (pdf * (1.f - Pbrdf));
+            else T *= f * cosTerm / (pdf * Pbrdf);
+        }
+        bool alive = true;
+        if (k >= 3) alive = !russian_roulette<false>(&T, rng);
+        if (alive) {
+            bo.o = vs.ptInWorld;
+            bo.d = wi;
+            bo.a = T;
+            bo.x = -1.f;
+            bo.meta = WorkItem::pack(k + 1, slot, RAY_BOUNCE);
+            bo.c0 = rng.c0;
+            bo.c1 = ev.c1;
+            haveBounce = true;
+        }
+    }
+}
+
 // One more block per SM than the other shapes (64 registers, some spills): this kernel serves incoherent deep
 // paths in volumes that miss the caches, where more warps in flight pay (C4: 130 -> 125 ms per 128 spp).
+// (Round 2 also tried flying the shadow ray and the bounce ray of a scatter event in ONE loop, their cell loads and taps issued
+// side by side -- two outstanding fetches per lane: 216 ms per 128 spp on C4 against 117; both halves of the loop run with
+// the lanes of either ray, 51 % more warp instructions, and two walks' state spills: profiles/r02/pt_c4_paired_flights_experiment.summary.txt.)
 template <bool COUNT>
 __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_QUEUE_BLOCKS) pathtrace_queue_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
@@ -1468,79 +1632,6 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_PROFILE_BLOCKS) pat
 // A path is still a pure function of (seed, pixel, sample); the shadow ray draws from a stream of its own (it flies
 // concurrently with the bounce ray), so walks differ from shapes 1-3: parity is statistical.
 // ---------------------------------------------------------------------------------------------
-// Capacities: every ray in the pool can become one event, so nEv + nPool <= SVR_EVQ_CAP is kept at all times (a flight
-// phase can then always empty the pool); an event phase turns up to 32 events into up to 64 rays, a camera batch adds 32.
-// The more rays a flight phase starts with, the better its lanes stay packed (rays per lane), at the price of shared memory.
-// Measured on C4 (128 spp per launch, round 2): 64 / 64 at 6 blocks per SM 153.6 ms, 96 / 128 at 4 blocks 185 ms, 128 / 160 at
-// 3 blocks 211 ms, 192 / 224 at 2 blocks 259 ms -- the kernel is bound by memory latency, and resident warps buy more than
-// packed lanes (shape 3 at 8 blocks per SM: 120.8 ms).
-#ifndef SVR_POOL_CAP
-#define SVR_POOL_CAP 64
-#endif
-#ifndef SVR_EVQ_CAP
-#define SVR_EVQ_CAP 64
-#endif
-constexpr int SVR_ITEM_WORDS = 13;   // orig 3, dir 3, a 3 (throughput / contribution), x (optical depth left | collision parameter), meta, c0, c1
-constexpr int SVR_POOL_SLOTS = 16;   // pixels of a warp's run
-#ifndef SVR_POOL_CHUNK
-#define SVR_POOL_CHUNK 24
-#endif
-#ifndef SVR_PT_POOL_BLOCKS
-#define SVR_PT_POOL_BLOCKS 6
-#endif
-enum RayKind { RAY_CAMERA = 0, RAY_BOUNCE = 1, RAY_SHADOW = 2 };
-
-struct WorkItem {
-    float3 o, d, a;
-    float x;
-    uint32_t meta, c0, c1;  // meta: bounce count (20 bits) | pixel slot << 20 | kind << 26
-    SVR_DEV uint32_t k() const { return meta & 0xfffffu; }
-    SVR_DEV uint32_t slot() const { return (meta >> 20) & 63u; }
-    SVR_DEV uint32_t kind() const { return meta >> 26; }
-    static SVR_DEV uint32_t pack(uint32_t k, uint32_t slot, uint32_t kind) { return k | (slot << 20) | (kind << 26); }
-};
-
-template <int CAP>
-SVR_DEV void item_store(float* q, int idx, const WorkItem& it)
-{
-    q[0 * CAP + idx] = it.o.x;
-    q[1 * CAP + idx] = it.o.y;
-    q[2 * CAP + idx] = it.o.z;
-    q[3 * CAP + idx] = it.d.x;
-    q[4 * CAP + idx] = it.d.y;
-    q[5 * CAP + idx] = it.d.z;
-    q[6 * CAP + idx] = it.a.x;
-    q[7 * CAP + idx] = it.a.y;
-    q[8 * CAP + idx] = it.a.z;
-    q[9 * CAP + idx] = it.x;
-    q[10 * CAP + idx] = __uint_as_float(it.meta);
-    q[11 * CAP + idx] = __uint_as_float(it.c0);
-    q[12 * CAP + idx] = __uint_as_float(it.c1);
-}
-
-template <int CAP>
-SVR_DEV WorkItem item_load(const float* q, int idx)
-{
-    WorkItem it;
-    it.o = f3(q[0 * CAP + idx], q[1 * CAP + idx], q[2 * CAP + idx]);
-    it.d = f3(q[3 * CAP + idx], q[4 * CAP + idx], q[5 * CAP + idx]);
-    it.a = f3(q[6 * CAP + idx], q[7 * CAP + idx], q[8 * CAP + idx]);
-    it.x = q[9 * CAP + idx];
-    it.meta = __float_as_uint(q[10 * CAP + idx]);
-    it.c0 = __float_as_uint(q[11 * CAP + idx]);
-    it.c1 = __float_as_uint(q[12 * CAP + idx]);
-    return it;
-}
-
-// radiance into the pixel's fixed-point sum (2^-32; contributions are non-negative)
-SVR_DEV void accum_add(unsigned long long* acc, uint32_t slot, float3 v)
-{
-    const float sc = 4294967296.f, top = 4.0e9f;
-    if (v.x > 0.f) atomicAdd(acc + slot * 3 + 0, (unsigned long long)(fminf(v.x, top) * sc));
-    if (v.y > 0.f) atomicAdd(acc + slot * 3 + 1, (unsigned long long)(fminf(v.y, top) * sc));
-    if (v.z > 0.f) atomicAdd(acc + slot * 3 + 2, (unsigned long long)(fminf(v.z, top) * sc));
-}
-
 template <bool COUNT>
 __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_POOL_BLOCKS) pathtrace_pool_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
@@ -1600,83 +1691,9 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_POOL_BLOCKS) pathtr
                 WorkItem sh, bo;
                 if (active) {
                     const WorkItem ev = item_load<SVR_EVQ_CAP>(evq, nEv + (int)lane);
-                    const uint32_t k = ev.k(), slot = ev.slot();
-                    const float t = ev.x;
-                    bool done = false;
-                    if (k == 0 && (pflag[slot] & 1u)) {
-                        // the camera ray may hit a light before its collision (pathtracer.cu:214-229)
-                        Ray cr;
-                        cr.orig = ev.o;
-                        cr.dir = ev.d;
-                        LightHit ls;
-                        if (nearest_light(s, cr, &ls) && ls.t < t) {
-                            const float cosTerm = dot(ls.normal, -ev.d);
-                            accum_add(acc, slot, ev.a * ls.radiance * (cosTerm <= 0.f ? 0.f : 1.f));
-                            done = true;
-                        }
-                    }
-                    if (!done) {
-                        Philox rng;
-                        rng.c0 = ev.c0;
-                        rng.c1 = ev.c1;
-                        rng.r1 = 0;
-                        rng.have = 0;
-                        VolumeSample vs;
-                        vs.wo = -ev.d;
-                        vs.ptInWorld = ev.o + t * ev.d;
-                        const float intensity = intensity_at(s.vol, vs.ptInWorld);
-                        vs.color_opacity = tf_at(s.tf, intensity);
-                        vs.gradient = gradient_at(s.vol, vs.ptInWorld);
-                        const float gradientMagnitude = sqrtf(dot(vs.gradient, vs.gradient));
-                        lc.add(SVR_CNT_SHADE_TAPS, 7);
-                        lc.add(SVR_CNT_TF_LOOKUPS, 1);
-                        lc.add(SVR_CNT_SCATTERS, 1);
-                        const float gf = s.vol.gradientFactor;
-                        const float Pbrdf = vs.color_opacity.w * (1.f - expf(-25.f * gf * gf * gf * gradientMagnitude * 65535.f * s.vol.invMaxMagnitude));
-                        const ShadingType st = (rng.next() < Pbrdf) ? BRDF : ISOTROPIC;
-                        // estimate_direct_light (pathtracer.cu:171-198): the shadow ray carries T * nLights * bsdf * Li / pdf
-                        if (s.numLights != 0) {
-                            int lightId = (int)((float)s.numLights * rng.next());
-                            lightId = lightId < (int)s.numLights ? lightId : (int)s.numLights - 1;
-                            float3 lightPos, wi;
-                            float pdf;
-                            const float3 Li = sample_light<false>(s.lights[lightId], vs.ptInWorld, rng, &lightPos, &wi, &pdf);
-                            if (pdf > 0.f && max3(Li) > 0.f) {
-                                sh.o = vs.ptInWorld;
-                                sh.d = normalize(lightPos - vs.ptInWorld);
-                                sh.a = ev.a * ((float)s.numLights * bsdf(vs, wi, st) * Li / pdf);
-                                sh.x = -1.f;
-                                sh.meta = WorkItem::pack(k, slot, RAY_SHADOW);
-                                sh.c0 = rng.c0;
-                                sh.c1 = ev.c1 ^ 0xA511E9B3u;  // a stream of its own: it flies beside the bounce ray
-                                haveShadow = max3(sh.a) > 0.f;
-                            }
-                        }
-                        // the bounce (pathtracer.cu:257-276); the last bounce's BSDF sample would never be used
-                        if (k + 1 < a.traceDepth) {
-                            float3 wi = f3(0.f);
-                            float pdf = 0.f;
-                            const float3 f = sample_bsdf<false>(vs, &wi, &pdf, rng, st);
-                            const float cosTerm = fabsf(dot(normalize(vs.gradient), wi));
-                            float3 T = ev.a;
-                            if (max3(f) > 0.f && pdf > 0.f) {
-                                if (st == ISOTROPIC) T *= f / (pdf * (1.f - Pbrdf));
-                                else T *= f * cosTerm / (pdf * Pbrdf);
-                            }
-                            bool alive = true;
-                            if (k >= 3) alive = !russian_roulette<false>(&T, rng);
-                            if (alive) {
-                                bo.o = vs.ptInWorld;
-                                bo.d = wi;
-                                bo.a = T;
-                                bo.x = -1.f;
-                                bo.meta = WorkItem::pack(k + 1, slot, RAY_BOUNCE);
-                                bo.c0 = rng.c0;
-                                bo.c1 = ev.c1;
-                                haveBounce = true;
-                            }
-                        }
-                    }
+                    float3 direct = f3(0.f);
+                    scatter_event<COUNT>(s, a.traceDepth, (pflag[ev.slot()] & 1u) != 0u, ev, sh, haveShadow, bo, haveBounce, direct, lc);
+                    accum_add(acc, ev.slot(), direct);
                 }
                 __syncwarp();  // every load of the phase precedes every store
                 const unsigned mS = __ballot_sync(FULL, haveShadow), mB = __ballot_sync(FULL, haveBounce);
