@@ -191,6 +191,44 @@ def gather_ceilings(r, achieved_gtaps=None):
     return out
 
 
+def layout_study(r, voxels16, n):
+    """north_star offers "a bricked, Morton-ordered layout bound as a 3D texture object or staged through shared memory" for
+    the voxels; the product keeps the caller's cudaArray texture (hardware block-linear tiling, filter in the texture unit).
+    The measurement behind that: the same independent trilinear taps -- coherent and random -- (0) as one TEX on the
+    cudaArray, (1) in software from a linear copy (8 loads + filter in the SM), (2) in software from a copy in 8^3-voxel
+    bricks in Morton order.  `voxels16`: the volume's n^3 16-bit voxels on the device.  G taps/s, best of 3."""
+    import torch
+
+    from sunvolumerender_b200 import _lib as L
+
+    sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+    bricked = torch.empty_like(voxels16)
+    L.check(r.lib.svr_layout_brick(C.c_void_p(voxels16.data_ptr()), C.c_void_p(bricked.data_ptr()), n))
+    torch.cuda.synchronize()
+
+    def rate(launch):
+        taps_out, best = C.c_uint64(0), None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            launch(taps_out)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return round(taps_out.value / (best * 1e-3) / 1e9, 2)
+
+    out = {}
+    for name, rnd, per in (("coherent", 0, 256), ("random", 1, 64)):
+        out[name] = {
+            "cudaarray_tex3d": rate(lambda t: L.check(r.lib.svr_microbench_taps(C.byref(r.volume), rnd, 1 << 20, per, C.c_void_p(sink.data_ptr()), C.byref(t)))),
+            "linear_software_trilinear": rate(lambda t: L.check(r.lib.svr_microbench_soft_taps(C.c_void_p(voxels16.data_ptr()), n, 1, rnd, 1 << 20, per, C.c_void_p(sink.data_ptr()), C.byref(t)))),
+            "bricked_morton_software_trilinear": rate(lambda t: L.check(r.lib.svr_microbench_soft_taps(C.c_void_p(bricked.data_ptr()), n, 2, rnd, 1 << 20, per, C.c_void_p(sink.data_ptr()), C.byref(t)))),
+        }
+    out["unit"] = "G taps/s (2^20 threads x 256 coherent / 64 random independent trilinear taps, best of 3)"
+    return out
+
+
 def issue_counters(workload, spp, kernel):
     """Issue-slot utilisation and lanes per instruction of the dominant kernel, from the committed ncu --set full capture of
     this very launch (profiles/r02/issue.json, written by tools/ncu_issue.py from the .ncu-rep): the bound that limits it."""
@@ -821,7 +859,10 @@ def other_workload_lines(r, a):
 
     # ---- C3, close view and drop-in protocol
     cfg = S.CONFIGS["C3"]
-    setup_config(r, cfg)
+    vb3 = setup_config(r, cfg)
+    layouts = {"workload": "voxel layout study: independent trilinear taps on the benched volumes, three storages (see layout_study)",
+               "C3_512^3_u16": layout_study(r, vb3, cfg.n)}
+    del vb3
     npix = cfg.width * cfg.height
     buf = torch.zeros(npix * 4, dtype=torch.float32, device="cuda")
     cam0 = r.camera
@@ -856,7 +897,10 @@ def other_workload_lines(r, a):
     # ---- C4 at its full 512 spp: 4 launches of 128
     cfg = S.CONFIGS["C4"]
     try:
-        setup_config(r, cfg)
+        vb4 = setup_config(r, cfg)
+        layouts["C4_1024^3_f16_bits"] = layout_study(r, vb4, cfg.n)
+        del vb4
+        torch.cuda.empty_cache()
         npix = cfg.width * cfg.height
         per, launches = cfg.spp, 1   # one launch renders the config's 512 spp (4 launches of 128: 12 % slower, the per-pixel drains repeat)
         buf = torch.zeros(npix * 4, dtype=torch.float32, device="cuda")
@@ -910,6 +954,7 @@ def other_workload_lines(r, a):
     except (FileNotFoundError, OSError) as e:
         line["reference_cuda_raycast"] = {"unavailable": str(e)}
     out.append(line)
+    out.append(layouts)
     return out
 
 

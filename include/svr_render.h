@@ -289,6 +289,14 @@ uint64_t svr_launch_count(void);
 int svr_microbench_taps(const svr_volume* vol, int random, uint32_t threads, uint32_t taps_per_thread,
                         float* dev_sink, uint64_t* host_taps);
 
+/* Layout study behind the choice of voxel storage: the same taps as svr_microbench_taps done in
+ * software -- eight loads + the trilinear filter in the SM -- from a linear copy of n^3 16-bit voxels (layout 1, x fastest) or
+ * from a bricked copy (layout 2: 8^3-voxel bricks, each contiguous, bricks in Morton order; svr_layout_brick makes it, n a
+ * multiple of 8).  Not used by any render path. */
+int svr_layout_brick(const void* dev_linear, void* dev_bricked, uint32_t n);
+int svr_microbench_soft_taps(const void* dev_voxels16, uint32_t n, int layout, int random, uint32_t threads,
+                             uint32_t taps_per_thread, float* dev_sink, uint64_t* host_taps);
+
 /* ---- inspection hooks (used by the parity tests; cheap, never on the render path) ---- */
 /* Raw fetches through the caller's texture objects, exactly as the kernels issue them:
  * out[i] = tex3D<float>(vol->tex, uvw[3i], uvw[3i+1], uvw[3i+2]) (normalised coordinates, before

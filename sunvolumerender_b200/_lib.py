@@ -158,6 +158,8 @@ SIGNATURES = [
     ("svr_counters_read", C.c_int, [C.POINTER(C.c_uint64), C.c_uint32]),
     ("svr_launch_count", C.c_uint64, []),
     ("svr_microbench_taps", C.c_int, [C.POINTER(Volume), C.c_int, C.c_uint32, C.c_uint32, _P, C.POINTER(C.c_uint64)]),
+    ("svr_layout_brick", C.c_int, [_P, _P, C.c_uint32]),
+    ("svr_microbench_soft_taps", C.c_int, [_P, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, C.POINTER(C.c_uint64)]),
     ("svr_debug_sample_volume", C.c_int, [C.POINTER(Volume), _P, C.c_uint32, _P]),
     ("svr_debug_sample_tf", C.c_int, [C.POINTER(TransferFunction), _P, C.c_uint32, _P]),
     ("svr_grid_info", C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -713,3 +713,111 @@ extern "C" int svr_microbench_taps(const svr_volume* vol, int random, uint32_t t
     if (host_taps) *host_taps = (uint64_t)grid * block * taps_per_thread;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Layout study (north_star: "a bricked, Morton-ordered 8/16-bit density layout bound as a 3D texture object or staged
+// through shared memory").  The same trilinear taps three ways, so that the choice of storage rests on a measurement:
+//   0  the product's path: one TEX on the caller's cudaArray (hardware block-linear tiling, filter in the texture unit);
+//   1  software trilinear from a LINEAR copy of the voxels (x fastest): eight loads, weights and the filter in the SM;
+//   2  software trilinear from a BRICKED copy: 8 x 8 x 8-voxel bricks, each contiguous, bricks in Morton order.
+// Coherent taps (neighbouring lanes walk neighbouring rays) or random ones (hashed positions), no dependent arithmetic
+// between taps.  16-bit voxels (u16 or f16 bit patterns: the study is about addresses and sectors, not values).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ uint32_t part1by2(uint32_t x)  // spreads the low 10 bits: Morton interleave
+{
+    x &= 0x000003ffu;
+    x = (x ^ (x << 16)) & 0xff0000ffu;
+    x = (x ^ (x << 8)) & 0x0300f00fu;
+    x = (x ^ (x << 4)) & 0x030c30c3u;
+    x = (x ^ (x << 2)) & 0x09249249u;
+    return x;
+}
+
+__device__ __forceinline__ size_t brick_index(int x, int y, int z)
+{
+    const uint32_t m = part1by2((uint32_t)x >> 3) | (part1by2((uint32_t)y >> 3) << 1) | (part1by2((uint32_t)z >> 3) << 2);
+    return (size_t)m * 512u + (size_t)(((z & 7) << 6) | ((y & 7) << 3) | (x & 7));
+}
+
+__global__ void brick_reorder_kernel(const uint16_t* __restrict__ lin, uint16_t* __restrict__ bricked, int n)
+{
+    const size_t total = (size_t)n * n * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % n), y = (int)((i / n) % n), z = (int)(i / ((size_t)n * n));
+        bricked[brick_index(x, y, z)] = lin[i];
+    }
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ float voxel_at(const uint16_t* __restrict__ v, int n, int x, int y, int z)
+{
+    if ((unsigned)x >= (unsigned)n || (unsigned)y >= (unsigned)n || (unsigned)z >= (unsigned)n) return 0.f;  // border addressing
+    const size_t i = LAYOUT == 1 ? ((size_t)z * n + y) * n + x : brick_index(x, y, z);
+    return (float)__ldg(v + i) * (1.f / 65535.f);
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ float soft_tap(const uint16_t* __restrict__ v, int n, float u, float w1, float w2)
+{
+    const float xb = u * (float)n - 0.5f, yb = w1 * (float)n - 0.5f, zb = w2 * (float)n - 0.5f;
+    const float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    const int x = (int)fx, y = (int)fy, z = (int)fz;
+    const float a = xb - fx, b = yb - fy, c = zb - fz;
+    const float v000 = voxel_at<LAYOUT>(v, n, x, y, z), v100 = voxel_at<LAYOUT>(v, n, x + 1, y, z);
+    const float v010 = voxel_at<LAYOUT>(v, n, x, y + 1, z), v110 = voxel_at<LAYOUT>(v, n, x + 1, y + 1, z);
+    const float v001 = voxel_at<LAYOUT>(v, n, x, y, z + 1), v101 = voxel_at<LAYOUT>(v, n, x + 1, y, z + 1);
+    const float v011 = voxel_at<LAYOUT>(v, n, x, y + 1, z + 1), v111 = voxel_at<LAYOUT>(v, n, x + 1, y + 1, z + 1);
+    const float x00 = v000 + a * (v100 - v000), x10 = v010 + a * (v110 - v010), x01 = v001 + a * (v101 - v001), x11 = v011 + a * (v111 - v011);
+    const float y0 = x00 + b * (x10 - x00), y1 = x01 + b * (x11 - x01);
+    return y0 + c * (y1 - y0);
+}
+
+template <int LAYOUT>
+__global__ void soft_taps_kernel(const uint16_t* __restrict__ v, int n, int random, uint32_t tapsPerThread, float* sink)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    if (random) {
+        uint32_t h = tid * 0x9E3779B1u + 12345u;
+#pragma unroll 4
+        for (uint32_t i = 0; i < tapsPerThread; ++i) {
+            h = h * 1664525u + 1013904223u;
+            uint32_t a = h ^ (h >> 15);
+            a *= 0x2C1B3C6Du;
+            a ^= a >> 13;
+            acc += soft_tap<LAYOUT>(v, n, (float)(a & 0x3ffu) * (1.f / 1024.f), (float)((a >> 10) & 0x3ffu) * (1.f / 1024.f),
+                                    (float)((a >> 20) & 0x3ffu) * (1.f / 1024.f));
+        }
+    } else {
+        const uint32_t warp = tid >> 5, lane = tid & 31;
+        const uint32_t px = (warp % 128u) * 8u + (lane & 7u), py = ((warp / 128u) % 256u) * 4u + (lane >> 3);
+        const float u = ((float)px + 0.5f) * (1.f / 1024.f), w1 = ((float)py + 0.5f) * (1.f / 1024.f), dw = 1.f / (float)tapsPerThread;
+#pragma unroll 4
+        for (uint32_t i = 0; i < tapsPerThread; ++i) acc += soft_tap<LAYOUT>(v, n, u, w1, ((float)i + 0.5f) * dw);
+    }
+    if (acc == 123456.789f) sink[0] = acc;
+}
+}  // namespace
+
+extern "C" int svr_layout_brick(const void* dev_linear, void* dev_bricked, uint32_t n)
+{
+    if (!dev_linear || !dev_bricked || !n || (n & 7u) || n > 8192u) return fail_msg("svr_layout_brick: n must be a multiple of 8 (at most 8192)");
+    brick_reorder_kernel<<<148 * 8, 256, 0, state().stream>>>((const uint16_t*)dev_linear, (uint16_t*)dev_bricked, (int)n);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svr_microbench_soft_taps(const void* dev_voxels16, uint32_t n, int layout, int random, uint32_t threads, uint32_t taps_per_thread,
+                                        float* dev_sink, uint64_t* host_taps)
+{
+    if (!dev_voxels16 || !dev_sink || !n || (layout != 1 && layout != 2)) return fail_msg("svr_microbench_soft_taps: bad argument");
+    const uint32_t block = 256, grid = (threads + block - 1) / block;
+    if (layout == 1) soft_taps_kernel<1><<<grid, block, 0, state().stream>>>((const uint16_t*)dev_voxels16, (int)n, random, taps_per_thread, dev_sink);
+    else soft_taps_kernel<2><<<grid, block, 0, state().stream>>>((const uint16_t*)dev_voxels16, (int)n, random, taps_per_thread, dev_sink);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    if (host_taps) *host_taps = (uint64_t)grid * block * taps_per_thread;
+    return 0;
+}

@@ -448,3 +448,34 @@ def test_peer_frame_on_one_gpu_is_the_plain_image(renderer):
     pf.frame_done()
     assert torch.equal(pf.image().view(cfg.height, cfg.width, 4), whole)
     pf.close()
+
+
+def test_layout_study_software_taps_read_the_same_voxels(renderer):
+    """The layout microbenchmarks (bench.py: layout_study) fetch from a linear and from a Morton-bricked copy of the voxels:
+    the bricked copy is a permutation of the linear one, brick by brick (8^3 voxels contiguous)."""
+    n = 32
+    vox = renderer.generate_volume(L.GEN_CT, L.VOXEL_U16, n, 7)
+    bricked = torch.empty_like(vox)
+    L.check(renderer.lib.svr_layout_brick(C.c_void_p(vox.data_ptr()), C.c_void_p(bricked.data_ptr()), n))
+    torch.cuda.synchronize()
+    lin = vox.cpu().numpy().view(np.uint16).reshape(n, n, n)
+    br = bricked.cpu().numpy().view(np.uint16)
+    assert np.array_equal(np.sort(br), np.sort(lin.reshape(-1)))
+
+    def morton(bx, by, bz):
+        m = 0
+        for b in range(10):
+            m |= ((bx >> b) & 1) << (3 * b) | ((by >> b) & 1) << (3 * b + 1) | ((bz >> b) & 1) << (3 * b + 2)
+        return m
+
+    for (bx, by, bz) in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (3, 2, 1), (3, 3, 3)):
+        brick = br[morton(bx, by, bz) * 512: morton(bx, by, bz) * 512 + 512].reshape(8, 8, 8)
+        assert np.array_equal(brick, lin[bz * 8: bz * 8 + 8, by * 8: by * 8 + 8, bx * 8: bx * 8 + 8])
+    sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+    taps = C.c_uint64(0)
+    for layout, buf in ((1, vox), (2, bricked)):
+        for rnd in (0, 1):
+            L.check(renderer.lib.svr_microbench_soft_taps(C.c_void_p(buf.data_ptr()), n, layout, rnd, 4096, 16, C.c_void_p(sink.data_ptr()), C.byref(taps)))
+    torch.cuda.synchronize()
+    assert taps.value == 4096 * 16
+    assert renderer.lib.svr_layout_brick(C.c_void_p(vox.data_ptr()), C.c_void_p(bricked.data_ptr()), 30) != 0   # not a multiple of 8
