@@ -79,3 +79,20 @@ def test_struct_layouts_match_c_headers(tmp_path):
     mirrors = [L.Volume, L.TransferFunction, L.Camera, L.Disk, L.AreaLight, L.EnvLight, L.RenderParams, L.BBox]
     assert sizes == [C.sizeof(m) for m in mirrors]
     assert sizes == [112, 16, 76, 28, 44, 32, 16, 36]  # SURVEY.md section 8b probe of the reference structs
+
+
+def test_option_enum_and_binding_agree():
+    """Every svr_option of include/svr_render.h has the same value in the ctypes binding (OPT_* = SVR_OPT_* without the prefix)."""
+    src = open(os.path.join(ROOT, "include", "svr_render.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = re.search(r"enum svr_option\s*\{(.*?)\}", src, flags=re.S).group(1)
+    entries = re.findall(r"SVR_(OPT_\w+)\s*=\s*(\d+)", body)
+    assert len(entries) >= 24
+    for name, value in entries:
+        assert getattr(L, name) == int(value), name
+    assert re.search(r"SVR_OPT_COUNT_", body)
+    # defaults a drop-in host gets without calling svr_set_option
+    lib = L.load()
+    for name, default in (("OPT_PT_PROFILE", 0), ("OPT_PT_LIGHT_CULL", 1), ("OPT_ENV_NEE", 0), ("OPT_PT_BLOCK_SPLIT", 0), ("OPT_PT_PIXEL_CACHE", 1),
+                          ("OPT_PT_WARP_PIXELS", 2), ("OPT_ENV_ENABLED", 0), ("OPT_SHADOW_ESTIMATOR", 0)):
+        assert lib.svr_get_option(getattr(L, name)) == default, name
