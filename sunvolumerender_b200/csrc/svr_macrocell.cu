@@ -523,6 +523,7 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
     g.cell = st.gridCell;
     g.scale = f3((float)st.volDims.x / (float)st.gridCell, (float)st.volDims.y / (float)st.gridCell,
                  (float)st.volDims.z / (float)st.gridCell);
+    g.invScale = f3((float)st.gridCell / (float)st.volDims.x, (float)st.gridCell / (float)st.volDims.y, (float)st.gridCell / (float)st.volDims.z);
     g.toCell = f3(vol.bbox.invSize) * g.scale;
     g.cellOff = f3(vol.bbox.vmin) * g.toCell;
     return 0;

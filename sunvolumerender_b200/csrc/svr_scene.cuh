@@ -23,6 +23,7 @@ struct DevGrid {
     int px, pxy;             // row and slice pitch of `cells`
     int cell;                // cell edge in voxels
     float3 scale;            // normalised texture coordinate -> cell coordinate (dims / cell)
+    float3 invScale;         // and back (cell / dims): a tap along a ray is taken at (g0 + t dg) * invScale
     float3 toCell, cellOff;  // world -> cell coordinate: p * toCell - cellOff  (toCell = invSize * scale, cellOff = vmin * toCell)
     float pyF;               // rows per slice of `cells` (gy + 2), as a float
     SVR_DEV float at(int cx, int cy, int cz) const { return __ldg(cells + (cz * pxy + cy * px + cx)); }
