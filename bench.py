@@ -450,6 +450,8 @@ def run_ours(a):
     r = Renderer(local)
     vb = setup_config(r, cfg)  # synthetic voxels generated on the device (svr_generate_volume)
     r.set_option(L.OPT_PT_MODE, a.pt_mode)
+    if os.environ.get("SVR_BENCH_FUSED_UPLOAD") == "0":  # A/B of the e2e leg: copy + range kernel instead of the one-pass upload
+        r.set_option(L.OPT_FUSED_UPLOAD, 0)
     if a.cell:
         r.set_option(L.OPT_MACROCELL_SIZE, a.cell)
     sum_buf = torch.zeros(npix * 4, dtype=torch.float32, device=dev)
@@ -553,37 +555,66 @@ def run_ours(a):
         resolved = [torch.cuda.Event(), torch.cuda.Event()]
         read_back = [torch.cuda.Event(), torch.cuda.Event()]
 
+        h2d_trace = []
+        trace = [] if os.environ.get("SVR_BENCH_E2E_TRACE") else None  # per-step events on the render stream (stderr, diagnostic)
+
+        def mark(row):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                row.append(e)
+
         def e2e_step(i, prefetch_next, serial=False):
             main = torch.cuda.current_stream()
+            row = []
+            if trace is not None and not serial:
+                trace.append(row)
+            mark(row)
             if serial:
                 vs.prefetch(host_vox)                  # no overlap: transfer, then render
             vs.bind()                                  # staged voxels -> cudaArray; macrocell ranges rebuilt at the next render
+            mark(row)
             r.set_transfer_function(tf_table)          # H2D 16 KiB table into the bound 1-D array
             r.set_camera(cam)
             r.set_area_lights(lights)
             r.set_env_light(env, enabled=cfg.env)
             r.accumulate(sum_buf, depth, next_first(), spp, clear=True)
+            mark(row)
             if prefetch_next and not serial:
+                if trace is not None:
+                    h0 = torch.cuda.Event(enable_timing=True)
+                    h0.record(vs.copy_stream)
                 vs.prefetch(host_vox)                  # H2D (+ fan-out) of the NEXT frame, beside this frame's render kernel
+                if trace is not None:
+                    h1 = torch.cuda.Event(enable_timing=True)
+                    h1.record(vs.copy_stream)
+                    h2d_trace.append((row, h0, h1))
+            if rank == 0 and not serial and i > 0:
+                issue_read_back((i - 1) & 1)           # frame i-1 leaves for the host while frame i renders ...
+                read_back[(i - 1) & 1].synchronize()   # ... and the caller looks at it
             if world > 1:
                 dist.reduce(sum_buf, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 slot = i & 1
                 main.wait_event(read_back[slot ^ 1])   # resolve overwrites r.img / r.hdr: the previous frame's copy has left
                 r.resolve(sum_buf)
+                mark(row)
                 if serial:
                     host_imgs[slot].copy_(r.img, non_blocking=True)
                     host_hdrs[slot].copy_(r.hdr, non_blocking=True)
                     main.synchronize()                 # the caller looks at this frame
                 else:
                     resolved[slot].record(main)
-                    with torch.cuda.stream(rb_stream):
-                        rb_stream.wait_event(resolved[slot])
-                        host_imgs[slot].copy_(r.img, non_blocking=True)
-                        host_hdrs[slot].copy_(r.hdr, non_blocking=True)
-                        read_back[slot].record(rb_stream)
-                    if i > 0:
-                        read_back[slot ^ 1].synchronize()  # the caller looks at the previous frame
+
+        def issue_read_back(slot):
+            # A bulk device-to-host copy that starts between two frames delays the kernels that refresh the next frame's volume
+            # and grid (measured: +0.35 ms on a 0.25 ms upload kernel), a render kernel does not notice it: so frame i-1 is read
+            # back once frame i's render kernel has been launched.
+            with torch.cuda.stream(rb_stream):
+                rb_stream.wait_event(resolved[slot])
+                host_imgs[slot].copy_(r.img, non_blocking=True)
+                host_hdrs[slot].copy_(r.hdr, non_blocking=True)
+                read_back[slot].record(rb_stream)
 
         def e2e_run(steps, serial):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -596,6 +627,7 @@ def run_ours(a):
             for i in range(steps):
                 e2e_step(i, i + 1 < steps, serial)
             if rank == 0 and not serial:
+                issue_read_back((steps - 1) & 1)
                 read_back[(steps - 1) & 1].synchronize()   # the last frame has reached the host
             ev1.record()
             barrier()
@@ -610,6 +642,17 @@ def run_ours(a):
         if clocks:
             clocks.window(*win)
         e2e_value = npix * spp * world * a.steps / (e2e_ms * 1e-3)
+        if trace and rank == 0:
+            rows = [t for t in trace[-a.steps:] if len(t) == 4]
+            seg = [sum(t[k].elapsed_time(t[k + 1]) for t in rows) / len(rows) for k in range(3)]
+            gap = sum(rows[k][3].elapsed_time(rows[k + 1][0]) for k in range(len(rows) - 1)) / max(1, len(rows) - 1)
+            hh = [(h0.elapsed_time(h1), rw[1].elapsed_time(h0), rw[1].elapsed_time(h1), rw[1].elapsed_time(rw[2])) for rw, h0, h1 in h2d_trace[-(a.steps - 1):] if len(rw) == 4]
+            if hh:
+                print("e2e trace (ms): next frame's H2D takes %.3f; relative to the end of bind it starts at %.3f and ends at %.3f, the render ends at %.3f"
+                      % tuple(sum(x[k] for x in hh) / len(hh) for k in range(4)), file=sys.stderr)
+            print("e2e trace (ms): bind per step " + " ".join("%.2f" % t[0].elapsed_time(t[1]) for t in rows), file=sys.stderr)
+            print(f"e2e trace (ms, render stream): bind {seg[0]:.3f}  grid build + render {seg[1]:.3f}  reduce + resolve {seg[2]:.3f}  "
+                  f"between steps {gap:.3f}  (device-resident render {kernel_ms:.3f})", file=sys.stderr)
         small = tf_table.nbytes + 112 + 16 + 76 + 44 * len(lights) + 32  # table + scene PODs, every rank
         h2d = int(vb.numel() * (world if fanout == "pcie" else 1) + small * world)
         d2h = int(host_img.numel() + host_hdr.numel() * 4)

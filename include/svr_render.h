@@ -149,6 +149,11 @@ enum svr_option {
      * frames of a progressive render and recomputes it only after something a pixel can see has changed (any setup_*, upload or
      * option).  Images are bit-identical either way (only empty space is skipped); 0 = classify in every call. */
     SVR_OPT_PT_PIXEL_CACHE = 23,
+    /* 1 (default) = svr_volume_upload from a DEVICE buffer into an array made by svr_volume_create, once the macrocell grid
+     * exists for that array, runs as one kernel that stores the voxels into the array and reduces the grid's value ranges from
+     * the same pass (streamed time series: a new volume per frame).  0 = copy, then rebuild the ranges from the array at the
+     * next render.  Arrays, ranges and images are bit-identical either way. */
+    SVR_OPT_FUSED_UPLOAD = 24,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the
@@ -283,6 +288,8 @@ int svr_counters_read(uint64_t* host_out, uint32_t n);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t svr_launch_count(void);
+/* How many svr_volume_upload calls took the one-pass path (SVR_OPT_FUSED_UPLOAD) since the library was loaded. */
+uint64_t svr_fused_upload_count(void);
 
 /* Gather-roofline microbenchmarks: `taps_per_thread` dependent-free tex3D taps per thread over
  * the bound volume, coherent (ray-like) or random.  Returns taps issued via *host_taps. */

@@ -39,6 +39,7 @@ HostState& state()
         p->options[SVR_OPT_PT_PROFILE] = 0;  // measured slower than shape 2 on every BASELINE configuration
         p->options[SVR_OPT_PT_REFILL] = 0;
         p->options[SVR_OPT_PT_PIXEL_CACHE] = 1;
+        p->options[SVR_OPT_FUSED_UPLOAD] = 1;
         // A host that only knows the reference's seven entry points (gui/canvas.cpp) cannot call
         // svr_set_option: the same switches are read once from the environment.
         static const struct { const char* name; int key, lo, hi; } kEnv[] = {
@@ -245,6 +246,7 @@ extern "C" int svr_get_option(int key)
 }
 
 extern "C" uint64_t svr_launch_count(void) { return state().launches; }
+extern "C" uint64_t svr_fused_upload_count(void) { return state().fusedUploads; }
 
 extern "C" int svr_volume_invalidate_cache(void)
 {
@@ -323,7 +325,8 @@ extern "C" int svr_volume_create(svr_volume* out, const void* data, int data_on_
     cudaChannelFormatDesc ch = voxel_channel(format);
     cudaExtent extent = make_cudaExtent(nx, ny, nz);
     cudaArray_t arr = nullptr;
-    SVR_TRY(cudaMalloc3DArray(&arr, &ch, extent, cudaArrayDefault));
+    // surface stores allowed: svr_volume_upload fills the array and reduces the macrocell ranges in one pass (svr_macrocell.cu)
+    SVR_TRY(cudaMalloc3DArray(&arr, &ch, extent, cudaArraySurfaceLoadStore));
 
     cudaMemcpy3DParms cp;
     memset(&cp, 0, sizeof(cp));
@@ -410,15 +413,23 @@ extern "C" int svr_volume_upload(const svr_volume* vol, const void* data, int da
     unsigned int flags = 0;
     SVR_TRY(cudaArrayGetInfo(&ch, &ext, &flags, rd.res.array.array));
     const size_t bpe = (size_t)(ch.x + ch.y + ch.z + ch.w) / 8;
-    cudaMemcpy3DParms cp;
-    memset(&cp, 0, sizeof(cp));
-    cp.dstArray = rd.res.array.array;
-    cp.extent = ext;
-    cp.kind = data_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    cp.srcPtr = make_cudaPitchedPtr(const_cast<void*>(data), ext.width * bpe, ext.width, ext.height);
-    SVR_TRY(cudaMemcpy3DAsync(&cp, st.stream));
-    // same dims, new contents: the grid's allocations stay, its range stage reruns at the next render
-    if (rd.res.array.array == st.gridArray) st.rangeValid = false;
+    bool fused = false;
+    if (data_on_device) {
+        // one pass: voxels into the array and the macrocell ranges out of the same tile, when the grid exists for this array
+        int rc = upload_with_ranges(rd.res.array.array, ch, ext, flags, data, &fused);
+        if (rc) return rc;
+    }
+    if (!fused) {
+        cudaMemcpy3DParms cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.dstArray = rd.res.array.array;
+        cp.extent = ext;
+        cp.kind = data_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        cp.srcPtr = make_cudaPitchedPtr(const_cast<void*>(data), ext.width * bpe, ext.width, ext.height);
+        SVR_TRY(cudaMemcpy3DAsync(&cp, st.stream));
+        // same dims, new contents: the grid's allocations stay, its range stage reruns at the next render
+        if (rd.res.array.array == st.gridArray) st.rangeValid = false;
+    }
     st.uploadEpoch++;
     st.sceneEpoch++;
     return 0;

@@ -26,6 +26,9 @@
 // walk needs no clamping at the volume faces.
 // The boundary passes only a texture handle (cuda_volume.h:111-121); dims, format and voxels are
 // recovered with cudaGetTextureObjectResourceDesc -> cudaArrayGetInfo.
+#include <cuda_fp16.h>
+
+#include <algorithm>
 #include <climits>
 #include <cstring>
 #include <vector>
@@ -68,6 +71,56 @@ __global__ void range_kernel(cudaTextureObject_t pointTex, int3 vol, int3 grid, 
             mx = fmaxf(mx, smx[i]);
         }
         out[((size_t)cz * grid.y + cy) * grid.x + cx] = make_float2(mn, mx);
+    }
+}
+
+// The separable min/max reduction of a brick's texels (tile with its one-texel apron in shared memory) into the cells of
+// the brick: along x, then y, then z.  Shared by the kernel that reads the array and the one that fills it (below).
+struct RangeAsIs {
+    static __device__ float finish(float x) { return x; }
+};
+// FIN::finish maps the reduced min / max to the value the volume texture returns (monotonic, so it commutes with min / max)
+template <int CELL, class FIN>
+__device__ __forceinline__ void reduce_brick(const float* tex, float2* rx, float2* ry, int cx0, int cy0, int cz0, int3 grid, float2* out)
+{
+    constexpr int BX = 32 / CELL, BY = CELL <= 8 ? 8 / CELL : 1, BZ = BY;
+    constexpr int TX = BX * CELL + 2, TY = BY * CELL + 2, TZ = BZ * CELL + 2;
+    for (int i = threadIdx.x; i < BX * TY * TZ; i += 256) {
+        const int c = i % BX, y = (i / BX) % TY, z = i / (BX * TY);
+        const float* row = tex + (z * TY + y) * TX + c * CELL;
+        float mn = row[0], mx = row[0];
+#pragma unroll
+        for (int k = 1; k < CELL + 2; ++k) {
+            mn = fminf(mn, row[k]);
+            mx = fmaxf(mx, row[k]);
+        }
+        rx[(z * TY + y) * BX + c] = make_float2(mn, mx);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BX * BY * TZ; i += 256) {
+        const int c = i % BX, cy = (i / BX) % BY, z = i / (BX * BY);
+        float2 r = rx[(z * TY + cy * CELL) * BX + c];
+#pragma unroll
+        for (int k = 1; k < CELL + 2; ++k) {
+            const float2 v = rx[(z * TY + cy * CELL + k) * BX + c];
+            r.x = fminf(r.x, v.x);
+            r.y = fmaxf(r.y, v.y);
+        }
+        ry[(z * BY + cy) * BX + c] = r;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BX * BY * BZ; i += 256) {
+        const int c = i % BX, cy = (i / BX) % BY, cz = i / (BX * BY);
+        float2 r = ry[((cz * CELL) * BY + cy) * BX + c];
+#pragma unroll
+        for (int k = 1; k < CELL + 2; ++k) {
+            const float2 v = ry[((cz * CELL + k) * BY + cy) * BX + c];
+            r.x = fminf(r.x, v.x);
+            r.y = fmaxf(r.y, v.y);
+        }
+        const int gx = cx0 + c, gy = cy0 + cy, gz = cz0 + cz;
+        if (gx < grid.x && gy < grid.y && gz < grid.z)
+            out[((size_t)gz * grid.y + gy) * grid.x + gx] = make_float2(FIN::finish(r.x), FIN::finish(r.y));
     }
 }
 
@@ -117,43 +170,7 @@ __global__ void __launch_bounds__(256) range_brick_kernel(Fetch fetch, int3 grid
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < BX * TY * TZ; i += 256) {
-        const int c = i % BX, y = (i / BX) % TY, z = i / (BX * TY);
-        const float* row = tex + (z * TY + y) * TX + c * CELL;
-        float mn = row[0], mx = row[0];
-#pragma unroll
-        for (int k = 1; k < CELL + 2; ++k) {
-            mn = fminf(mn, row[k]);
-            mx = fmaxf(mx, row[k]);
-        }
-        rx[(z * TY + y) * BX + c] = make_float2(mn, mx);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < BX * BY * TZ; i += 256) {
-        const int c = i % BX, cy = (i / BX) % BY, z = i / (BX * BY);
-        float2 r = rx[(z * TY + cy * CELL) * BX + c];
-#pragma unroll
-        for (int k = 1; k < CELL + 2; ++k) {
-            const float2 v = rx[(z * TY + cy * CELL + k) * BX + c];
-            r.x = fminf(r.x, v.x);
-            r.y = fmaxf(r.y, v.y);
-        }
-        ry[(z * BY + cy) * BX + c] = r;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < BX * BY * BZ; i += 256) {
-        const int c = i % BX, cy = (i / BX) % BY, cz = i / (BX * BY);
-        float2 r = ry[((cz * CELL) * BY + cy) * BX + c];
-#pragma unroll
-        for (int k = 1; k < CELL + 2; ++k) {
-            const float2 v = ry[((cz * CELL + k) * BY + cy) * BX + c];
-            r.x = fminf(r.x, v.x);
-            r.y = fmaxf(r.y, v.y);
-        }
-        const int gx = cx0 + c, gy = cy0 + cy, gz = cz0 + cz;
-        if (gx < grid.x && gy < grid.y && gz < grid.z)
-            out[((size_t)gz * grid.y + gy) * grid.x + gx] = r;
-    }
+    reduce_brick<CELL, RangeAsIs>(tex, rx, ry, cx0, cy0, cz0, grid, out);
 }
 
 template <class Fetch, int CELL>
@@ -179,6 +196,188 @@ int launch_range_brick(HostState& st, Fetch fetch)
         case 4: return launch_range_brick_cell<Fetch, 4>(st, fetch);
         case 8: return launch_range_brick_cell<Fetch, 8>(st, fetch);
         case 16: return launch_range_brick_cell<Fetch, 16>(st, fetch);
+        default: return fail_msg("range grid: brick kernel needs a cell edge of 2, 4, 8 or 16");
+    }
+}
+
+// ---- svr_volume_upload from a linear device buffer (a staged frame of a streamed time series): ONE pass reads the
+// voxels, stores them into the cudaArray through a surface object and reduces the range grid from the same shared-memory
+// tile, instead of a driver copy into the array followed by range_brick_kernel reading the array back (measured at 512^3
+// u16 inside the streamed pipeline: 0.52 ms + 0.37 ms).  Row-wise: the 32 interior texels of a tile row are one
+// coalesced warp load and one surface store, lanes 0 and 1 fetch the row's two apron texels; a row's address is computed
+// once per warp.  Needs an array created with cudaArraySurfaceLoadStore (svr_volume_create does; a foreign array takes the
+// copy + texture path).
+// What a voxel reads as through the point-sampled view: normalised float for the integer formats (the texture unit
+// returns the correctly rounded v / (2^n - 1); tests/test_gpu_resources.py holds the two paths bit-equal), the stored
+// value for the float formats.  The division is monotonic, so the tile holds the integers (as exact floats) and only each
+// cell's min and max are divided (the first version divided every texel: 60 % of the kernel's instructions).
+struct VoxU8 {
+    typedef unsigned char raw;
+    static __device__ float value(raw v) { return (float)v; }
+    static __device__ float finish(float x) { return __fdiv_rn(x, 255.f); }
+};
+struct VoxU16 {
+    typedef unsigned short raw;
+    static __device__ float value(raw v) { return (float)v; }
+    static __device__ float finish(float x) { return __fdiv_rn(x, 65535.f); }
+};
+struct VoxF16 {
+    typedef unsigned short raw;
+    static __device__ float value(raw v) { return __half2float(__ushort_as_half(v)); }
+    static __device__ float finish(float x) { return x; }
+};
+struct VoxF32 {
+    typedef float raw;
+    static __device__ float value(raw v) { return v; }
+    static __device__ float finish(float x) { return x; }
+};
+
+template <class V, int CELL>
+__global__ void __launch_bounds__(256) upload_range_kernel(const typename V::raw* __restrict__ src, cudaSurfaceObject_t surf, int3 dims,
+                                                           int3 grid, float2* out)
+{
+    typedef typename V::raw raw;
+    constexpr int BX = 32 / CELL, BY = CELL <= 8 ? 8 / CELL : 1, BZ = BY;
+    constexpr int TX = BX * CELL + 2, TY = BY * CELL + 2, TZ = BZ * CELL + 2;
+    static_assert(TX == 34, "a tile row is one warp of interior texels plus two apron texels");
+    constexpr int TOTAL = TX * TY * TZ, ROWS = TY * TZ;
+    extern __shared__ float smem[];
+    float* tex = smem;
+    float2* rx = (float2*)(smem + TOTAL);
+    float2* ry = rx + BX * TY * TZ;
+    const int cx0 = blockIdx.x * BX, cy0 = blockIdx.y * BY, cz0 = blockIdx.z * BZ;
+    const int x0 = cx0 * CELL - 1, y0 = cy0 * CELL - 1, z0 = cz0 * CELL - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = x0 + 1 + lane;                    // this lane's interior texel
+    const int ax = lane == 0 ? x0 : x0 + TX - 1;     // lanes 0, 1: the row's apron texels
+    const bool inX = gx < dims.x, apX = lane < 2 && ax >= 0 && ax < dims.x;
+    for (int r0 = warp; r0 < ROWS; r0 += 8 * 4) {
+        raw v[4], e[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 8;
+            v[u] = 0;
+            e[u] = 0;
+            if (r < ROWS) {
+                const int gy = y0 + r % TY, gz = z0 + r / TY;
+                if (gy >= 0 && gy < dims.y && gz >= 0 && gz < dims.z) {  // outside the array: the border value 0
+                    const raw* row = src + ((size_t)gz * dims.y + gy) * dims.x;
+                    if (inX) v[u] = __ldg(row + gx);
+                    if (apX) e[u] = __ldg(row + ax);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 8;
+            if (r < ROWS) {
+                const int y = r % TY, z = r / TY;
+                float* trow = tex + r * TX;
+                trow[1 + lane] = V::value(v[u]);
+                if (lane < 2) trow[lane == 0 ? 0 : TX - 1] = V::value(e[u]);
+                const int gy = y0 + y, gz = z0 + z;
+                // the brick's own texels (not the apron, which belongs to the neighbouring bricks) go into the array
+                if (y >= 1 && y < TY - 1 && z >= 1 && z < TZ - 1 && inX && gy < dims.y && gz < dims.z)
+                    surf3Dwrite(v[u], surf, gx * (int)sizeof(raw), gy, gz);
+            }
+        }
+    }
+    __syncthreads();
+    reduce_brick<CELL, V>(tex, rx, ry, cx0, cy0, cz0, grid, out);
+}
+
+// The same pass for the common case -- rows of a multiple of 32 voxels, 16-byte aligned source: every memory instruction
+// moves 16 bytes (8 u16 voxels), one load and one surface store per thread for a 32 x 8 x 8 brick of 2-byte voxels instead
+// of one per voxel (the 2-byte surface stores of the kernel above cost it 1.4 ms at 512^3 u16; this one takes a quarter).
+template <class V, int CELL>
+__global__ void __launch_bounds__(256) upload_range_vec_kernel(const typename V::raw* __restrict__ src, cudaSurfaceObject_t surf, int3 dims,
+                                                               int3 grid, float2* out)
+{
+    typedef typename V::raw raw;
+    constexpr int BX = 32 / CELL, BY = CELL <= 8 ? 8 / CELL : 1, BZ = BY;
+    constexpr int TX = BX * CELL + 2, TY = BY * CELL + 2, TZ = BZ * CELL + 2;
+    constexpr int TOTAL = TX * TY * TZ, ROWS = TY * TZ;
+    constexpr int PER = 16 / (int)sizeof(raw);  // voxels per 16-byte word
+    constexpr int Q = 32 / PER;                 // words per tile row
+    constexpr int ITEMS = ROWS * Q;
+    extern __shared__ float smem[];
+    float* tex = smem;
+    float2* rx = (float2*)(smem + TOTAL);
+    float2* ry = rx + BX * TY * TZ;
+    const int cx0 = blockIdx.x * BX, cy0 = blockIdx.y * BY, cz0 = blockIdx.z * BZ;
+    const int gx0 = cx0 * CELL, y0 = cy0 * CELL - 1, z0 = cz0 * CELL - 1;
+    for (int i0 = threadIdx.x; i0 < ITEMS; i0 += 2 * 256) {
+        uint4 w[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * 256;
+            w[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < ITEMS) {
+                const int r = i / Q, q = i % Q;
+                const int gy = y0 + r % TY, gz = z0 + r / TY;
+                if (gy >= 0 && gy < dims.y && gz >= 0 && gz < dims.z)  // outside the array: the border value 0
+                    w[u] = __ldg((const uint4*)(src + ((size_t)gz * dims.y + gy) * dims.x + gx0) + q);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * 256;
+            if (i < ITEMS) {
+                const int r = i / Q, q = i % Q;
+                const int y = r % TY, z = r / TY;
+                const int gy = y0 + y, gz = z0 + z;
+                raw v[PER];
+                memcpy(v, &w[u], 16);
+                float* t = tex + r * TX + 1 + q * PER;
+#pragma unroll
+                for (int k = 0; k < PER; ++k) t[k] = V::value(v[k]);
+                // the brick's own rows (not the apron rows, which belong to the neighbouring bricks) go into the array
+                if (y >= 1 && y < TY - 1 && z >= 1 && z < TZ - 1 && gy < dims.y && gz < dims.z)
+                    surf3Dwrite(w[u], surf, gx0 * (int)sizeof(raw) + q * 16, gy, gz);
+            }
+        }
+    }
+    // the two apron texels of every row
+    for (int i = threadIdx.x; i < ROWS * 2; i += 256) {
+        const int r = i >> 1, side = i & 1;
+        const int gx = side ? gx0 + 32 : gx0 - 1, gy = y0 + r % TY, gz = z0 + r / TY;
+        raw v = 0;
+        if (gx >= 0 && gx < dims.x && gy >= 0 && gy < dims.y && gz >= 0 && gz < dims.z) v = __ldg(src + ((size_t)gz * dims.y + gy) * dims.x + gx);
+        tex[r * TX + (side ? TX - 1 : 0)] = V::value(v);
+    }
+    __syncthreads();
+    reduce_brick<CELL, V>(tex, rx, ry, cx0, cy0, cz0, grid, out);
+}
+
+template <class V, int CELL>
+int launch_upload_range_cell(HostState& st, const void* src, cudaSurfaceObject_t surf)
+{
+    constexpr int BX = 32 / CELL, BY = CELL <= 8 ? 8 / CELL : 1, BZ = BY;
+    constexpr int TX = BX * CELL + 2, TY = BY * CELL + 2, TZ = BZ * CELL + 2;
+    constexpr size_t shm = sizeof(float) * ((size_t)TX * TY * TZ + 2 * (size_t)BX * TY * TZ + 2 * (size_t)BX * BY * TZ);
+    dim3 g((st.gridDims.x + BX - 1) / BX, (st.gridDims.y + BY - 1) / BY, (st.gridDims.z + BZ - 1) / BZ);
+    if (st.volDims.x % 32 == 0 && ((uintptr_t)src & 15u) == 0) {
+        if (shm > 48 * 1024)
+            SVR_TRY(cudaFuncSetAttribute(upload_range_vec_kernel<V, CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        upload_range_vec_kernel<V, CELL><<<g, 256, shm, st.stream>>>((const typename V::raw*)src, surf, st.volDims, st.gridDims, st.dRange);
+    } else {
+        if (shm > 48 * 1024)
+            SVR_TRY(cudaFuncSetAttribute(upload_range_kernel<V, CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        upload_range_kernel<V, CELL><<<g, 256, shm, st.stream>>>((const typename V::raw*)src, surf, st.volDims, st.gridDims, st.dRange);
+    }
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <class V>
+int launch_upload_range(HostState& st, const void* src, cudaSurfaceObject_t surf)
+{
+    switch (st.gridCell) {
+        case 2: return launch_upload_range_cell<V, 2>(st, src, surf);
+        case 4: return launch_upload_range_cell<V, 4>(st, src, surf);
+        case 8: return launch_upload_range_cell<V, 8>(st, src, surf);
+        case 16: return launch_upload_range_cell<V, 16>(st, src, surf);
         default: return fail_msg("range grid: brick kernel needs a cell edge of 2, 4, 8 or 16");
     }
 }
@@ -297,10 +496,58 @@ __global__ void fingerprint_kernel(cudaTextureObject_t pointTex, int3 vol, unsig
     if ((threadIdx.x & 31) == 0) atomicAdd(out, c);
 }
 
+// Small control traffic stays off the copy engines.  A frame pipeline reads its images back with bulk device-to-host copies
+// on another stream; a 16-byte cudaMemcpyAsync or an 8-byte cudaMemsetAsync issued meanwhile queues behind them on the same
+// engine (measured: 0.3 ms per call beside a 33 MB read-back; the grid refresh of a streamed frame took 0.62 ms, most of it
+// waiting).  So: words are zeroed by a kernel, and results travel to the host through a mapped pinned mailbox that a kernel
+// writes, followed by a stream synchronize.
+__global__ void zero_words_kernel(unsigned int* p, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+
+int zero_words(HostState& st, void* p, size_t bytes)
+{
+    const size_t n = bytes / 4;
+    const unsigned blocks = n <= 1024 ? 1u : (unsigned)std::min<size_t>((n + 1023) / 1024, 148 * 8);
+    zero_words_kernel<<<blocks, n <= 32 ? 32 : 256, 0, st.stream>>>((unsigned int*)p, n);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    return 0;
+}
+
+__global__ void mailbox_kernel(const unsigned int* src, unsigned int* mailbox, int words)
+{
+    if ((int)threadIdx.x < words) mailbox[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
+int ensure_mailbox(HostState& st)
+{
+    if (!st.hMailbox) {
+        SVR_TRY(cudaHostAlloc(&st.hMailbox, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        SVR_TRY(cudaHostGetDevicePointer(&st.dMailbox, st.hMailbox, 0));
+    }
+    return 0;
+}
+
+// host <- device, at most 64 bytes, synchronous with respect to the library's stream
+int read_small(HostState& st, void* host, const void* dev, size_t bytes)
+{
+    if (bytes > 64 || (bytes & 3)) return fail_msg("read_small: at most 64 bytes, a multiple of 4");
+    if (int rc = ensure_mailbox(st)) return rc;
+    mailbox_kernel<<<1, 32, 0, st.stream>>>((const unsigned int*)dev, (unsigned int*)st.dMailbox, (int)(bytes / 4));
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    SVR_TRY(cudaStreamSynchronize(st.stream));
+    memcpy(host, st.hMailbox, bytes);
+    return 0;
+}
+
 int launch_fingerprint(HostState& st, int slot)
 {
     if (!st.dFingerprint) SVR_TRY(cudaMalloc(&st.dFingerprint, 2 * sizeof(unsigned long long)));
-    SVR_TRY(cudaMemsetAsync(st.dFingerprint + slot, 0, sizeof(unsigned long long), st.stream));
+    if (int rc = zero_words(st, st.dFingerprint + slot, sizeof(unsigned long long))) return rc;
     fingerprint_kernel<<<64, 128, 0, st.stream>>>(st.volPointTex, st.volDims, st.dFingerprint + slot);
     count_launch();
     SVR_TRY(cudaGetLastError());
@@ -309,7 +556,8 @@ int launch_fingerprint(HostState& st, int slot)
 
 // 64-bit hash of a transfer-function table: of the linear copy the majorants are built from (tex == 0), or of the live
 // array read through its texture object at the texel centres (where the linear filter returns the texel itself)
-__global__ void tf_hash_kernel(const float4* table, cudaTextureObject_t tex, int n, unsigned long long* out)
+__global__ void tf_hash_kernel(const float4* table, cudaTextureObject_t tex, int n, unsigned long long* out, const unsigned long long* ref,
+                               unsigned long long* mailbox)
 {
     unsigned long long h = 0ull;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -320,7 +568,20 @@ __global__ void tf_hash_kernel(const float4* table, cudaTextureObject_t tex, int
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
+    // one block: the sum is written, not accumulated (no zeroing launch), and when the caller wants to compare it with the
+    // stored hash both go to the host mailbox from here (the ray caster does this on every call: one launch, not three)
+    __shared__ unsigned long long part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned w = 1; w < (blockDim.x + 31u) / 32u; ++w) h += part[w];
+        *out = h;
+        if (mailbox) {
+            mailbox[0] = *ref;
+            mailbox[1] = h;
+            __threadfence_system();
+        }
+    }
 }
 
 int create_point_view(HostState& st, const cudaResourceDesc& vrd, const cudaChannelFormatDesc& ch)
@@ -344,6 +605,10 @@ void release_grid(HostState& st)
 {
     if (st.volPointTex) cudaDestroyTextureObject(st.volPointTex);
     st.volPointTex = 0;
+    if (st.uploadSurf) cudaDestroySurfaceObject(st.uploadSurf);
+    st.uploadSurf = 0;
+    st.uploadSurfArray = nullptr;
+    cudaGetLastError();  // as for the view: the array behind it may be gone already
     cudaFree(st.dRange);
     cudaFree(st.dMajorant);
     cudaFree(st.dDist[0]);
@@ -358,6 +623,47 @@ void release_grid(HostState& st)
     st.autoArray = nullptr;  // the automatic cell size is re-derived for whatever volume comes next
     st.rangeValid = false;
     st.majorantValid = false;
+}
+
+// svr_volume_upload's fast path (see upload_range_kernel).  *done stays false when the array, the grid or the options do
+// not allow it; the caller then copies with the driver and the ranges are rebuilt from the array at the next render.
+int upload_with_ranges(cudaArray_t arr, const cudaChannelFormatDesc& ch, const cudaExtent& ext, unsigned int flags, const void* devData, bool* done)
+{
+    HostState& st = state();
+    *done = false;
+    if (!st.options[SVR_OPT_FUSED_UPLOAD] || !(flags & cudaArraySurfaceLoadStore)) return 0;
+    if (arr != st.gridArray || !st.dRange || !st.volPointTex || st.gridCell > 16) return 0;
+    // setup_volume since the last render: the array behind the handle may be a new one (build_grid looks first)
+    if (st.fingerprintDue) return 0;
+    if ((int)ext.width != st.volDims.x || (int)ext.height != st.volDims.y || (int)ext.depth != st.volDims.z) return 0;
+    if (ch.y || ch.z || ch.w) return 0;
+    const bool isFloat = ch.f == cudaChannelFormatKindFloat, isUint = ch.f == cudaChannelFormatKindUnsigned;
+    if (!((isUint && (ch.x == 8 || ch.x == 16)) || (isFloat && (ch.x == 16 || ch.x == 32)))) return 0;
+    if (st.uploadSurfArray != arr) {
+        if (st.uploadSurf) cudaDestroySurfaceObject(st.uploadSurf);
+        st.uploadSurf = 0;
+        st.uploadSurfArray = nullptr;
+        cudaGetLastError();
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        SVR_TRY(cudaCreateSurfaceObject(&st.uploadSurf, &rd));
+        st.uploadSurfArray = arr;
+    }
+    int rc;
+    if (isUint && ch.x == 8) rc = launch_upload_range<VoxU8>(st, devData, st.uploadSurf);
+    else if (isUint) rc = launch_upload_range<VoxU16>(st, devData, st.uploadSurf);
+    else if (ch.x == 16) rc = launch_upload_range<VoxF16>(st, devData, st.uploadSurf);
+    else rc = launch_upload_range<VoxF32>(st, devData, st.uploadSurf);
+    if (rc) return rc;
+    st.rangeValid = true;
+    st.majorantValid = false;
+    rc = launch_fingerprint(st, 0);  // of the voxels these ranges describe
+    if (rc) return rc;
+    st.fusedUploads++;
+    *done = true;
+    return 0;
 }
 
 // sum and count of the non-zero majorants (the statistic behind the automatic cell size)
@@ -417,8 +723,8 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
                 rc = launch_fingerprint(st, 1);
                 if (rc) return rc;
                 unsigned long long h[2] = {0, 1};
-                SVR_TRY(cudaMemcpyAsync(h, st.dFingerprint, sizeof(h), cudaMemcpyDeviceToHost, st.stream));
-                SVR_TRY(cudaStreamSynchronize(st.stream));
+                rc = read_small(st, h, st.dFingerprint, sizeof(h));
+                if (rc) return rc;
                 if (h[0] != h[1]) st.rangeValid = false;
             }
         }
@@ -485,11 +791,10 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
                                            cudaMemcpyDeviceToDevice, st.stream));
         tf_sparse_kernel<<<1, 1024, 0, st.stream>>>(st.dTfTable, n, levels, st.dTfSparse);
         if (!st.dTfHash) SVR_TRY(cudaMalloc(&st.dTfHash, 2 * sizeof(unsigned long long)));
-        SVR_TRY(cudaMemsetAsync(st.dTfHash, 0, sizeof(unsigned long long), st.stream));
-        tf_hash_kernel<<<1, 256, 0, st.stream>>>(st.dTfTable, 0, n, st.dTfHash);  // of the table these majorants come from
+        tf_hash_kernel<<<1, 256, 0, st.stream>>>(st.dTfTable, 0, n, st.dTfHash, nullptr, nullptr);  // of the table these majorants come from
         const int px = st.gridDims.x + 2, py = st.gridDims.y + 2, pz = st.gridDims.z + 2;
         const size_t padded = (size_t)px * py * pz;
-        SVR_TRY(cudaMemsetAsync(st.dMajorant, 0, padded * sizeof(float), st.stream));
+        if (int rc = zero_words(st, st.dMajorant, padded * sizeof(float))) return rc;
         occ_init_kernel<<<1, 32, 0, st.stream>>>(st.dOcc);
         dim3 mb(32, 4, 1), mg((st.gridDims.x + 31) / 32, (st.gridDims.y + 3) / 4, st.gridDims.z);
         majorant_kernel<<<mg, mb, 0, st.stream>>>(st.dRange, st.gridDims, st.dTfSparse, n, vol.densityScale, st.dMajorant, st.dOcc);
@@ -538,15 +843,14 @@ static int auto_cell(HostState& st, int current, int* want)
 {
     const size_t padded = (size_t)(st.gridDims.x + 2) * (st.gridDims.y + 2) * (st.gridDims.z + 2);
     if (!st.dStats) SVR_TRY(cudaMalloc(&st.dStats, 16));
-    SVR_TRY(cudaMemsetAsync(st.dStats, 0, 16, st.stream));
+    if (int rc = zero_words(st, st.dStats, 16)) return rc;
     majorant_stats_kernel<<<148 * 4, 256, 0, st.stream>>>(st.dMajorant, padded, (double*)st.dStats, (unsigned long long*)((char*)st.dStats + 8));
     count_launch();
     struct {
         double sum;
         unsigned long long count;
     } h;
-    SVR_TRY(cudaMemcpyAsync(&h, st.dStats, 16, cudaMemcpyDeviceToHost, st.stream));
-    SVR_TRY(cudaStreamSynchronize(st.stream));
+    if (int rc = read_small(st, &h, st.dStats, 16)) return rc;
     *want = current;
     if (h.count == 0 || !(h.sum > 0.0)) return 0;  // nothing to track through: any size will do
     const double ideal = log2(2.0 / (h.sum / (double)h.count));  // log2 of twice the mean free path, in voxels
@@ -567,12 +871,13 @@ int tf_content_changed(const svr_transfer_function& tf, bool* changed)
     cudaResourceDesc trd;
     SVR_TRY(cudaGetTextureObjectResourceDesc(&trd, tf.tex));
     if (trd.resType != cudaResourceTypeArray || trd.res.array.array != st.majorantTfArray) return 0;
-    SVR_TRY(cudaMemsetAsync(st.dTfHash + 1, 0, sizeof(unsigned long long), st.stream));
-    tf_hash_kernel<<<1, 256, 0, st.stream>>>(nullptr, tf.tex, st.tfEntries, st.dTfHash + 1);
+    if (int rc = ensure_mailbox(st)) return rc;
+    tf_hash_kernel<<<1, 256, 0, st.stream>>>(nullptr, tf.tex, st.tfEntries, st.dTfHash + 1, st.dTfHash, (unsigned long long*)st.dMailbox);
     count_launch();
-    unsigned long long h[2] = {0, 1};
-    SVR_TRY(cudaMemcpyAsync(h, st.dTfHash, sizeof(h), cudaMemcpyDeviceToHost, st.stream));
+    SVR_TRY(cudaGetLastError());
     SVR_TRY(cudaStreamSynchronize(st.stream));
+    unsigned long long h[2];
+    memcpy(h, st.hMailbox, sizeof(h));
     *changed = h[0] != h[1];
     return 0;
 }

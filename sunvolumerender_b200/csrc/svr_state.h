@@ -35,6 +35,11 @@ struct HostState {
     float4* dTfTable = nullptr;           // linear copy of the TF array
     int tfEntries = 0;
     cudaTextureObject_t volPointTex = 0;  // point-sampled view of gridArray
+    cudaSurfaceObject_t uploadSurf = 0;   // store view of uploadSurfArray (svr_volume_upload from a device buffer, svr_macrocell.cu)
+    cudaArray_t uploadSurfArray = nullptr;
+    unsigned long long fusedUploads = 0;
+    void* hMailbox = nullptr;             // 64 bytes of mapped pinned memory: small results reach the host without a copy engine
+    void* dMailbox = nullptr;
     bool rangeValid = false;              // false until the range grid reflects the array's current voxels
     bool fingerprintDue = false;          // setup_volume was called since the voxels were last looked at
     unsigned long long* dFingerprint = nullptr;  // [0] sampled hash of the voxels the ranges were built from, [1] scratch
@@ -108,6 +113,7 @@ int ensure_grid(DevScene* scene, bool force, int maxAutoCell = 32);
 // launch + an 16-byte read-back; the ray caster's drop-in entry point, whose host may edit the table behind an unchanged
 // handle, gui/transferfunction.cpp:128-151).  Also true when no majorants exist yet.
 int tf_content_changed(const svr_transfer_function& tf, bool* changed);
+int upload_with_ranges(cudaArray_t arr, const cudaChannelFormatDesc& ch, const cudaExtent& ext, unsigned int flags, const void* devData, bool* done);
 
 // Builds / refreshes the environment light's importance sampler for scene->env and fills scene->envS.
 int ensure_env_sampler(DevScene* scene);

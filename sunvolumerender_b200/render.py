@@ -464,7 +464,8 @@ class VolumeStream:
         main.wait_event(self.ready[slot])
         L.check(self.lib.svr_volume_upload(C.byref(self.r.volume), self.stage_ptr[slot], 1), "svr_volume_upload")
         self.consumed[slot].record(main)
-        self.r.lib.setup_volume(C.byref(self.r.volume))
+        # no setup_volume: the svr_volume struct is unchanged, and the upload itself has invalidated what depends on the voxels
+        # (a setup_volume here would make the next render re-check the array behind the handle: one more host round trip per frame)
         self.r.frame_no = 0
         self.tail ^= 1
         self.inflight -= 1

@@ -140,12 +140,14 @@ def test_upload_into_bound_resources_equals_fresh_load(renderer):
 
 
 @pytest.mark.parametrize("fmt", [L.VOXEL_U8, L.VOXEL_U16, L.VOXEL_F16, L.VOXEL_F32])
-@pytest.mark.parametrize("cell", [4, 8, 16])
-def test_range_grid_follows_uploads_from_host_and_device(renderer, fmt, cell):
+@pytest.mark.parametrize("cell", [2, 4, 8, 16])
+@pytest.mark.parametrize("dims", [(45, 38, 29), (64, 21, 19)])  # x, y, z; rows of a multiple of 32 voxels take the 16-byte kernel
+def test_range_grid_follows_uploads_from_host_and_device(renderer, fmt, cell, dims):
     """The macrocell ranges after svr_volume_upload (host or device source) are those of a fresh load of
     the same voxels, float for float -- every u8 / u16 value, a volume whose dimensions are not multiples
-    of the cell (zero border), every brick-kernel cell size."""
-    dims = (45, 38, 29)  # x, y, z
+    of the cell (zero border), every brick-kernel cell size.  A device source takes the one-pass kernel that fills
+    the array and reduces the ranges together (SVR_OPT_FUSED_UPLOAD): same array contents, same ranges as the copy +
+    read-back path."""
     rng = np.random.default_rng(11)
     nvox = dims[0] * dims[1] * dims[2]
     dt = S.VOXEL_DTYPES[fmt]
@@ -184,12 +186,21 @@ def test_range_grid_follows_uploads_from_host_and_device(renderer, fmt, cell):
     renderer.upload_volume(b)                            # host source
     rb_tex = ranges()
     assert not np.array_equal(ra_tex, rb_tex)
-    renderer.upload_volume(torch.from_numpy(a.copy()).cuda().view(torch.uint8))   # device source
+    fused0 = renderer.lib.svr_fused_upload_count()
+    renderer.upload_volume(torch.from_numpy(a.copy()).cuda().view(torch.uint8))   # device source: one pass
     ra_lin = ranges()
+    assert np.array_equal(renderer.download_volume(dims, dt).view(np.uint8), a.view(np.uint8))
     renderer.upload_volume(torch.from_numpy(b.copy()).cuda().view(torch.uint8))
     rb_lin = ranges()
+    assert np.array_equal(renderer.download_volume(dims, dt).view(np.uint8), b.view(np.uint8))
+    assert renderer.lib.svr_fused_upload_count() == fused0 + 2
     assert np.array_equal(ra_tex.view(np.uint32), ra_lin.view(np.uint32))
     assert np.array_equal(rb_tex.view(np.uint32), rb_lin.view(np.uint32))
+    renderer.set_option(L.OPT_FUSED_UPLOAD, 0)                                    # device source: copy, ranges from the array
+    renderer.upload_volume(torch.from_numpy(a.copy()).cuda().view(torch.uint8))
+    assert np.array_equal(ranges().view(np.uint32), ra_lin.view(np.uint32))
+    assert renderer.lib.svr_fused_upload_count() == fused0 + 2
+    renderer.set_option(L.OPT_FUSED_UPLOAD, 1)
     assert ra_lin[..., 0].min() == 0.0 and ra_lin[..., 1].max() > 0.9
     # against numpy on the same voxels: min / max over texels cC-1 .. (c+1)C with a zero border
     norm = {L.VOXEL_U8: 255.0, L.VOXEL_U16: 65535.0}.get(fmt, 1.0)
