@@ -404,36 +404,47 @@ __global__ void majorant_kernel(const float2* range, int3 grid, const float* spa
                                 float* padded, int* occ)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
-    if (x >= grid.x || y >= grid.y) return;
-    float2 r = range[((size_t)z * grid.y + y) * grid.x + x];
-    float a = r.x * densityScale, b = r.y * densityScale;
-    if (a > b) {
-        float t = a;
-        a = b;
-        b = t;
+    const bool inside = x < grid.x && y < grid.y;
+    float m = 0.f;
+    if (inside) {
+        float2 r = range[((size_t)z * grid.y + y) * grid.x + x];
+        float a = r.x * densityScale, b = r.y * densityScale;
+        if (a > b) {
+            float t = a;
+            a = b;
+            b = t;
+        }
+        // linear-filter footprint of tex1D at x: entries floor(x*n - 0.5) and +1 (clamped).  The unit
+        // converts x*n - 0.5 to fixed point with 8 fractional bits, so widen the interval by 2/256 of an
+        // entry; a coordinate rounded onto an entry boundary gives the entry beyond it weight 0.
+        // (Widening by whole entries would make air, intensity exactly 0, inherit the opacity of
+        // entry 1 and never be empty.)
+        float fa = floorf(a * (float)n - 0.5f - 0.0078125f), fb = floorf(b * (float)n - 0.5f + 0.0078125f) + 1.f;
+        if (!(fa == fa)) fa = 0.f;  // NaN voxels: cover the whole table
+        if (!(fb == fb)) fb = (float)(n - 1);
+        int lo = (int)fminf(fmaxf(fa, 0.f), (float)(n - 1));
+        int hi = (int)fminf(fmaxf(fb, 0.f), (float)(n - 1));
+        int len = hi - lo + 1;
+        int k = 31 - __clz(len);
+        m = fmaxf(fmaxf(sparse[k * n + lo], sparse[k * n + hi - (1 << k) + 1]), 0.f);
+        int px = grid.x + 2, py = grid.y + 2;
+        padded[((size_t)(z + 1) * py + (y + 1)) * px + (x + 1)] = m;
     }
-    // linear-filter footprint of tex1D at x: entries floor(x*n - 0.5) and +1 (clamped).  The unit
-    // converts x*n - 0.5 to fixed point with 8 fractional bits, so widen the interval by 2/256 of an
-    // entry; a coordinate rounded onto an entry boundary gives the entry beyond it weight 0.
-    // (Widening by whole entries would make air, intensity exactly 0, inherit the opacity of
-    // entry 1 and never be empty.)
-    float fa = floorf(a * (float)n - 0.5f - 0.0078125f), fb = floorf(b * (float)n - 0.5f + 0.0078125f) + 1.f;
-    if (!(fa == fa)) fa = 0.f;  // NaN voxels: cover the whole table
-    if (!(fb == fb)) fb = (float)(n - 1);
-    int lo = (int)fminf(fmaxf(fa, 0.f), (float)(n - 1));
-    int hi = (int)fminf(fmaxf(fb, 0.f), (float)(n - 1));
-    int len = hi - lo + 1;
-    int k = 31 - __clz(len);
-    float m = fmaxf(fmaxf(sparse[k * n + lo], sparse[k * n + hi - (1 << k) + 1]), 0.f);
-    int px = grid.x + 2, py = grid.y + 2;
-    padded[((size_t)(z + 1) * py + (y + 1)) * px + (x + 1)] = m;
-    if (m > 0.f) {
-        atomicMin(&occ[0], x);
-        atomicMin(&occ[1], y);
-        atomicMin(&occ[2], z);
-        atomicMax(&occ[3], x);
-        atomicMax(&occ[4], y);
-        atomicMax(&occ[5], z);
+    // occupied box: reduced over the warp first (a warp is one row of 32 cells), six atomics per warp with an occupied cell
+    // instead of six per occupied cell (they all hit the same six words: the kernel took 0.085 ms at 128^3 cells, most of it here)
+    const bool occupied = m > 0.f;
+    const unsigned any = __ballot_sync(0xffffffffu, occupied);
+    if (any) {
+        const int xlo = __reduce_min_sync(0xffffffffu, occupied ? x : INT_MAX), xhi = __reduce_max_sync(0xffffffffu, occupied ? x : -1);
+        const int ylo = __reduce_min_sync(0xffffffffu, occupied ? y : INT_MAX), yhi = __reduce_max_sync(0xffffffffu, occupied ? y : -1);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&occ[0], xlo);
+            atomicMin(&occ[1], ylo);
+            atomicMin(&occ[2], z);
+            atomicMax(&occ[3], xhi);
+            atomicMax(&occ[4], yhi);
+            atomicMax(&occ[5], z);
+        }
     }
 }
 
