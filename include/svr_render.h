@@ -154,6 +154,16 @@ enum svr_option {
      * the same pass (streamed time series: a new volume per frame).  0 = copy, then rebuild the ranges from the array at the
      * next render.  Arrays, ranges and images are bit-identical either way. */
     SVR_OPT_FUSED_UPLOAD = 24,
+    /* render_pathtracer (one sample per call): once a progressive render has reached frame 16 with nothing changed, the next 32
+     * samples of every pixel are computed in ONE launch of the sample-parallel kernel and kept; the following calls only fold the
+     * kept sample of their frame into the running mean and tone-map (the same arithmetic on the same sample values: hdrBuffer and
+     * image are bit-identical, frame for frame, to computing one sample per call).  Any setup_*, upload or option, a frameNo other
+     * than the next one, another hdrBuffer, size or traceDepth discards what was kept.  Value = the batch (default 32, at most
+     * 32); > 0: the library times one single-sample launch, the first batch and one fold per scene and stops batching for that
+     * scene when it does not pay (views in which the volume fills the frame); < 0: always batch -value samples; 0, 1, -1 = off.
+     * Not used with SVR_OPT_COUNTERS, nor where the scatter-queue kernel would run (traceDepth >= SVR_OPT_PT_QUEUE_MIN_DEPTH).
+     * Memory: batch x pixels x 12 bytes (at most 1 GiB; larger canvases get smaller batches). */
+    SVR_OPT_PT_LOOKAHEAD = 25,
     SVR_OPT_COUNT_
 };
 /* Defaults can also come from the environment, read once at first use, for hosts that only know the
@@ -290,6 +300,8 @@ int svr_counters_read(uint64_t* host_out, uint32_t n);
 uint64_t svr_launch_count(void);
 /* How many svr_volume_upload calls took the one-pass path (SVR_OPT_FUSED_UPLOAD) since the library was loaded. */
 uint64_t svr_fused_upload_count(void);
+/* How many look-ahead batches (SVR_OPT_PT_LOOKAHEAD) render_pathtracer has launched since the library was loaded. */
+uint64_t svr_lookahead_batch_count(void);
 
 /* Gather-roofline microbenchmarks: `taps_per_thread` dependent-free tex3D taps per thread over
  * the bound volume, coherent (ray-like) or random.  Returns taps issued via *host_taps. */

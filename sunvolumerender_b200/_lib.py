@@ -100,7 +100,7 @@ assert C.sizeof(RenderParams) == 16 and RenderParams.hdrBuffer.offset == 8
 (OPT_PT_MODE, OPT_SHADOW_ESTIMATOR, OPT_ENV_ENABLED, OPT_MACROCELL_SIZE, OPT_RC_SKIP, OPT_SEED, OPT_COUNTERS,
  OPT_PT_BLOCK, OPT_RC_BLOCK, OPT_PT_KERNEL, OPT_PT_ROUNDS, OPT_LEAP, OPT_PT_ENTRY_CACHE, OPT_PT_WARP_PIXELS,
  OPT_PT_WARP_MIN_SPP, OPT_PT_QUEUE_MIN_DEPTH, OPT_SETUP_SYNC, OPT_PT_LIGHT_CULL, OPT_PT_PROFILE, OPT_PT_REFILL, OPT_PT_POOL_PIXELS, OPT_ENV_NEE, OPT_PT_BLOCK_SPLIT, OPT_PT_PIXEL_CACHE,
- OPT_FUSED_UPLOAD) = range(25)
+ OPT_FUSED_UPLOAD, OPT_PT_LOOKAHEAD) = range(26)
 # enum svr_voxel_format
 VOXEL_U8, VOXEL_U16, VOXEL_F16, VOXEL_F32 = range(4)
 VOXEL_BYTES = {VOXEL_U8: 1, VOXEL_U16: 2, VOXEL_F16: 2, VOXEL_F32: 4}
@@ -159,6 +159,7 @@ SIGNATURES = [
     ("svr_counters_read", C.c_int, [C.POINTER(C.c_uint64), C.c_uint32]),
     ("svr_launch_count", C.c_uint64, []),
     ("svr_fused_upload_count", C.c_uint64, []),
+    ("svr_lookahead_batch_count", C.c_uint64, []),
     ("svr_microbench_taps", C.c_int, [C.POINTER(Volume), C.c_int, C.c_uint32, C.c_uint32, _P, C.POINTER(C.c_uint64)]),
     ("svr_layout_brick", C.c_int, [_P, _P, C.c_uint32]),
     ("svr_microbench_soft_taps", C.c_int, [_P, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, C.POINTER(C.c_uint64)]),

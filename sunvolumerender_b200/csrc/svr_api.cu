@@ -40,6 +40,7 @@ HostState& state()
         p->options[SVR_OPT_PT_REFILL] = 0;
         p->options[SVR_OPT_PT_PIXEL_CACHE] = 1;
         p->options[SVR_OPT_FUSED_UPLOAD] = 1;
+        p->options[SVR_OPT_PT_LOOKAHEAD] = 32;
         // A host that only knows the reference's seven entry points (gui/canvas.cpp) cannot call
         // svr_set_option: the same switches are read once from the environment.
         static const struct { const char* name; int key, lo, hi; } kEnv[] = {
@@ -171,6 +172,10 @@ extern "C" int svr_set_device(int device)
     cudaFree(st.dPixelCache);
     st.dPixelCache = nullptr;
     st.pixelCacheCap = 0;
+    cudaFree(st.dAhead);
+    st.dAhead = nullptr;
+    st.aheadCapFloats = 0;
+    st.aheadCount = 0;
     st.sceneEpoch++;
     cudaFree(st.dEnvMarg);
     cudaFree(st.dEnvCond);
@@ -247,6 +252,7 @@ extern "C" int svr_get_option(int key)
 
 extern "C" uint64_t svr_launch_count(void) { return state().launches; }
 extern "C" uint64_t svr_fused_upload_count(void) { return state().fusedUploads; }
+extern "C" uint64_t svr_lookahead_batch_count(void) { return state().aheadBatches; }
 
 extern "C" int svr_volume_invalidate_cache(void)
 {

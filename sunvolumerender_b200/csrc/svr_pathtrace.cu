@@ -42,6 +42,10 @@
 #ifndef SVR_PT_MAX_THREADS
 #define SVR_PT_MAX_THREADS 128
 #endif
+// the lane-per-pixel kernel (shape 1: render_pathtracer's one sample per call)
+#ifndef SVR_PT_MEGA_BLOCKS
+#define SVR_PT_MEGA_BLOCKS SVR_PT_MIN_BLOCKS
+#endif
 // the majorant-profile kernel (shape 4) and the scatter-queue kernel (shape 3) have budgets of their own
 #ifndef SVR_PT_PROFILE_BLOCKS
 #define SVR_PT_PROFILE_BLOCKS 7
@@ -76,6 +80,8 @@ struct PtLaunch {
     float2* pixelInfo;               // (tSkip, flags: bit 0 lights, bit 1 empty) per pixel
     int32_t blockSplit;              // shape 2: the warps of a block split the samples of one row's pixels (SVR_OPT_PT_BLOCK_SPLIT)
     uint32_t bandPhase, bandStride;  // this launch renders the row bands (block rows) phase, phase + stride, ... (1 GPU: 0, 1)
+    float* perSample;                // look-ahead launch (shape 2, nSamples <= 32): component c of sample j of pixel p -> perSample[p * 3 * nSamples + 3 * j + c], nothing else is written
+    uint8_t* constantPixel;          // look-ahead launch: 1 for a pixel whose every sample is the constant sky (no record written), else 0
 };
 
 template <int MODE>
@@ -758,7 +764,7 @@ SVR_DEV void trace_sample(const DevScene& s, const PtLaunch& a, PathState<MODE>&
 }
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtrace_mega_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
+__global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MEGA_BLOCKS) pathtrace_mega_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idx = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
@@ -799,7 +805,9 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
 // (warp w takes the rounds w, w + nWarps, ...; their sums meet in shared memory in a fixed order) instead of taking a row
 // each.  A pixel then occupies a warp for a quarter of the time, which shortens the end of a launch -- the last blocks of a
 // frame run with the machine half empty -- and matters when a frame is short (one frame divided over 8 GPUs).
-template <int MODE, bool COUNT, bool SPLIT>
+// AHEAD (SVR_OPT_PT_LOOKAHEAD): at most 32 samples, one per lane, and instead of a pixel's sum every sample's radiance is stored
+// for render_pathtracer's later calls.
+template <int MODE, bool COUNT, bool SPLIT, bool AHEAD = false>
 __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtrace_warp_kernel(const __grid_constant__ DevScene s, const PtLaunch a, Counters* cnt)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nWarps = blockDim.x >> 5;
@@ -831,6 +839,10 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
                 // every sample of this pixel is the constant sky (see trace_sample): nSamples times the same value, written by one lane
                 const float3 sky = (a.traceDepth != 0 && s.envEnabled) ? f3(s.env.defaultRadiance) * s.env.intensity : f3(0.f);
+                if (AHEAD) {
+                    if (lane == 0) a.constantPixel[offset] = 1;
+                    continue;
+                }
                 if (lane == 0 && (!SPLIT || warp == 0)) {
                     lc.add(SVR_CNT_PATHS, a.nSamples);
                     write_pixel(s, a, offset, sky * (float)a.nSamples);
@@ -841,6 +853,21 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
                 trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
             float3 sum = pixel_sum<MODE>(ps);
             __syncwarp();
+            if (AHEAD) {
+                // lane j traced exactly sample j: `sum` is that sample's radiance.  The pixel's record is 3 * nSamples consecutive
+                // floats (x, y, z of sample 0, of sample 1, ...): transposed through shuffles so that every store is one coalesced
+                // row of the record (one 4-byte store per lane into 32 slices 25 MB apart took 4 ms per 32-sample batch).
+                float* rec = a.perSample + (size_t)offset * (3u * a.nSamples);
+#pragma unroll
+                for (uint32_t r = 0; r < 3u; ++r) {
+                    const uint32_t i = r * 32u + lane, src = i / 3u, c = i - 3u * src;
+                    const float vx = __shfl_sync(0xffffffffu, sum.x, (int)src), vy = __shfl_sync(0xffffffffu, sum.y, (int)src),
+                                vz = __shfl_sync(0xffffffffu, sum.z, (int)src);
+                    if (i < 3u * a.nSamples) rec[i] = c == 0u ? vx : (c == 1u ? vy : vz);
+                }
+                if (lane == 0) a.constantPixel[offset] = 0;
+                continue;
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
@@ -1981,6 +2008,23 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     lc.flush(cnt);
 }
 
+// A later call of the look-ahead protocol: fold the kept sample of frame a.firstSample into the running mean and tone-map --
+// write_pixel itself, on the value the sample-parallel launch stored.
+__global__ void __launch_bounds__(256) lookahead_consume_kernel(const __grid_constant__ DevScene s, const PtLaunch a, const float* __restrict__ records,
+                                                                const uint8_t* __restrict__ constantPixel, uint32_t batch, uint32_t j)
+{
+    const uint32_t offset = blockIdx.x * blockDim.x + threadIdx.x;
+    if (offset >= s.cam.imageW * s.cam.imageH) return;
+    float3 v;
+    if (constantPixel[offset]) {
+        v = (a.traceDepth != 0 && s.envEnabled) ? f3(s.env.defaultRadiance) * s.env.intensity : f3(0.f);  // as the kernels write it for an all-sky pixel
+    } else {
+        const float* rec = records + (size_t)offset * (3u * batch) + 3u * j;
+        v = f3(rec[0], rec[1], rec[2]);
+    }
+    write_pixel(s, a, offset, v);
+}
+
 // root-side resolve of summed partials: hdr = rgb / w, tone map, both in one pass
 __global__ void resolve_kernel(const float4* __restrict__ sum, float* __restrict__ hdr, uint32_t* __restrict__ img,
                                uint32_t npix, float exposure)
@@ -2020,6 +2064,8 @@ void launch_mode(int shape, dim3 grid, int block, cudaStream_t stream, const Dev
     } else if (shape == 3) {  // launch_pathtrace() only picks it for MODE 2
         if (cnt) pathtrace_queue_kernel<true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_queue_kernel<false><<<grid, block, 0, stream>>>(sc, a, cnt);
+    } else if (shape == 2 && a.perSample) {  // launch_pathtrace() only sets it without counters and without the block split
+        pathtrace_warp_kernel<MODE, false, false, true><<<grid, block, 0, stream>>>(sc, a, cnt);
     } else if (shape == 2 && a.blockSplit) {
         if (cnt) pathtrace_warp_kernel<MODE, true, true><<<grid, block, 0, stream>>>(sc, a, cnt);
         else pathtrace_warp_kernel<MODE, false, true><<<grid, block, 0, stream>>>(sc, a, cnt);
@@ -2084,7 +2130,12 @@ int launch_pathtrace(PtLaunch& a)
     if (shape == 4 && (mode != 2 || sc.cam.apeture != 0.f)) shape = 2;
     if (shape == 5 && mode != 2) shape = 2;
     if (sc.envNee && shape >= 3) shape = 2;  // environment next-event estimation lives in the shared event code of shapes 0-2
-    if (shape >= 2 && a.nSamples < (uint32_t)st.options[SVR_OPT_PT_WARP_MIN_SPP]) shape = 1;
+    if (shape >= 2 && a.nSamples < (uint32_t)st.options[SVR_OPT_PT_WARP_MIN_SPP] && !a.perSample) shape = 1;
+    if (a.perSample && (shape != 2 || cnt || a.nSamples > 32u)) {
+        a.perSample = nullptr;  // look-ahead is for the plain sample-parallel shape: the caller renders this frame the ordinary way
+        return 0;
+    }
+    if (a.hdr) st.aheadCount = 0;  // an ordinary launch moves the running mean on: samples kept for later frames no longer follow it
     // shape 4: idle lanes take new camera samples together, once this many wait (SVR_OPT_PT_REFILL)
     if (shape == 4) a.marchBurst = st.options[SVR_OPT_PT_REFILL] > 0 ? st.options[SVR_OPT_PT_REFILL] : 8;
     if (shape == 5) a.marchBurst = st.options[SVR_OPT_PT_REFILL] > 0 ? st.options[SVR_OPT_PT_REFILL] : 8;
@@ -2149,18 +2200,159 @@ int launch_pathtrace(PtLaunch& a)
 using namespace svr;
 
 // pathtracer.h:17 / pathtracer.cu:292-304.  One call = one sample per pixel; asynchronous.
+// SVR_OPT_PT_LOOKAHEAD > 0: whether batches pay is MEASURED once per scene (events around one single-sample launch, the first
+// batch and one fold; read when the next batch is due, never waited for).  Where nearly every pixel is sky a 32-sample batch of
+// the sample-parallel kernel plus 32 folds take 0.55 of 32 single launches (C3: 26.3 -> 16.8 ms per 256 frames); with the body
+// filling the frame a 32-sample launch is no better per sample than the lane-per-pixel kernel (68.0 against 64.5 ms), and
+// look-ahead switches itself off until the scene changes.  Images do not depend on the decision (the two paths are bit-equal).
+static bool lookahead_events(HostState& st)
+{
+    if (!st.aheadEvReady) {
+        for (int i = 0; i < 6; ++i)
+            if (cudaEventCreate(&st.aheadEv[i]) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+        st.aheadEvReady = true;
+    }
+    return true;
+}
+
+// true = measured, and batches do not pay for the current scene
+static bool lookahead_does_not_pay(HostState& st)
+{
+    if (st.aheadTimedEpoch != st.sceneEpoch || st.aheadSingleEpoch != st.sceneEpoch || st.aheadTimeFold || !st.aheadTimedBatch) return false;
+    for (int i = 1; i < 6; i += 2)
+        if (cudaEventQuery(st.aheadEv[i]) != cudaSuccess) {
+            cudaGetLastError();
+            return false;  // not there yet: ask again at the next batch
+        }
+    float single = 0.f, batch = 0.f, fold = 0.f;
+    if (cudaEventElapsedTime(&single, st.aheadEv[0], st.aheadEv[1]) != cudaSuccess || cudaEventElapsedTime(&batch, st.aheadEv[2], st.aheadEv[3]) != cudaSuccess ||
+        cudaEventElapsedTime(&fold, st.aheadEv[4], st.aheadEv[5]) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return batch / (float)st.aheadTimedBatch + fold > 0.97f * single;
+}
+
+// *done = the frame has been produced (from samples kept by an earlier call, or by a batch launched now).
+static int lookahead_frame(uint32_t* img, float* hdr, uint32_t traceDepth, uint32_t frameNo, bool* done)
+{
+    HostState& st = state();
+    *done = false;
+    const uint32_t W = st.scene.cam.imageW, H = st.scene.cam.imageH;
+    const int opt = st.options[SVR_OPT_PT_LOOKAHEAD];
+    const bool adaptive = opt > 0;
+    const uint32_t maxBatch = (uint32_t)std::min(opt < 0 ? -opt : opt, 32);
+    if (maxBatch < 2u || !hdr || !W || !H || st.options[SVR_OPT_COUNTERS] || (adaptive && st.aheadOffEpoch == st.sceneEpoch)) {
+        st.aheadCount = 0;
+        return 0;
+    }
+    const size_t npix = (size_t)W * H;
+    const bool kept = st.aheadCount != 0 && st.aheadEpoch == st.sceneEpoch && st.aheadW == W && st.aheadH == H && st.aheadDepth == traceDepth &&
+                      st.aheadHdr == hdr && frameNo == st.aheadNext && frameNo < st.aheadFirst + st.aheadCount;
+    if (!kept) {
+        st.aheadCount = 0;
+        // a render that has come this far without a change is likely to go on (whoever moves the camera every few frames never
+        // gets here and pays nothing)
+        if (frameNo < 16u) return 0;
+        if (adaptive && lookahead_does_not_pay(st)) {
+            st.aheadOffEpoch = st.sceneEpoch;
+            return 0;
+        }
+        uint32_t batch = maxBatch;
+        while (batch >= 2u && (size_t)batch * npix * 3 * sizeof(float) > ((size_t)1 << 30)) batch >>= 1;
+        if (batch < 2u) return 0;
+        const size_t need = (size_t)batch * npix * 3 + (npix + 3) / 4;  // records, then one flag byte per pixel
+        if (st.aheadCapFloats < need) {
+            cudaFree(st.dAhead);
+            st.dAhead = nullptr;
+            st.aheadCapFloats = 0;
+            if (cudaMalloc(&st.dAhead, need * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                return 0;  // no memory for it: one sample per call as before
+            }
+            st.aheadCapFloats = need;
+        }
+        PtLaunch a;
+        memset(&a, 0, sizeof(a));
+        a.traceDepth = traceDepth;
+        a.firstSample = frameNo;
+        a.nSamples = batch;
+        a.y0 = 0;
+        a.y1 = 0xffffffffu;
+        a.perSample = st.dAhead;
+        a.constantPixel = (uint8_t*)(st.dAhead + (size_t)batch * npix * 3);
+        const bool timeIt = adaptive && st.aheadTimedEpoch != st.sceneEpoch && lookahead_events(st);
+        if (timeIt) SVR_TRY(cudaEventRecord(st.aheadEv[2], st.stream));
+        int rc = launch_pathtrace(a);
+        if (rc) return rc;
+        if (!a.perSample) return 0;  // another kernel shape serves this scene
+        if (timeIt) {
+            SVR_TRY(cudaEventRecord(st.aheadEv[3], st.stream));
+            st.aheadTimedEpoch = st.sceneEpoch;
+            st.aheadTimedBatch = batch;
+            st.aheadTimeFold = true;
+        }
+        st.aheadFirst = st.aheadNext = frameNo;
+        st.aheadCount = batch;
+        st.aheadEpoch = st.sceneEpoch;  // after the launch: refreshing the majorants moves the epoch
+        st.aheadW = W;
+        st.aheadH = H;
+        st.aheadDepth = traceDepth;
+        st.aheadHdr = hdr;
+        st.aheadBatches++;
+    }
+    PtLaunch c;
+    memset(&c, 0, sizeof(c));
+    c.traceDepth = traceDepth;
+    c.firstSample = frameNo;
+    c.nSamples = 1;
+    c.hdr = hdr;
+    c.img = img;
+    DevScene sc = st.scene;
+    sc.envEnabled = st.options[SVR_OPT_ENV_ENABLED];  // as launch_pathtrace sets it
+    const bool timeFold = st.aheadTimeFold && st.aheadTimedEpoch == st.sceneEpoch;
+    if (timeFold) SVR_TRY(cudaEventRecord(st.aheadEv[4], st.stream));
+    lookahead_consume_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st.stream>>>(sc, c, st.dAhead, (const uint8_t*)(st.dAhead + (size_t)st.aheadCount * npix * 3),
+                                                                                   st.aheadCount, frameNo - st.aheadFirst);
+    count_launch();
+    SVR_TRY(cudaGetLastError());
+    if (timeFold) {
+        SVR_TRY(cudaEventRecord(st.aheadEv[5], st.stream));
+        st.aheadTimeFold = false;
+    }
+    st.aheadNext = frameNo + 1u;
+    *done = true;
+    return 0;
+}
+
 extern "C" void render_pathtracer(svr_u8vec4* img, const svr_render_params* renderParams)
 {
-    PtLaunch a;
-    memset(&a, 0, sizeof(a));
-    a.traceDepth = renderParams->traceDepth;
-    a.firstSample = renderParams->frameNo;
-    a.nSamples = 1;
-    a.y0 = 0;
-    a.y1 = 0xffffffffu;
-    a.hdr = (float*)renderParams->hdrBuffer;
-    a.img = (uint32_t*)img;
-    int rc = launch_pathtrace(a);
+    bool done = false;
+    int rc = lookahead_frame((uint32_t*)img, (float*)renderParams->hdrBuffer, renderParams->traceDepth, renderParams->frameNo, &done);
+    if (!rc && !done) {
+        PtLaunch a;
+        memset(&a, 0, sizeof(a));
+        a.traceDepth = renderParams->traceDepth;
+        a.firstSample = renderParams->frameNo;
+        a.nSamples = 1;
+        a.y0 = 0;
+        a.y1 = 0xffffffffu;
+        a.hdr = (float*)renderParams->hdrBuffer;
+        a.img = (uint32_t*)img;
+        // look-ahead's yardstick: one steady-state single-sample launch per scene (classification cached, nothing to refresh)
+        HostState& st = state();
+        const bool timeIt = st.options[SVR_OPT_PT_LOOKAHEAD] > 1 && a.firstSample >= 8u && a.firstSample < 16u && st.aheadSingleEpoch != st.sceneEpoch &&
+                            st.pixelCacheEpoch == st.sceneEpoch && lookahead_events(st);
+        if (timeIt) cudaEventRecord(st.aheadEv[0], st.stream);
+        rc = launch_pathtrace(a);
+        if (timeIt && !rc) {
+            cudaEventRecord(st.aheadEv[1], st.stream);
+            st.aheadSingleEpoch = st.sceneEpoch;
+        }
+    }
     if (rc) {
         fprintf(stderr, "CUDA error at %s:%d code=%d \"%s\" \n", __FILE__, __LINE__, rc, svr_last_error());
         cudaDeviceReset();

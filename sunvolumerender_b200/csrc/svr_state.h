@@ -69,6 +69,20 @@ struct HostState {
     uint32_t pixelCacheW = 0, pixelCacheH = 0;
     int pixelCacheMode = -1;
 
+    // Sample look-ahead of the 1-sample-per-call protocol (SVR_OPT_PT_LOOKAHEAD, svr_pathtrace.cu): the radiance of the samples
+    // [aheadFirst, aheadFirst + aheadCount) of every pixel, computed in one sample-parallel launch; aheadNext is the frame the
+    // next call must ask for
+    float* dAhead = nullptr;
+    size_t aheadCapFloats = 0;
+    uint32_t aheadFirst = 0, aheadCount = 0, aheadNext = 0, aheadW = 0, aheadH = 0, aheadDepth = 0;
+    unsigned long long aheadEpoch = 0, aheadBatches = 0;
+    const void* aheadHdr = nullptr;
+    // does it pay for this scene?  timed once per scene epoch: a single-sample launch [0,1], the first batch [2,3], one fold [4,5]
+    cudaEvent_t aheadEv[6] = {};
+    bool aheadEvReady = false, aheadTimeFold = false;
+    unsigned long long aheadSingleEpoch = 0, aheadTimedEpoch = 0, aheadOffEpoch = 0;
+    uint32_t aheadTimedBatch = 0;
+
     Counters* dCounters = nullptr;
     unsigned long long launches = 0;
     std::string lastError;

@@ -33,6 +33,7 @@ def setup(r, cfg):
     r.set_option(L.OPT_PT_BLOCK_SPLIT, 0)
     r.set_option(L.OPT_PT_PIXEL_CACHE, 1)
     r.set_option(L.OPT_FUSED_UPLOAD, 1)
+    r.set_option(L.OPT_PT_LOOKAHEAD, 32)
     r.set_option(L.OPT_MACROCELL_SIZE, 8)
     r.set_option(L.OPT_COUNTERS, 0)
     r.set_option(L.OPT_SEED, 0x5EED)

@@ -716,3 +716,91 @@ def test_pixel_classification_cache_is_bit_exact_across_frames_and_scene_changes
     r.render_pathtracer_spp(6, 2)
     torch.cuda.synchronize()
     assert torch.allclose(r.hdr_image(), one_by_one, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("depth", [1, 3])
+def test_sample_lookahead_is_bit_exact_frame_for_frame(renderer, depth):
+    """SVR_OPT_PT_LOOKAHEAD: from frame 16 of an undisturbed progressive render, render_pathtracer computes the next 32
+    samples of every pixel in one sample-parallel launch and later calls only fold their frame's sample into the running mean.
+    hdrBuffer and image after EVERY call are those of one sample per call, bit for bit -- through camera moves and edits in the
+    middle of a kept batch, frame counters that jump or restart, another traceDepth, every estimator mode."""
+    cfg = small_config(n=64, w=150, h=101, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=depth)
+    vox = setup(renderer, cfg)
+    r = renderer
+
+    def script(ahead):
+        setup(r, cfg)
+        r.set_option(L.OPT_PT_LOOKAHEAD, ahead)
+        out = []
+
+        def frames(n, every=1):
+            for i in range(n):
+                r.render_pathtracer(depth)
+                if (i + 1) % every == 0 or i + 1 == n:
+                    torch.cuda.synchronize()
+                    out.append((r.hdr_image().clone(), r.ldr_image().clone()))
+
+        frames(70, every=7)                              # 16 singles, a batch of 32, 22 frames into the next one
+        r.set_camera(S.look_at_camera((60.0, 40.0, 110.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), image_w=cfg.width, image_h=cfg.height))
+        r.frame_no = 0                                   # what a host does after a camera move
+        frames(21, every=5)                              # 5 frames of a kept batch are used ...
+        r.set_transfer_function(S.tf_table("thin"))      # ... when the transfer function changes WITHOUT a restart of the counter
+        frames(30, every=6)
+        r.frame_no = 100                                 # a counter that jumps
+        frames(3)
+        r.upload_volume(np.ascontiguousarray(vox[::-1]))
+        frames(40, every=8)                              # upload_volume restarts the counter
+        for mode in (0, 1):
+            r.set_option(L.OPT_PT_MODE, mode)
+            r.frame_no = 0
+            frames(36, every=9)
+        r.set_option(L.OPT_PT_MODE, 2)
+        return out
+
+    batches0 = r.lib.svr_lookahead_batch_count()
+    ahead = script(-32)   # forced: what the timing-based switch would decide is not the subject here
+    batches = r.lib.svr_lookahead_batch_count() - batches0
+    plain = script(0)
+    assert r.lib.svr_lookahead_batch_count() - batches0 == batches   # none with the option off
+    assert batches == 8
+    r.set_option(L.OPT_PT_LOOKAHEAD, 32)
+    assert len(ahead) == len(plain)
+    for i, ((ha, la), (hb, lb)) in enumerate(zip(ahead, plain)):
+        assert float(ha.max()) > 0, i
+        assert torch.equal(ha, hb), i
+        assert torch.equal(la, lb), i
+
+
+def test_sample_lookahead_launch_pattern_and_fallbacks(renderer):
+    """80 undisturbed frames = 16 single launches and two batches of 32 with 32 folds each; counters on, a traceDepth that takes
+    the scatter-queue kernel, or the option at 0 leave one launch per call."""
+    cfg = small_config(n=48, w=96, h=64, gen=L.GEN_CT, fmt=L.VOXEL_U16, depth=2)
+    setup(renderer, cfg)
+    r = renderer
+
+    def launches(n, depth=2):
+        r.frame_no = 0
+        r.render_pathtracer(depth)   # the frame that refreshes the grid after a change
+        torch.cuda.synchronize()
+        l0, b0 = r.launch_count(), r.lib.svr_lookahead_batch_count()
+        for _ in range(n - 1):
+            r.render_pathtracer(depth)
+        torch.cuda.synchronize()
+        return r.launch_count() - l0, r.lib.svr_lookahead_batch_count() - b0
+
+    r.set_option(L.OPT_PT_LOOKAHEAD, -32)                # forced (a positive value lets the library's timing decide)
+    assert launches(80) == (15 + (1 + 32) + (1 + 32), 2)
+    r.set_option(L.OPT_PT_LOOKAHEAD, -8)
+    assert launches(32) == (15 + (1 + 8) + (1 + 8), 2)
+    r.set_option(L.OPT_PT_LOOKAHEAD, 0)
+    assert launches(40) == (39, 0)
+    r.set_option(L.OPT_PT_LOOKAHEAD, -32)
+    r.set_option(L.OPT_COUNTERS, 1)
+    assert launches(40) == (39, 0)
+    r.set_option(L.OPT_COUNTERS, 0)
+    assert launches(40, depth=8) == (39, 0)              # SVR_OPT_PT_QUEUE_MIN_DEPTH: the scatter-queue kernel's territory
+    assert launches(40)[1] == 1
+    r.set_option(L.OPT_PT_LOOKAHEAD, 32)                 # the default: batches as long as the library's own timing says they pay
+    l, b = launches(200)
+    # 15 single launches, then every call is a launch (a fold or, once batching is found not to pay, a single sample) plus one per batch
+    assert 1 <= b <= 6 and l == 199 + b
