@@ -144,10 +144,11 @@ enum svr_option {
      * for a quarter of the time: shorter blocks, a shorter end of the launch -- for short frames (one frame divided over
      * several GPUs).  The image differs from 0 only in the order of four float additions per pixel. */
     SVR_OPT_PT_BLOCK_SPLIT = 22,
-    /* 1 (default) = the lane-per-pixel kernel (render_pathtracer: one sample per call) keeps every pixel's classification --
-     * how far its camera rays can skip empty space, whether they can hit a light, whether the pixel is all sky -- across the
-     * frames of a progressive render and recomputes it only after something a pixel can see has changed (any setup_*, upload or
-     * option).  Images are bit-identical either way (only empty space is skipped); 0 = classify in every call. */
+    /* Every pixel's classification -- how far its camera rays can skip empty space, whether they can hit a light, whether the
+     * pixel is all sky -- is made for the whole image by a kernel of its own (one lane per pixel) and read by the render kernels
+     * (shapes 1-3).  1 (default) = it is kept across launches -- the frames of a progressive render, the batches of an
+     * accumulation -- and made again only after something a pixel can see has changed (any setup_*, upload or option);
+     * 0 = made again for every launch.  Images are bit-identical either way (only empty space is skipped). */
     SVR_OPT_PT_PIXEL_CACHE = 23,
     /* 1 (default) = svr_volume_upload from a DEVICE buffer into an array made by svr_volume_create, once the macrocell grid
      * exists for that array, runs as one kernel that stores the voxels into the array and reduces the grid's value ranges from

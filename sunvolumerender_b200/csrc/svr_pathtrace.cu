@@ -76,7 +76,7 @@ struct PtLaunch {
     int32_t lightCull;     // 1 = classify_pixel may rule out camera-ray light hits (SVR_OPT_PT_LIGHT_CULL)
     int32_t clipped;       // some clip plane is active: the volume's box is smaller than its texture
     uint32_t bandRows;               // (out) rows per band of the kernel shape chosen
-    int32_t pixelCache;              // shape 1: 0 classify, 1 classify (with the walk) and store into pixelInfo, 2 load from pixelInfo
+    int32_t pixelCache;              // shapes 1-3: 2 = pixelInfo holds the classification of every pixel (classify_pixels_kernel); others 0
     float2* pixelInfo;               // (tSkip, flags: bit 0 lights, bit 1 empty) per pixel
     int32_t blockSplit;              // shape 2: the warps of a block split the samples of one row's pixels (SVR_OPT_PT_BLOCK_SPLIT)
     uint32_t bandPhase, bandStride;  // this launch renders the row bands (block rows) phase, phase + stride, ... (1 GPU: 0, 1)
@@ -377,6 +377,31 @@ SVR_DEV PixelInfo classify_pixel(const DevScene& s, uint32_t idx, uint32_t idy, 
     }
     pi.tSkip = t;
     return pi;
+}
+
+// The classification of every pixel, made once per scene by a kernel of its own (classify_pixels_kernel: one lane per pixel,
+// 32 different pixels per warp) and read by the render kernels -- inside the sample-parallel kernel a warp classifies the two
+// pixels of its run with two lanes while thirty wait, 0.3 ms per C3 launch against 0.03 ms for the whole image here.
+SVR_DEV PixelInfo load_pixel_info(const float2* info, uint32_t offset)
+{
+    const float2 c = info[offset];
+    const uint32_t f = __float_as_uint(c.y);
+    PixelInfo pi;
+    pi.tSkip = c.x;
+    pi.lights = (f & 1u) != 0u;
+    pi.empty = (f & 2u) != 0u;
+    return pi;
+}
+
+__global__ void __launch_bounds__(128) classify_pixels_kernel(const __grid_constant__ DevScene s, float2* info, int haveGrid, int walk, int lightCull)
+{
+    // 8 x 4 pixels per warp, 16 x 8 per block: neighbouring centre rays walk the same macrocells
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t idx = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t idy = blockIdx.y * 8u + (warp >> 1) * 4u + (lane >> 3);
+    if (idx >= s.cam.imageW || idy >= s.cam.imageH) return;
+    const PixelInfo pi = classify_pixel(s, idx, idy, haveGrid != 0, walk != 0, lightCull != 0);
+    info[idy * s.cam.imageW + idx] = make_float2(pi.tSkip, __uint_as_float((pi.lights ? 1u : 0u) | (pi.empty ? 2u : 0u)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -774,17 +799,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MEGA_BLOCKS) pathtr
     if (inside) {
         const uint32_t offset = idy * s.cam.imageW + idx;
         PixelInfo pi;
-        if (a.pixelCache == 2) {
-            // a later frame of a progressive render: what was found out about this pixel in the first one
-            const float2 c = a.pixelInfo[offset];
-            const uint32_t f = __float_as_uint(c.y);
-            pi.tSkip = c.x;
-            pi.lights = (f & 1u) != 0u;
-            pi.empty = (f & 2u) != 0u;
-        } else {
-            pi = classify_pixel(s, idx, idy, MODE >= 2, a.entryCache != 0 || a.pixelCache == 1, a.lightCull != 0);
-            if (a.pixelCache == 1) a.pixelInfo[offset] = make_float2(pi.tSkip, __uint_as_float((pi.lights ? 1u : 0u) | (pi.empty ? 2u : 0u)));
-        }
+        pi = load_pixel_info(a.pixelInfo, offset);
         PathState<MODE> ps;
         pixel_begin<MODE>(ps);
         for (uint32_t n = 0; n < a.nSamples; ++n) trace_sample<MODE, COUNT>(s, a, ps, idx, idy, offset, a.firstSample + n, pi, lc);
@@ -816,25 +831,28 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     LocalCounters<COUNT> lc;
     if (idy < a.y1) {
         PathState<MODE> ps;
-        PixelInfo mine;  // the classification of pixel (run start + lane): the run's pixels are classified side by side, one per lane
+#ifdef SVR_VAR_PI_SHFL
+        PixelInfo mine;
         mine.tSkip = 0.f;
         mine.lights = mine.empty = false;
+#endif
         for (uint32_t i = 0; i < (uint32_t)a.warpPixels; ++i) {
             const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
+#ifdef SVR_VAR_PI_SHFL
             if ((i & 31u) == 0u) {
-                // classify_pixel is a serial walk along the pixel's centre ray: 32 lanes repeating it for one pixel cost what one
-                // lane costs, so every lane takes a pixel of its own (the walk of the longest one is what the warp pays, once)
                 const uint32_t px = idx + lane;
-                if (i + lane < (uint32_t)a.warpPixels && px < s.cam.imageW)
-                    mine = classify_pixel(s, px, idy, MODE >= 2, a.entryCache != 0, a.lightCull != 0);
+                if (i + lane < (uint32_t)a.warpPixels && px < s.cam.imageW) mine = load_pixel_info(a.pixelInfo, offset + lane);
                 __syncwarp();
             }
             PixelInfo pi;
             pi.tSkip = __shfl_sync(0xffffffffu, mine.tSkip, (int)(i & 31u));
             pi.lights = __shfl_sync(0xffffffffu, (int)mine.lights, (int)(i & 31u)) != 0;
             pi.empty = __shfl_sync(0xffffffffu, (int)mine.empty, (int)(i & 31u)) != 0;
+#else
+            const PixelInfo pi = load_pixel_info(a.pixelInfo, offset);  // classify_pixels_kernel, once per scene
+#endif
             pixel_begin<MODE>(ps);
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
                 // every sample of this pixel is the constant sky (see trace_sample): nSamples times the same value, written by one lane
@@ -1129,7 +1147,7 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_QUEUE_BLOCKS) patht
             const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
-            const PixelInfo pi = classify_pixel(s, idx, idy, true, a.entryCache != 0, a.lightCull != 0);
+            const PixelInfo pi = load_pixel_info(a.pixelInfo, offset);
             pixel_begin<MODE>(ps);
             ps.camLights = pi.lights;
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
@@ -2146,29 +2164,40 @@ int launch_pathtrace(PtLaunch& a)
         tileW = (uint32_t)a.warpPixels;
         tileH = (uint32_t)block / 32u;
     }
-    // the lane-per-pixel kernel keeps its per-pixel classification across the frames of a progressive render
+    // Per-pixel classification (shapes 1-3): made for the whole image by a kernel of its own and, with SVR_OPT_PT_PIXEL_CACHE, kept
+    // until something a pixel can see changes (sceneEpoch); without it, made again for every launch.  The render kernels only
+    // read it.  A kept classification includes the entry walk whenever the option allows one: its cost is paid once, so it also
+    // serves single-sample launches, for which a walk per launch does not pay (images are bit-identical either way: only empty
+    // space is skipped).
     a.pixelCache = 0;
     a.pixelInfo = nullptr;
-    bool storeCache = false;
-    if (shape == 1 && st.options[SVR_OPT_PT_PIXEL_CACHE] && a.y0 == 0 && a.y1 >= sc.cam.imageH && a.bandStride <= 1) {
+    if (shape >= 1 && shape <= 3) {
+        const bool keep = st.options[SVR_OPT_PT_PIXEL_CACHE] != 0;
+        const int walk = keep ? (st.options[SVR_OPT_PT_ENTRY_CACHE] != 0) : a.entryCache;
         const size_t npix = (size_t)sc.cam.imageW * sc.cam.imageH;
         if (st.pixelCacheCap < npix) {
             cudaFree(st.dPixelCache);
             st.dPixelCache = nullptr;
             st.pixelCacheCap = 0;
-            if (cudaMalloc(&st.dPixelCache, npix * sizeof(float2)) == cudaSuccess) st.pixelCacheCap = npix;
-            else cudaGetLastError();
+            SVR_TRY(cudaMalloc(&st.dPixelCache, npix * sizeof(float2)));
+            st.pixelCacheCap = npix;
             st.pixelCacheEpoch = 0;
         }
-        if (st.dPixelCache) {
-            const int key = sc.envNee ? 3 : mode;
-            const bool valid = st.pixelCacheEpoch == st.sceneEpoch && st.pixelCacheW == sc.cam.imageW && st.pixelCacheH == sc.cam.imageH &&
-                               st.pixelCacheMode == key;
-            a.pixelCache = valid ? 2 : 1;
-            a.pixelInfo = st.dPixelCache;
-            storeCache = !valid;
+        const int key = (sc.envNee ? 3 : mode) * 2 + walk;
+        const bool valid = keep && st.pixelCacheEpoch == st.sceneEpoch && st.pixelCacheW == sc.cam.imageW && st.pixelCacheH == sc.cam.imageH &&
+                           st.pixelCacheMode == key;
+        if (!valid) {
+            dim3 cg((sc.cam.imageW + 15u) / 16u, (sc.cam.imageH + 7u) / 8u);
+            classify_pixels_kernel<<<cg, 128, 0, st.stream>>>(sc, st.dPixelCache, mode >= 2 ? 1 : 0, walk, a.lightCull);
+            count_launch();
+            SVR_TRY(cudaGetLastError());
+            st.pixelCacheEpoch = keep ? st.sceneEpoch : 0;
+            st.pixelCacheW = sc.cam.imageW;
+            st.pixelCacheH = sc.cam.imageH;
             st.pixelCacheMode = key;
         }
+        a.pixelCache = 2;
+        a.pixelInfo = st.dPixelCache;
     }
     a.blockSplit = shape == 2 && st.options[SVR_OPT_PT_BLOCK_SPLIT] != 0 && a.nSamples >= 32u * ((uint32_t)block / 32u);
     if (a.blockSplit) tileH = 1u;
@@ -2186,11 +2215,6 @@ int launch_pathtrace(PtLaunch& a)
     }
     count_launch();
     SVR_TRY(cudaGetLastError());
-    if (storeCache) {
-        st.pixelCacheEpoch = st.sceneEpoch;
-        st.pixelCacheW = sc.cam.imageW;
-        st.pixelCacheH = sc.cam.imageH;
-    }
     return 0;
 }
 
