@@ -303,7 +303,7 @@ def strong_scaling_line(r, a, cfg, sum_buf, rank, world, dev, barrier):
             "scaling": "strong", "unit": UNIT, "spp_total": spp,
             "split_samples": {"value": npix * spp / (ms * 1e-3), "ms_per_step": ms, "spp_per_gpu": count, "ms_render_only": ms_render,
                               "ms_reduce_and_resolve_only": ms_reduce, "exchange": f"NCCL sum-reduce of {npix * 16 / 1e6:.1f} MB float4 accumulators",
-                              "limiter": "the per-pixel set-up (classification, accumulator pass) is paid by every GPU for every pixel: render time does not shrink like 1/N"}}
+                              "limiter": "the per-pixel accumulator pass is paid by every GPU for every pixel, and 32-sample launches leave a warp one round per pixel (it waits for its longest path): render time does not shrink like 1/N"}}
     try:
         pf = D.PeerFrame(r, npix * 16)
         gb = [0]
