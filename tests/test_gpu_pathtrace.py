@@ -804,3 +804,37 @@ def test_sample_lookahead_launch_pattern_and_fallbacks(renderer):
     l, b = launches(200)
     # 15 single launches, then every call is a launch (a fold or, once batching is found not to pay, a single sample) plus one per batch
     assert 1 <= b <= 6 and l == 199 + b
+
+
+def test_config_c3_protocol_and_streamed_upload_full_size(renderer):
+    """C3 at full size through the two paths round 2 added behind unchanged entry points: (a) 80 calls of render_pathtracer with
+    sample look-ahead (16 single launches, two batches of 32) against one sample per call -- hdrBuffer and image bit-equal;
+    (b) svr_volume_upload from a device buffer as one pass (array fill + macrocell ranges) against copy + range kernel -- same
+    image, bit for bit, from the re-uploaded voxels."""
+    cfg = S.CONFIGS["C3"]
+    vox = setup(renderer, cfg)
+    r = renderer
+    frames = {}
+    for ahead in (-32, 0):
+        r.set_option(L.OPT_PT_LOOKAHEAD, ahead)
+        r.frame_no = 0
+        for _ in range(80):
+            r.render_pathtracer(cfg.trace_depth)
+        torch.cuda.synchronize()
+        frames[ahead] = (r.hdr_image().clone(), r.ldr_image().clone())
+    r.set_option(L.OPT_PT_LOOKAHEAD, 32)
+    assert float(frames[0][0].max()) > 0
+    assert torch.equal(frames[-32][0], frames[0][0]) and torch.equal(frames[-32][1], frames[0][1])
+    imgs = {}
+    src = torch.from_numpy(np.ascontiguousarray(vox[::-1])).cuda().view(torch.uint8)   # other voxels than the bound ones
+    for fused in (1, 0):
+        r.set_option(L.OPT_FUSED_UPLOAD, fused)
+        f0 = r.lib.svr_fused_upload_count()
+        r.upload_volume(src)
+        assert r.lib.svr_fused_upload_count() - f0 == fused
+        r.render_pathtracer_spp(32, cfg.trace_depth)
+        torch.cuda.synchronize()
+        imgs[fused] = r.hdr_image().clone()
+    r.set_option(L.OPT_FUSED_UPLOAD, 1)
+    assert float(imgs[1].max()) > 0 and torch.equal(imgs[1], imgs[0])
+    assert not torch.equal(imgs[1], frames[0][0])
