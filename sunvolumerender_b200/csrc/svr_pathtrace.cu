@@ -831,28 +831,11 @@ __global__ void __launch_bounds__(SVR_PT_MAX_THREADS, SVR_PT_MIN_BLOCKS) pathtra
     LocalCounters<COUNT> lc;
     if (idy < a.y1) {
         PathState<MODE> ps;
-#ifdef SVR_VAR_PI_SHFL
-        PixelInfo mine;
-        mine.tSkip = 0.f;
-        mine.lights = mine.empty = false;
-#endif
         for (uint32_t i = 0; i < (uint32_t)a.warpPixels; ++i) {
             const uint32_t idx = blockIdx.x * (uint32_t)a.warpPixels + i;
             if (idx >= s.cam.imageW) break;
             const uint32_t offset = idy * s.cam.imageW + idx;
-#ifdef SVR_VAR_PI_SHFL
-            if ((i & 31u) == 0u) {
-                const uint32_t px = idx + lane;
-                if (i + lane < (uint32_t)a.warpPixels && px < s.cam.imageW) mine = load_pixel_info(a.pixelInfo, offset + lane);
-                __syncwarp();
-            }
-            PixelInfo pi;
-            pi.tSkip = __shfl_sync(0xffffffffu, mine.tSkip, (int)(i & 31u));
-            pi.lights = __shfl_sync(0xffffffffu, (int)mine.lights, (int)(i & 31u)) != 0;
-            pi.empty = __shfl_sync(0xffffffffu, (int)mine.empty, (int)(i & 31u)) != 0;
-#else
             const PixelInfo pi = load_pixel_info(a.pixelInfo, offset);  // classify_pixels_kernel, once per scene
-#endif
             pixel_begin<MODE>(ps);
             if (pi.empty && !pi.lights && (!s.envEnabled || s.env.tex == 0)) {
                 // every sample of this pixel is the constant sky (see trace_sample): nSamples times the same value, written by one lane
@@ -2440,6 +2423,7 @@ extern "C" int svr_pathtracer_resolve(svr_u8vec4* img, svr_vec3* hdrOut, const s
     if (!sum) return fail_msg("svr_pathtracer_resolve: sum is null");
     uint32_t npix = st.scene.cam.imageW * st.scene.cam.imageH;
     if (!npix) return fail_msg("svr_pathtracer_resolve: setup_camera not called");
+    if (hdrOut && (const void*)hdrOut == st.aheadHdr) st.aheadCount = 0;  // the running mean render_pathtracer's kept samples follow is overwritten
     resolve_kernel<<<(npix + 255u) / 256u, 256, 0, st.stream>>>((const float4*)sum, (float*)hdrOut, (uint32_t*)img, npix,
                                                                st.scene.cam.exposure);
     count_launch();
