@@ -176,6 +176,16 @@ extern "C" int svr_set_device(int device)
     st.dAhead = nullptr;
     st.aheadCapFloats = 0;
     st.aheadCount = 0;
+    if (st.aheadEvReady)
+        for (int i = 0; i < 6; ++i) cudaEventDestroy(st.aheadEv[i]);  // events belong to the device they were created on
+    st.aheadEvReady = false;
+    st.aheadSingleEpoch = st.aheadTimedEpoch = st.aheadOffEpoch = 0;
+    cudaFreeHost(st.hMailbox);
+    st.hMailbox = st.dMailbox = nullptr;
+    if (st.uploadSurf) cudaDestroySurfaceObject(st.uploadSurf);
+    st.uploadSurf = 0;
+    st.uploadSurfArray = nullptr;
+    cudaGetLastError();
     st.sceneEpoch++;
     cudaFree(st.dEnvMarg);
     cudaFree(st.dEnvCond);
