@@ -1,5 +1,5 @@
 """Short, fixed workload for ncu:
-    python tools/prof_run.py <pt|rc|ref> <config> [mode] [spp] [reps] [shape] [view]
+    python tools/prof_run.py <pt|proto|rc|ref> <config> [mode] [spp] [reps] [shape] [view]
 Sets up one BASELINE.json configuration and launches the chosen kernel a few times.  `ref` runs the
 reference's own kernels (oracle/_ref) on the same scene, for side-by-side profiles.  view = close
 moves the camera in so that the volume fills the frame."""
@@ -26,6 +26,9 @@ if view == "close":
     r.set_camera(S.make_camera((0, 0, cam.pos.z * 0.45), (1, 0, 0), (0, 1, 0), (0, 0, 1), 45.0, 0.0, 1.0, 1.0, cfg.width, cfg.height))
 r.set_option(L.OPT_PT_MODE, mode)
 r.set_option(L.OPT_PT_KERNEL, shape)
+import os  # noqa: E402
+if os.environ.get("SVR_LOOKAHEAD"):  # e.g. -32: batches forced (under ncu the per-launch overhead makes the library's own timing switch them off)
+    r.set_option(L.OPT_PT_LOOKAHEAD, int(os.environ["SVR_LOOKAHEAD"]))
 if what == "ref":
     from oracle import binding as B  # noqa: E402  (profiling aid, not a product path)
 
@@ -36,7 +39,11 @@ if what == "ref":
         ref.render_pathtracer(spp, cfg.trace_depth)
 else:
     for _ in range(reps):
-        if what == "pt":
+        if what == "proto":   # the drop-in protocol: spp calls of one sample each (sample look-ahead from frame 16)
+            r.frame_no = 0
+            for _ in range(spp):
+                r.render_pathtracer(cfg.trace_depth)
+        elif what == "pt":
             r.frame_no = 0
             r.render_pathtracer_spp(spp, cfg.trace_depth)
         else:
