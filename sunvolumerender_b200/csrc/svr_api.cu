@@ -180,6 +180,9 @@ extern "C" int svr_set_device(int device)
         for (int i = 0; i < 6; ++i) cudaEventDestroy(st.aheadEv[i]);  // events belong to the device they were created on
     st.aheadEvReady = false;
     st.aheadSingleEpoch = st.aheadTimedEpoch = st.aheadOffEpoch = 0;
+    if (st.tfCheckEvent) cudaEventDestroy(st.tfCheckEvent);
+    st.tfCheckEvent = nullptr;
+    st.tfCheckPending = false;
     cudaFreeHost(st.hMailbox);
     st.hMailbox = st.dMailbox = nullptr;
     if (st.uploadSurf) cudaDestroySurfaceObject(st.uploadSurf);

@@ -542,10 +542,10 @@ int ensure_mailbox(HostState& st)
     return 0;
 }
 
-// host <- device, at most 64 bytes, synchronous with respect to the library's stream
+// host <- device, at most 32 bytes, synchronous with respect to the library's stream
 int read_small(HostState& st, void* host, const void* dev, size_t bytes)
 {
-    if (bytes > 64 || (bytes & 3)) return fail_msg("read_small: at most 64 bytes, a multiple of 4");
+    if (bytes > 32 || (bytes & 3)) return fail_msg("read_small: at most 32 bytes, a multiple of 4");  // bytes 32..63 of the mailbox: tf_check_launch
     if (int rc = ensure_mailbox(st)) return rc;
     mailbox_kernel<<<1, 32, 0, st.stream>>>((const unsigned int*)dev, (unsigned int*)st.dMailbox, (int)(bytes / 4));
     count_launch();
@@ -568,7 +568,7 @@ int launch_fingerprint(HostState& st, int slot)
 // 64-bit hash of a transfer-function table: of the linear copy the majorants are built from (tex == 0), or of the live
 // array read through its texture object at the texel centres (where the linear filter returns the texel itself)
 __global__ void tf_hash_kernel(const float4* table, cudaTextureObject_t tex, int n, unsigned long long* out, const unsigned long long* ref,
-                               unsigned long long* mailbox)
+                               unsigned long long* mailbox, unsigned int* staleFlag)
 {
     unsigned long long h = 0ull;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -579,16 +579,19 @@ __global__ void tf_hash_kernel(const float4* table, cudaTextureObject_t tex, int
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-    // one block: the sum is written, not accumulated (no zeroing launch), and when the caller wants to compare it with the
-    // stored hash both go to the host mailbox from here (the ray caster does this on every call: one launch, not three)
+    // one block: the sum is written, not accumulated (no zeroing launch).  The ray caster's per-call check (ref != null): the
+    // verdict goes to a device word the ray-cast kernel of the same frame reads (stale majorants -> it does not skip), and
+    // both hashes to the host mailbox, which the NEXT call looks at -- no host synchronisation per frame.
     __shared__ unsigned long long part[32];
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (unsigned w = 1; w < (blockDim.x + 31u) / 32u; ++w) h += part[w];
         *out = h;
-        if (mailbox) {
-            mailbox[0] = *ref;
+        if (ref) {
+            const unsigned long long r = *ref;
+            *staleFlag = r != h ? 1u : 0u;
+            mailbox[0] = r;
             mailbox[1] = h;
             __threadfence_system();
         }
@@ -801,8 +804,8 @@ static int build_grid(DevScene* scene, bool force, int cell, bool* majorantsRebu
         SVR_TRY(cudaMemcpy2DFromArrayAsync(st.dTfTable, (size_t)n * sizeof(float4), tarr, 0, 0, (size_t)n * sizeof(float4), 1,
                                            cudaMemcpyDeviceToDevice, st.stream));
         tf_sparse_kernel<<<1, 1024, 0, st.stream>>>(st.dTfTable, n, levels, st.dTfSparse);
-        if (!st.dTfHash) SVR_TRY(cudaMalloc(&st.dTfHash, 2 * sizeof(unsigned long long)));
-        tf_hash_kernel<<<1, 256, 0, st.stream>>>(st.dTfTable, 0, n, st.dTfHash, nullptr, nullptr);  // of the table these majorants come from
+        if (!st.dTfHash) SVR_TRY(cudaMalloc(&st.dTfHash, 4 * sizeof(unsigned long long)));  // [0] built-from, [1] live, [2] stale flag (32 bit)
+        tf_hash_kernel<<<1, 256, 0, st.stream>>>(st.dTfTable, 0, n, st.dTfHash, nullptr, nullptr, nullptr);  // of the table these majorants come from
         const int px = st.gridDims.x + 2, py = st.gridDims.y + 2, pz = st.gridDims.z + 2;
         const size_t padded = (size_t)px * py * pz;
         if (int rc = zero_words(st, st.dMajorant, padded * sizeof(float))) return rc;
@@ -874,22 +877,42 @@ static int auto_cell(HostState& st, int current, int* want)
     return 0;
 }
 
-int tf_content_changed(const svr_transfer_function& tf, bool* changed)
+// The ray caster's per-call check that the transfer-function table behind an unchanged handle still is the one the
+// majorants were built from, without a host synchronisation per frame: a call first collects the verdict of the PREVIOUS
+// call's hash (its event has long completed; tf_check_collect), rebuilds if that table had changed, and then launches
+// this frame's hash (tf_check_launch), whose verdict the ray-cast kernel of this very frame reads from device memory: with
+// stale majorants it does not skip (skipping is exact, so the image is the same, only slower, for that one frame).
+int tf_check_collect(bool* changed)
 {
     HostState& st = state();
-    *changed = true;
+    *changed = false;
+    if (!st.tfCheckPending) return 0;
+    st.tfCheckPending = false;
+    SVR_TRY(cudaEventSynchronize(st.tfCheckEvent));
+    unsigned long long h[2];
+    memcpy(h, (const char*)st.hMailbox + 32, sizeof(h));
+    *changed = h[0] != h[1];
+    return 0;
+}
+
+// *staleFlag: device word for the ray-cast kernel (null when nothing could be checked: the grid was just rebuilt from this table)
+int tf_check_launch(const svr_transfer_function& tf, const unsigned int** staleFlag)
+{
+    HostState& st = state();
+    *staleFlag = nullptr;
     if (!tf.tex || !st.majorantValid || !st.dTfHash || !st.tfEntries) return 0;
     cudaResourceDesc trd;
     SVR_TRY(cudaGetTextureObjectResourceDesc(&trd, tf.tex));
     if (trd.resType != cudaResourceTypeArray || trd.res.array.array != st.majorantTfArray) return 0;
     if (int rc = ensure_mailbox(st)) return rc;
-    tf_hash_kernel<<<1, 256, 0, st.stream>>>(nullptr, tf.tex, st.tfEntries, st.dTfHash + 1, st.dTfHash, (unsigned long long*)st.dMailbox);
+    if (!st.tfCheckEvent) SVR_TRY(cudaEventCreateWithFlags(&st.tfCheckEvent, cudaEventDisableTiming));
+    unsigned int* flag = (unsigned int*)(st.dTfHash + 2);
+    tf_hash_kernel<<<1, 256, 0, st.stream>>>(nullptr, tf.tex, st.tfEntries, st.dTfHash + 1, st.dTfHash, (unsigned long long*)((char*)st.dMailbox + 32), flag);
     count_launch();
     SVR_TRY(cudaGetLastError());
-    SVR_TRY(cudaStreamSynchronize(st.stream));
-    unsigned long long h[2];
-    memcpy(h, st.hMailbox, sizeof(h));
-    *changed = h[0] != h[1];
+    SVR_TRY(cudaEventRecord(st.tfCheckEvent, st.stream));
+    st.tfCheckPending = true;
+    *staleFlag = flag;
     return 0;
 }
 

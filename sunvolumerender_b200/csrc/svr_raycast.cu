@@ -21,7 +21,7 @@ namespace {
 template <bool SKIP, bool COUNT>
 __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ DevScene s, float stepSize, uint32_t* __restrict__ img,
                                                       float4* __restrict__ outf, uint32_t y0, uint32_t y1, uint32_t bandPhase,
-                                                      uint32_t bandStride, Counters* cnt)
+                                                      uint32_t bandStride, Counters* cnt, const unsigned int* __restrict__ staleGrid)
 {
     // warp = 8x4 pixel tile; block = 16 pixels wide, 2 warps across.  Row bands of the block's height are dealt out
     // round robin: this launch renders bands bandPhase, bandPhase + bandStride, ... (1 GPU: phase 0, stride 1)
@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ De
     const bool inside = idx < s.cam.imageW && idy < y1;
     LocalCounters<COUNT> lc;
 
+    // the majorants may describe an older table than the one bound now (render_raycasting's per-call check): then no skipping
+    const bool useGrid = SKIP && (staleGrid == nullptr || *staleGrid == 0u);
     float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
     if (inside) {
         Ray ray = camera_ray_center(s.cam, idx, idy);
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ De
             while (t <= tFar) {
                 float3 p = ray.orig + t * ray.dir;
                 float3 tc = tex_coord(s.vol, p);
-                if (SKIP) {
+                if (SKIP && useGrid) {
                     float3 g = tc * s.grid.scale;
                     int cx = min(max((int)floorf(g.x), 0), s.grid.gx - 1);
                     int cy = min(max((int)floorf(g.y), 0), s.grid.gy - 1);
@@ -130,20 +132,27 @@ int launch_raycast(uint32_t* img, float4* outf, const svr_volume* volume, const 
     sc.cam = *camera;
     const bool skip = st.options[SVR_OPT_RC_SKIP] != 0;
     const bool count = st.options[SVR_OPT_COUNTERS] != 0;
+    const unsigned int* staleGrid = nullptr;
     if (skip) {
         // Empty-space skipping needs majorants of the CURRENT table.  Edits that go through setup_transferfunction /
         // svr_tf_upload, and any change of handle, invalidate them (svr_macrocell.cu).  The reference's own host can also
         // put new contents behind an unchanged handle without telling anybody (gui/transferfunction.cpp:128-151 destroys and
         // re-creates the texture; render_raycasting gets the struct by reference): the drop-in entry point therefore
         // compares a hash of the live table with the hash of the table the majorants came from -- one small launch instead
-        // of the six-launch rebuild it used to force on every frame -- and rebuilds only on a difference.
+        // of the six-launch rebuild it used to force on every frame, and no host synchronisation: the verdict reaches this
+        // frame's kernel through device memory (stale majorants: it renders without skipping) and the host at the next
+        // call, which then rebuilds.
         bool changed = false;
         if (checkTfContent) {
-            int rc = tf_content_changed(sc.tf, &changed);
+            int rc = tf_check_collect(&changed);  // what the previous call's hash found
             if (rc) return rc;
         }
         int rc = ensure_grid(&sc, /*force=*/changed, /*maxAutoCell=*/8);
         if (rc) return rc;
+        if (checkTfContent) {
+            rc = tf_check_launch(sc.tf, &staleGrid);  // this frame's table against the one the majorants came from
+            if (rc) return rc;
+        }
     } else {
         memset(&sc.grid, 0, sizeof(sc.grid));
     }
@@ -158,11 +167,11 @@ int launch_raycast(uint32_t* img, float4* outf, const svr_volume* volume, const 
     if (bandPhase >= bands) return 0;
     dim3 grid((camera->imageW + 15u) / 16u, (bands - bandPhase + bandStride - 1u) / bandStride);
     if (skip) {
-        if (count) raycast_kernel<true, true><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt);
-        else raycast_kernel<true, false><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt);
+        if (count) raycast_kernel<true, true><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt, staleGrid);
+        else raycast_kernel<true, false><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt, staleGrid);
     } else {
-        if (count) raycast_kernel<false, true><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt);
-        else raycast_kernel<false, false><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt);
+        if (count) raycast_kernel<false, true><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt, staleGrid);
+        else raycast_kernel<false, false><<<grid, block, 0, st.stream>>>(sc, stepSize, img, outf, y0, y1, bandPhase, bandStride, cnt, staleGrid);
     }
     count_launch();
     SVR_TRY(cudaGetLastError());

@@ -46,7 +46,9 @@ struct HostState {
     bool majorantValid = false;           // false after setup_volume/setup_transferfunction
     float majorantDensityScale = 0.f;
     cudaArray_t majorantTfArray = nullptr;
-    unsigned long long* dTfHash = nullptr;  // [0] hash of the TF table the majorants were built from, [1] scratch
+    unsigned long long* dTfHash = nullptr;  // [0] hash of the TF table the majorants were built from, [1] of the live table, [2] stale flag
+    cudaEvent_t tfCheckEvent = nullptr;     // behind the ray caster's per-call hash of the live table (svr_macrocell.cu: tf_check_*)
+    bool tfCheckPending = false;
 
     // automatic macrocell size (SVR_OPT_MACROCELL_SIZE = 0): the choice and the scene it was made for
     int autoCell = 0;
@@ -126,7 +128,8 @@ int ensure_grid(DevScene* scene, bool force, int maxAutoCell = 32);
 // true when the transfer-function table behind `tf` differs from the one the majorants were built from (one small
 // launch + an 16-byte read-back; the ray caster's drop-in entry point, whose host may edit the table behind an unchanged
 // handle, gui/transferfunction.cpp:128-151).  Also true when no majorants exist yet.
-int tf_content_changed(const svr_transfer_function& tf, bool* changed);
+int tf_check_collect(bool* changed);
+int tf_check_launch(const svr_transfer_function& tf, const unsigned int** staleFlag);
 int upload_with_ranges(cudaArray_t arr, const cudaChannelFormatDesc& ch, const cudaExtent& ext, unsigned int flags, const void* devData, bool* done);
 
 // Builds / refreshes the environment light's importance sampler for scene->env and fills scene->envS.

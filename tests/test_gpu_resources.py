@@ -407,7 +407,8 @@ def test_reference_arm_scene_builder_makes_the_same_scene_without_the_product_li
 def test_raycaster_notices_a_table_edited_behind_an_unchanged_handle(renderer):
     """The reference's host re-creates the transfer-function texture on every edit (gui/transferfunction.cpp:128-151) and
     hands render_raycasting the struct by reference: new contents can sit behind the handle the majorants were built for.
-    The drop-in entry point compares the table's hash on every call (one small launch) and rebuilds on a difference."""
+    The drop-in entry point compares the table's hash on every call (one small launch, no host synchronisation: a frame whose
+    table differs renders without empty-space skipping, the next call rebuilds)."""
     rt = _cudart()
     rt.cudaMemcpy2DToArray.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
     cfg = small_config(n=64, w=96, h=96, gen=L.GEN_CT, fmt=L.VOXEL_U16, tf="default")
@@ -432,6 +433,16 @@ def test_raycaster_notices_a_table_edited_behind_an_unchanged_handle(renderer):
     torch.cuda.synchronize()
     edited = r.ldr_image().clone()
     assert not torch.equal(edited, before)
+    # that call found out on the device (its kernel did not skip); the next one rebuilds the majorants, the one after is back to
+    # hash + ray cast -- and all three render the same image
+    launches0 = r.launch_count()
+    r.render_raycasting()
+    torch.cuda.synchronize()
+    assert r.launch_count() - launches0 > 2 and torch.equal(r.ldr_image(), edited)
+    launches0 = r.launch_count()
+    r.render_raycasting()
+    torch.cuda.synchronize()
+    assert r.launch_count() - launches0 == 2 and torch.equal(r.ldr_image(), edited)
     # ground truth: the same table through the announced path, and without empty-space skipping at all
     r.set_transfer_function(table)
     r.render_raycasting()
