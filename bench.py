@@ -320,10 +320,10 @@ def strong_scaling_line(r, a, cfg, sum_buf, rank, world, dev, barrier):
         ms_b = timed_steps(step_bands, a.steps, max(a.warmup, 3), barrier, dev)
         # With few pixels per GPU the frame ends when the last block does: shorter blocks shorten that tail -- runs of 1 pixel
         # per warp, and / or the warps of a block splitting the samples of one row's pixels (SVR_OPT_PT_BLOCK_SPLIT).
-        wp0 = r.get_option(L.OPT_PT_WARP_PIXELS)
+        wp0 = r.get_option(L.OPT_PT_WARP_PIXELS)   # 0 = the library's choice by launch length
         best_cfg = (wp0, 0)
         if world >= 4:
-            for cand in ((1, 0), (wp0, 1), (1, 1)):
+            for cand in dict.fromkeys(c for c in ((1, 0), (2, 0), (wp0, 1), (1, 1)) if c != (wp0, 0)):
                 r.set_option(L.OPT_PT_WARP_PIXELS, cand[0])
                 r.set_option(L.OPT_PT_BLOCK_SPLIT, cand[1])
                 ms_c = timed_steps(step_bands, a.steps, 2, barrier, dev)

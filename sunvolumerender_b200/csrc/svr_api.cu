@@ -31,7 +31,12 @@ HostState& state()
         p->options[SVR_OPT_PT_KERNEL] = 2;
         p->options[SVR_OPT_LEAP] = 1;
         p->options[SVR_OPT_PT_ENTRY_CACHE] = 1;
-        p->options[SVR_OPT_PT_WARP_PIXELS] = 2;  // 4 rows x 2 pixels per block: 8.22 ms on C3 against 8.47 with 4 pixels, 8.81 with 1 (round 2)
+        // 0 = chosen per launch (launch_pathtrace): one pixel per warp for launches of 128 samples or more, two below.  While a
+        // warp classified its run's pixels itself, runs of 2 were best at every length (8.22 ms on C3 against 8.81 with 1, 8.47
+        // with 4); with the classification made once per scene by a kernel of its own the shortest run balances long launches
+        // best -- C3 at 256 spp: 7.48 / 7.60 / 7.98 ms for runs of 1 / 2 / 4 pixels, at 128 spp 3.89 / 3.92 / 4.11 -- while short
+        // launches still want fewer, longer blocks: 64 spp 2.12 / 2.08 / 2.14, 32 spp 1.24 / 1.15 / 1.17 (tools/gpu_run_length.py)
+        p->options[SVR_OPT_PT_WARP_PIXELS] = 0;
         p->options[SVR_OPT_PT_WARP_MIN_SPP] = 32;
         p->options[SVR_OPT_PT_QUEUE_MIN_DEPTH] = 8;
         p->options[SVR_OPT_SETUP_SYNC] = 1;
@@ -233,7 +238,7 @@ extern "C" int svr_set_option(int key, int value)
             if (value < 0 || value > 5) return fail_msg("SVR_OPT_PT_KERNEL must be 0 .. 5");
             break;
         case SVR_OPT_PT_WARP_PIXELS:
-            if (value < 1 || value > 64) return fail_msg("SVR_OPT_PT_WARP_PIXELS must be in 1..64");
+            if (value < 0 || value > 64) return fail_msg("SVR_OPT_PT_WARP_PIXELS must be in 0..64");
             break;
         case SVR_OPT_PT_WARP_MIN_SPP:
             if (value < 1) return fail_msg("SVR_OPT_PT_WARP_MIN_SPP must be >= 1");

@@ -2141,6 +2141,7 @@ int launch_pathtrace(PtLaunch& a)
     if (shape == 4) a.marchBurst = st.options[SVR_OPT_PT_REFILL] > 0 ? st.options[SVR_OPT_PT_REFILL] : 8;
     if (shape == 5) a.marchBurst = st.options[SVR_OPT_PT_REFILL] > 0 ? st.options[SVR_OPT_PT_REFILL] : 8;
     a.warpPixels = st.options[SVR_OPT_PT_WARP_PIXELS];
+    if (a.warpPixels <= 0) a.warpPixels = a.nSamples >= 128u ? 1 : 2;  // automatic: see the option's default (svr_api.cu)
     if (shape == 5) a.warpPixels = st.options[SVR_OPT_PT_POOL_PIXELS] > 0 ? st.options[SVR_OPT_PT_POOL_PIXELS] : 16;
     uint32_t tileW = 16u, tileH = (uint32_t)block / 16u;
     if (shape >= 2) {

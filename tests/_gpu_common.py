@@ -18,7 +18,7 @@ def setup(r, cfg):
     """Loads cfg into the renderer; returns the voxels as a host numpy array (z, y, x)."""
     r.set_option(L.OPT_PT_MODE, 2)
     r.set_option(L.OPT_PT_KERNEL, 2)
-    r.set_option(L.OPT_PT_WARP_PIXELS, 2)
+    r.set_option(L.OPT_PT_WARP_PIXELS, 0)
     r.set_option(L.OPT_PT_WARP_MIN_SPP, 32)
     r.set_option(L.OPT_PT_QUEUE_MIN_DEPTH, 8)
     r.set_option(L.OPT_SHADOW_ESTIMATOR, 0)

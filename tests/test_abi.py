@@ -94,5 +94,5 @@ def test_option_enum_and_binding_agree():
     # defaults a drop-in host gets without calling svr_set_option
     lib = L.load()
     for name, default in (("OPT_PT_PROFILE", 0), ("OPT_PT_LIGHT_CULL", 1), ("OPT_ENV_NEE", 0), ("OPT_PT_BLOCK_SPLIT", 0), ("OPT_PT_PIXEL_CACHE", 1), ("OPT_FUSED_UPLOAD", 1), ("OPT_PT_LOOKAHEAD", 32),
-                          ("OPT_PT_WARP_PIXELS", 2), ("OPT_ENV_ENABLED", 0), ("OPT_SHADOW_ESTIMATOR", 0)):
+                          ("OPT_PT_WARP_PIXELS", 0), ("OPT_ENV_ENABLED", 0), ("OPT_SHADOW_ESTIMATOR", 0)):
         assert lib.svr_get_option(getattr(L, name)) == default, name

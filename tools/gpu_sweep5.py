@@ -13,7 +13,7 @@ r = Renderer(0)
 def run(cfg, t, spp, reps=4):
     buf = torch.zeros(cfg.width * cfg.height * 4, dtype=torch.float32, device="cuda")
     for o in optsets:
-        defaults = {"profile": 0, "refill": 0, "kernel": 2, "cell": 0, "wp": 2, "qdepth": 8, "block": 128, "shadow": 0, "split": 0}
+        defaults = {"profile": 0, "refill": 0, "kernel": 2, "cell": 0, "wp": 0, "qdepth": 8, "block": 128, "shadow": 0, "split": 0}
         for kv in o.split(","):
             if kv:
                 k, v = kv.split("="); defaults[k] = int(v)
