@@ -102,10 +102,10 @@ enum svr_option {
      * samples can be advanced through empty macrocells; 0 = every sample walks from the volume face.
      * Images are bit-identical either way (only empty cells are skipped). */
     SVR_OPT_PT_ENTRY_CACHE = 12,
-    /* sample-parallel kernel (SVR_OPT_PT_KERNEL = 2): pixels a warp renders one after the other (1..64; 0, the default: 1 for launches of at
-     * least 128 samples, 2 below),
-     * and the smallest batch (samples per pixel per launch) it is used for; smaller batches run the
-     * megakernel.  Images differ from the other shapes only in float summation order. */
+    /* sample-parallel kernel (SVR_OPT_PT_KERNEL = 2): pixels a warp renders one after the other (1..64; 0, the
+     * default, lets the library choose by launch length: 1 from 128 samples per launch on, 2 below), and the
+     * smallest batch (samples per pixel per launch) the kernel is used for; smaller batches run the megakernel.
+     * Images differ from the other shapes only in float summation order. */
     SVR_OPT_PT_WARP_PIXELS = 13,
     SVR_OPT_PT_WARP_MIN_SPP = 14,
     /* SVR_OPT_PT_KERNEL = 2 with local majorants (SVR_OPT_PT_MODE = 2): from this traceDepth on the
